@@ -1,0 +1,197 @@
+"""ctypes/numpy front-end of the CPU oracle (oracle/gut_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class Camera(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("principal", C.c_float * 2), ("focal", C.c_float * 2),
+        ("radial", C.c_float * 6), ("tangential", C.c_float * 2), ("thin_prism", C.c_float * 4),
+        ("pose_start", C.c_float * 7), ("pose_end", C.c_float * 7),
+    ]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("kernel_degree", C.c_int32), ("min_kernel_density", C.c_float), ("min_alpha", C.c_float),
+        ("max_alpha", C.c_float), ("min_transmittance", C.c_float),
+        ("ut_alpha", C.c_float), ("ut_beta", C.c_float), ("ut_kappa", C.c_float), ("ut_delta", C.c_float),
+        ("ut_margin", C.c_float),
+        ("rect_bounding", C.c_int32), ("tight_opacity_bounding", C.c_int32), ("tile_culling", C.c_int32),
+        ("global_z_order", C.c_int32),
+    ]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libgut_oracle.so")
+    src = os.path.join(_HERE, "gut_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "libgut_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.gut_oracle_bin.restype = C.c_int64
+        _LIB.gut_oracle_higher_msb.restype = C.c_uint32
+        _LIB.gut_oracle_hit_forward.restype = C.c_int
+    return _LIB
+
+
+def default_config() -> Config:
+    cfg = Config()
+    lib().gut_oracle_default_config(C.byref(cfg))
+    return cfg
+
+
+def make_camera(width, height, fx, fy, cx, cy, pose_start, pose_end=None) -> Camera:
+    cam = Camera()
+    cam.width, cam.height = int(width), int(height)
+    cam.principal[:] = [cx, cy]
+    cam.focal[:] = [fx, fy]
+    cam.pose_start[:] = [float(v) for v in pose_start]
+    cam.pose_end[:] = [float(v) for v in (pose_end if pose_end is not None else pose_start)]
+    return cam
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+@dataclass
+class Projection:
+    tiles_count: np.ndarray
+    proj_pos: np.ndarray
+    conic_opacity: np.ndarray
+    extent: np.ndarray
+    depth: np.ndarray
+    rgb: np.ndarray
+    visibility: np.ndarray
+
+
+@dataclass
+class Binning:
+    unsorted_keys: np.ndarray
+    unsorted_values: np.ndarray
+    sorted_keys: np.ndarray
+    sorted_values: np.ndarray
+    ranges: np.ndarray
+
+
+def sensor_matrices(cam: Camera):
+    view = np.zeros(12, np.float32)
+    inv = np.zeros(12, np.float32)
+    pos = np.zeros(3, np.float32)
+    lib().gut_oracle_sensor_matrices(C.byref(cam), _p(view, C.c_float), _p(inv, C.c_float), _p(pos, C.c_float))
+    return view.reshape(4, 3), inv.reshape(4, 3), pos
+
+
+def project(cfg, cam, particles, sph, sph_degree) -> Projection:
+    particles, sph = _f32(particles), _f32(sph)
+    n = particles.shape[0]
+    out = Projection(np.zeros(n, np.uint32), np.zeros((n, 2), np.float32), np.zeros((n, 4), np.float32),
+                     np.zeros((n, 2), np.float32), np.zeros(n, np.float32), np.zeros((n, 3), np.float32),
+                     np.zeros(n, np.int32))
+    lib().gut_oracle_project(C.byref(cfg), C.byref(cam), C.c_int64(n), _p(particles, C.c_float), _p(sph, C.c_float),
+                             C.c_int32(sph_degree), _p(out.tiles_count, C.c_uint32), _p(out.proj_pos, C.c_float),
+                             _p(out.conic_opacity, C.c_float), _p(out.extent, C.c_float), _p(out.depth, C.c_float),
+                             _p(out.rgb, C.c_float), _p(out.visibility, C.c_int32))
+    return out
+
+
+def bin_tiles(cfg, cam, pr: Projection) -> Binning:
+    n = pr.tiles_count.shape[0]
+    total = int(pr.tiles_count.astype(np.int64).sum())
+    gx, gy = (cam.width + 15) // 16, (cam.height + 15) // 16
+    m = max(total, 1)
+    b = Binning(np.zeros(m, np.uint64), np.zeros(m, np.uint32), np.zeros(m, np.uint64), np.zeros(m, np.uint32),
+                np.zeros((gx * gy, 2), np.uint32))
+    got = lib().gut_oracle_bin(C.byref(cfg), C.byref(cam), C.c_int64(n), _p(pr.tiles_count, C.c_uint32),
+                               _p(pr.proj_pos, C.c_float), _p(pr.conic_opacity, C.c_float), _p(pr.extent, C.c_float),
+                               _p(pr.depth, C.c_float), _p(b.unsorted_keys, C.c_uint64), _p(b.unsorted_values, C.c_uint32),
+                               _p(b.sorted_keys, C.c_uint64), _p(b.sorted_values, C.c_uint32), _p(b.ranges, C.c_uint32))
+    assert got == total
+    for k in ("unsorted_keys", "unsorted_values", "sorted_keys", "sorted_values"):
+        setattr(b, k, getattr(b, k)[:total])
+    return b
+
+
+def render_forward(cfg, cam, rays_o, rays_d, particles, pr: Projection, bn: Binning):
+    rays_o, rays_d, particles = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3), _f32(particles)
+    h, w = cam.height, cam.width
+    rgba = np.zeros((h, w, 4), np.float32)
+    dist = np.zeros((h, w, 1), np.float32)
+    hits = np.zeros((h, w, 1), np.float32)
+    sv = bn.sorted_values if bn.sorted_values.size else np.zeros(1, np.uint32)
+    lib().gut_oracle_render_forward(C.byref(cfg), C.byref(cam), _p(rays_o, C.c_float), _p(rays_d, C.c_float),
+                                    _p(particles, C.c_float), _p(pr.rgb, C.c_float), _p(sv, C.c_uint32),
+                                    _p(bn.ranges, C.c_uint32), _p(rgba, C.c_float), _p(dist, C.c_float),
+                                    _p(hits, C.c_float))
+    return rgba, dist, hits
+
+
+def render_backward(cfg, cam, rays_o, rays_d, particles, sph, sph_degree, pr, bn, rgba, dist, d_rgba, d_dist):
+    rays_o, rays_d = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
+    particles, sph = _f32(particles), _f32(sph)
+    rgba, dist, d_rgba, d_dist = _f32(rgba), _f32(dist), _f32(d_rgba), _f32(d_dist)
+    n = particles.shape[0]
+    dp = np.zeros((n, 12), np.float32)
+    ds = np.zeros((n, 48), np.float32)
+    sv = bn.sorted_values if bn.sorted_values.size else np.zeros(1, np.uint32)
+    lib().gut_oracle_render_backward(C.byref(cfg), C.byref(cam), C.c_int64(n), _p(rays_o, C.c_float), _p(rays_d, C.c_float),
+                                     _p(particles, C.c_float), _p(sph, C.c_float), C.c_int32(sph_degree),
+                                     _p(pr.rgb, C.c_float), _p(pr.tiles_count, C.c_uint32), _p(sv, C.c_uint32),
+                                     _p(bn.ranges, C.c_uint32), _p(rgba, C.c_float), _p(dist, C.c_float),
+                                     _p(d_rgba, C.c_float), _p(d_dist, C.c_float), _p(dp, C.c_float), _p(ds, C.c_float))
+    return dp, ds
+
+
+def forward_all(cfg, cam, rays_o, rays_d, particles, sph, sph_degree):
+    pr = project(cfg, cam, particles, sph, sph_degree)
+    bn = bin_tiles(cfg, cam, pr)
+    rgba, dist, hits = render_forward(cfg, cam, rays_o, rays_d, particles, pr, bn)
+    return pr, bn, rgba, dist, hits
+
+
+def hit_forward(cfg, ro, rd, particle):
+    a, t = C.c_float(0), C.c_float(0)
+    acc = lib().gut_oracle_hit_forward(C.byref(cfg), _p(_f32(ro), C.c_float), _p(_f32(rd), C.c_float), _p(_f32(particle), C.c_float),
+                                       C.byref(a), C.byref(t))
+    return acc, a.value, t.value
+
+
+def hit_backward(cfg, ro, rd, particle, prgb, Tint, T, Tgrad, Cint, Cacc, Cgrad, Dint, D, Dgrad):
+    T_, D_ = C.c_float(T), C.c_float(D)
+    Cc = _f32(Cacc).copy()
+    grad, rg = np.zeros(11, np.float32), np.zeros(3, np.float32)
+    acc = lib().gut_oracle_hit_backward(C.byref(cfg), _p(_f32(ro), C.c_float), _p(_f32(rd), C.c_float), _p(_f32(particle), C.c_float),
+                                        _p(_f32(prgb), C.c_float), C.c_float(Tint), C.byref(T_), C.c_float(Tgrad), _p(_f32(Cint), C.c_float),
+                                        _p(Cc, C.c_float), _p(_f32(Cgrad), C.c_float), C.c_float(Dint), C.byref(D_), C.c_float(Dgrad),
+                                        _p(grad, C.c_float), _p(rg, C.c_float))
+    return acc, grad, rg, T_.value, Cc, D_.value
+
+
+def sph_eval(degree, coeffs, direction):
+    out = np.zeros(3, np.float32)
+    lib().gut_oracle_sph_eval(C.c_int32(degree), _p(_f32(coeffs), C.c_float), _p(_f32(direction), C.c_float), _p(out, C.c_float))
+    return out
