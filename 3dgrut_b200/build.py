@@ -1,0 +1,65 @@
+"""In-tree build of libgut_b200.so (sm_100a only).  Called by __graft_entry__.build() and lazily by the loader.
+
+One nvcc compile per translation unit so the projection kernels can be built with -fmad=false (integer
+parity of tile counts / sort keys, see csrc/gut_project.cu) while the compositing kernels keep FMA contraction.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libgut_b200.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-Xcompiler", "-fvisibility=hidden"]
+UNITS = {
+    "gut_project.cu": ["-fmad=false"],
+    "gut_sort.cu": [],
+    "gut_render.cu": [],
+    "gut_api.cu": ["-fmad=false"],
+}
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build the sm_100a extension")
+
+
+def sources():
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "gut_b200.h")]
+    return deps
+
+
+def needs_build() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(p) > t for p in sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return OUT
+    nvcc = _nvcc()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for unit, extra in UNITS.items():
+        obj = os.path.join(objdir, unit.replace(".cu", ".o"))
+        cmd = [nvcc, *ARCH, *COMMON, *extra, "-Xptxas", "-v" if verbose else "-warn-spills", "-c", os.path.join(CSRC, unit), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+        objs.append(obj)
+    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", OUT, *objs])
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose="-v" in sys.argv))

@@ -1,0 +1,70 @@
+// 3dgrut_b200/csrc/gut_common.cuh -- shared device/host declarations of the B200 3DGUT renderer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gut_b200.h"
+
+namespace gutb200 {
+
+constexpr int kTile         = 16;   // GUTParameters::Tiling::BlockX/Y (gutRendererParameters.h:22-25): part of the key format
+constexpr int kTilePixels   = kTile * kTile;
+constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+
+// Per-frame camera block handed to every kernel by value (lives in the constant bank of the launch).
+struct FrameCamera {
+    int width, height, grid_x, grid_y;
+    float fx, fy, cx, cy;
+    float radial[6], tangential[2], thin_prism[4];
+    float rot_start[9];   // column-major world->sensor rotation at shutter open (cameraProjections.cuh:225-229)
+    float t_start[3];
+    float view[12];       // world->sensor at mid exposure, 4 columns x 3 (gutRenderer.cu:266,284)
+    float s2w[12];        // sensor->world at mid exposure (gutRenderer.cu:267,406)
+    float cam_pos[3];     // sensor position in world space (gutRenderer.cu:282)
+    float res_x, res_y;   // float copies of width/height
+};
+
+struct FrameConfig {
+    int kernel_degree;
+    float min_kernel_density, min_alpha, max_alpha, min_transmittance;
+    float ut_delta, ut_margin;
+    float w0_mean, wi, w0_cov;   // unscented-transform weights (gutProjector.cuh:150,163,201)
+    int rect_bounding, tight_opacity_bounding, tile_culling, global_z_order;
+};
+
+// Projection result of one particle consumed by the expand kernel: centre, extent, conic, opacity (32 B).
+struct __align__(16) ProjRecord {
+    float cx, cy, ex, ey;
+    float ca, cb, cc, op;
+};
+
+// Gradient accumulator row (64 B): one coalesced vector RED per (warp, particle).
+//   0..2 pos, 3 density, 4..7 quat(wxyz), 8..10 scale, 11 pad, 12..14 precomputed-rgb grad, 15 pad
+constexpr int kGradRow = 16;
+
+void launch_project(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const float* particles,
+                    const float* sph, int sph_degree, uint32_t* tiles_count, ProjRecord* proj, float* depth, float* rgb,
+                    float* visibility);
+void launch_expand(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const uint32_t* offsets,
+                   const ProjRecord* proj, const float* depth, uint64_t* keys, uint32_t* values);
+void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint64_t* sorted_keys, uint32_t* ranges);
+
+void launch_render_forward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
+                           const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
+                           const uint32_t* ranges, float* out_rgba, float* out_dist, float* out_hits);
+void launch_render_backward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
+                            const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
+                            const uint32_t* ranges, const float* out_rgba, const float* d_rgba, const float* out_dist,
+                            const float* d_dist, float* grad_acc);
+void launch_project_backward(cudaStream_t s, const FrameCamera& cam, int64_t n, const float* particles, const float* sph,
+                             int sph_degree, const float* rgb, const uint32_t* tiles_count, float* grad_acc,
+                             float* d_particles, float* d_sph);
+
+// CUB-backed helpers (scan + radix sort), gut_sort.cu
+size_t scan_temp_bytes(int64_t n);
+void run_inclusive_scan(cudaStream_t s, void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, int64_t n);
+size_t sort_temp_bytes(int64_t n, int end_bit);
+void run_sort_pairs(cudaStream_t s, void* temp, size_t temp_bytes, const uint64_t* kin, uint64_t* kout, const uint32_t* vin,
+                    uint32_t* vout, int64_t n, int end_bit);
+
+}  // namespace gutb200

@@ -1,0 +1,407 @@
+// 3dgrut_b200/csrc/gut_project.cu -- per-particle stages of the 3DGUT forward: unscented projection + tile
+// counting (G1), key expansion (G3), tile ranges (G5).
+//
+// Built with -fmad=false and IEEE div/sqrt: tile counts and sort keys are INTEGER outputs that must be
+// bit-identical to the checker, so every fp32 operation here is written in the order the reference writes it
+// (threedgut_tracer/include/3dgut/kernels/cuda/renderers/gutProjector.cuh) and nothing is contracted.
+// These kernels are HBM-bound, the un-fused multiplies cost nothing measurable.
+//
+// B200 specifics: the 48-byte particle records of a CTA are one contiguous 12 KB span, fetched with a single
+// TMA bulk copy (cp.async.bulk + mbarrier) into shared memory instead of 3 strided LDG.128 per thread; record
+// reads from shared memory are conflict-free (stride 12 words, LDS.128 phases of 8 lanes).
+#include "gut_common.cuh"
+
+namespace gutb200 {
+
+namespace {
+
+constexpr int kProjThreads = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+struct TileBox {
+    int x0, y0, x1, y1;
+};
+
+// computeTileSpaceBBox (gutProjector.cuh:32-43)
+__device__ __forceinline__ TileBox tile_box(int gx, int gy, float cx, float cy, float ex, float ey) {
+    TileBox b;
+    b.x0 = min(gx, max(0, static_cast<int>(floorf((cx - 0.5f - ex) / 16.0f))));
+    b.y0 = min(gy, max(0, static_cast<int>(floorf((cy - 0.5f - ey) / 16.0f))));
+    b.x1 = min(gx, max(0, static_cast<int>(ceilf((cx - 0.5f + ex) / 16.0f))));
+    b.y1 = min(gy, max(0, static_cast<int>(ceilf((cy - 0.5f + ey) / 16.0f))));
+    return b;
+}
+
+__device__ __forceinline__ float sat(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
+
+// tileMinParticlePowerResponse (gutProjector.cuh:49-78): smallest power of the 2-D conic over a tile.
+__device__ __forceinline__ float tile_min_power(float tx, float ty, float ca, float cb, float cc, float mx, float my) {
+    const float ts = 16.0f;
+    const float tminx = ts * tx, tminy = ts * ty;
+    const float tmaxx = ts + tminx, tmaxy = ts + tminy;
+    const float mox = tminx - mx, moy = tminy - my;
+    const float lax = mox > 0.0f ? 1.f : 0.f, lay = moy > 0.0f ? 1.f : 0.f;
+    const float nrx = lax + (mx > tmaxx ? 1.f : 0.f);
+    const float nry = lay + (my > tmaxy ? 1.f : 0.f);
+    if ((nrx + nry) > 0.0f) {
+        const float px = tmaxx * (1.f - lax) + tminx * lax;
+        const float py = tmaxy * (1.f - lay) + tminy * lay;
+        const float dxx = copysignf(ts, mox), dxy = copysignf(ts, moy);
+        const float dfx = mx - px, dfy = my - py;
+        const float rcx = 1.0f / (ts * ts * ca);
+        const float rcy = 1.0f / (ts * ts * cc);
+        const float tx_ = nry * sat((dxx * ca * dfx + dxx * cb * dfy) * rcx);
+        const float ty_ = nrx * sat((dxy * cb * dfx + dxy * cc * dfy) * rcy);
+        const float mdx = mx - (px + tx_ * dxx);
+        const float mdy = my - (py + ty_ * dxy);
+        return 0.5f * (ca * mdx * mdx + cc * mdy * mdy) + cb * mdx * mdy;
+    }
+    return 0.f;
+}
+
+// OpenCV pinhole projection of a sensor-space point (cameraProjections.cuh:67-118)
+__device__ __forceinline__ bool project_pinhole(const FrameCamera& cam, float tol, float x, float y, float z, float& ox, float& oy) {
+    if (z <= 0.f) {
+        ox = 0.f;
+        oy = 0.f;
+        return false;
+    }
+    const float u = x / z, v = y / z;
+    const float uu = u * u, vv = v * v;
+    const float r2 = uu + vv;
+    const float a1 = 2.f * u * v;
+    const float a2 = r2 + 2.f * uu;
+    const float a3 = r2 + 2.f * vv;
+    const float num = 1.f + r2 * (cam.radial[0] + r2 * (cam.radial[1] + r2 * cam.radial[2]));
+    const float den = 1.f + r2 * (cam.radial[3] + r2 * (cam.radial[4] + r2 * cam.radial[5]));
+    const float icd = num / den;
+    const float dx = cam.tangential[0] * a1 + cam.tangential[1] * a2 + r2 * (cam.thin_prism[0] + r2 * cam.thin_prism[1]);
+    const float dy = cam.tangential[0] * a3 + cam.tangential[1] * a1 + r2 * (cam.thin_prism[2] + r2 * cam.thin_prism[3]);
+    const float ndx = icd * u + dx, ndy = icd * v + dy;
+    const bool valid_radial = (icd > 0.8f) && (icd < 1.2f);
+    if (valid_radial) {
+        ox = ndx * cam.fx + cam.cx;
+        oy = ndy * cam.fy + cam.cy;
+    } else {
+        const float clip = hypotf(cam.res_x, cam.res_y);
+        const float f = clip / sqrtf(r2);
+        ox = f * u + cam.cx;
+        oy = f * v + cam.cy;
+    }
+    const float mx = cam.res_x * tol, my = cam.res_y * tol;
+    const bool inside = (ox > -mx) && (oy > -my) && (ox < cam.res_x + mx) && (oy < cam.res_y + my);
+    return valid_radial && inside;
+}
+
+// world point -> pixel with the shutter-open pose (global shutter branch, cameraProjections.cuh:225-232)
+__device__ __forceinline__ bool project_world(const FrameCamera& cam, float tol, float px, float py, float pz, float& ox, float& oy) {
+    float s[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float acc = 0.f;
+        acc += cam.rot_start[0 * 3 + j] * px;
+        acc += cam.rot_start[1 * 3 + j] * py;
+        acc += cam.rot_start[2 * 3 + j] * pz;
+        s[j] = acc + cam.t_start[j];
+    }
+    return project_pinhole(cam, tol, s[0], s[1], s[2], ox, oy);
+}
+
+constexpr float kC0 = 0.28209479177387814f;
+constexpr float kC1 = 0.4886025119029199f;
+__constant__ float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
+                             0.5462742152960396f};
+__constant__ float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                             -0.4570457994644658f, 1.445305721320277f,  -0.5900435899266435f};
+
+// unclamped view-dependent radiance of one particle (radianceFromSpH, models/gaussianParticles.cuh:68-100)
+__device__ __forceinline__ void sph_radiance(int deg, const float* __restrict__ c, float x, float y, float z, float out[3]) {
+    float cf[48];
+    const float4* c4 = reinterpret_cast<const float4*>(c);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const float4 v = __ldg(c4 + i);
+        cf[i * 4 + 0] = v.x;
+        cf[i * 4 + 1] = v.y;
+        cf[i * 4 + 2] = v.z;
+        cf[i * 4 + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#define CF(i) cf[(i)*3 + k]
+        float rad = kC0 * CF(0);
+        if (deg > 0) {
+            rad = rad - kC1 * y * CF(1) + kC1 * z * CF(2) - kC1 * x * CF(3);
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                rad = rad + kC2[0] * xy * CF(4) + kC2[1] * yz * CF(5) + kC2[2] * (2.0f * zz - xx - yy) * CF(6) + kC2[3] * xz * CF(7) +
+                      kC2[4] * (xx - yy) * CF(8);
+                if (deg > 2) {
+                    rad = rad + kC3[0] * y * (3.0f * xx - yy) * CF(9) + kC3[1] * xy * z * CF(10) +
+                          kC3[2] * y * (4.0f * zz - xx - yy) * CF(11) + kC3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * CF(12) +
+                          kC3[4] * x * (4.0f * zz - xx - yy) * CF(13) + kC3[5] * z * (xx - yy) * CF(14) +
+                          kC3[6] * x * (xx - 3.0f * yy) * CF(15);
+                }
+            }
+        }
+#undef CF
+        out[k] = rad + 0.5f;
+    }
+}
+
+// G1: one thread per particle (projectOnTiles -> GUTProjector::eval, gutProjector.cuh:217-322)
+__global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, FrameConfig cfg, int64_t n,
+                                                               const float* __restrict__ particles,
+                                                               const float* __restrict__ sph, int sph_degree,
+                                                               uint32_t* __restrict__ tiles_count, ProjRecord* __restrict__ proj,
+                                                               float* __restrict__ depth, float* __restrict__ rgb,
+                                                               float* __restrict__ visibility) {
+    __shared__ __align__(128) float4 s_rec[kProjThreads * 3];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * kProjThreads;
+    const int count = static_cast<int>(min(static_cast<int64_t>(kProjThreads), n - base));
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(count) * 48u;
+        mbar_expect_tx(&s_bar, bytes);
+        tma_bulk_g2s(s_rec, particles + base * 12, bytes, &s_bar);
+    }
+    mbar_wait(&s_bar, 0);
+
+    const int64_t i = base + threadIdx.x;
+    if (i >= n) return;
+
+    const float4 r0 = s_rec[threadIdx.x * 3 + 0];  // pos.xyz, density
+    const float4 r1 = s_rec[threadIdx.x * 3 + 1];  // quat wxyz
+    const float4 r2 = s_rec[threadIdx.x * 3 + 2];  // scale.xyz, pad
+    const float px = r0.x, py = r0.y, pz = r0.z, opacity = r0.w;
+
+    // rows of quaternionWXYZToMatrix == columns of R (models/gaussianParticles.cuh:39-59)
+    float rot[3][3];
+    {
+        const float r = r1.x, x = r1.y, y = r1.z, z = r1.w;
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+        const float rx = r * x, ry = r * y, rz = r * z;
+        rot[0][0] = 1.f - 2.f * (yy + zz); rot[0][1] = 2.f * (xy + rz); rot[0][2] = 2.f * (xz - ry);
+        rot[1][0] = 2.f * (xy - rz); rot[1][1] = 1.f - 2.f * (xx + zz); rot[1][2] = 2.f * (yz + rx);
+        rot[2][0] = 2.f * (xz + ry); rot[2][1] = 2.f * (yz - rx); rot[2][2] = 1.f - 2.f * (xx + yy);
+    }
+    const float scl[3] = {r2.x, r2.y, r2.z};
+
+    bool valid_proj = false, valid_conic = false;
+    float pcx = 0.f, pcy = 0.f, cov0 = 0.f, cov1 = 0.f, cov2 = 0.f;
+    const float zc = px * cam.view[0 * 3 + 2] + py * cam.view[1 * 3 + 2] + pz * cam.view[2 * 3 + 2] + cam.view[3 * 3 + 2];
+
+    // unscentedParticleProjection (gutProjector.cuh:118-215): 7 sigma points, lambda = 0
+    if (!(opacity < cfg.min_alpha) && !(zc < 0.2f)) {
+        float spx[7], spy[7];
+        int nvalid = 0;
+        nvalid += project_world(cam, cfg.ut_margin, px, py, pz, spx[0], spy[0]) ? 1 : 0;
+        pcx = spx[0] * cfg.w0_mean;
+        pcy = spy[0] * cfg.w0_mean;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float f = cfg.ut_delta * scl[k];
+            const float dx = rot[k][0] * f, dy = rot[k][1] * f, dz = rot[k][2] * f;
+            nvalid += project_world(cam, cfg.ut_margin, px + dx, py + dy, pz + dz, spx[k + 1], spy[k + 1]) ? 1 : 0;
+            pcx += cfg.wi * spx[k + 1];
+            pcy += cfg.wi * spy[k + 1];
+            nvalid += project_world(cam, cfg.ut_margin, px - dx, py - dy, pz - dz, spx[k + 4], spy[k + 4]) ? 1 : 0;
+            pcx += cfg.wi * spx[k + 4];
+            pcy += cfg.wi * spy[k + 4];
+        }
+        if (nvalid != 0) {
+            {
+                const float ex = spx[0] - pcx, ey = spy[0] - pcy;
+                cov0 = cfg.w0_cov * (ex * ex);
+                cov1 = cfg.w0_cov * (ex * ey);
+                cov2 = cfg.w0_cov * (ey * ey);
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const float ex = spx[k + 1] - pcx, ey = spy[k + 1] - pcy;
+                cov0 += cfg.wi * (ex * ex);
+                cov1 += cfg.wi * (ex * ey);
+                cov2 += cfg.wi * (ey * ey);
+            }
+            valid_proj = true;
+        }
+    }
+
+    // computeProjectedExtentConicOpacity (gutProjector.cuh:81-116)
+    float ex = 0.f, ey = 0.f, ca = 0.f, cb = 0.f, cc = 0.f, op = 0.f, maxpow = 0.f;
+    if (valid_proj) {
+        const float dcx = cov0 + 0.3f, dcy = cov1, dcz = cov2 + 0.3f;
+        const float ddet = dcx * dcz - dcy * dcy;
+        if (ddet != 0.0f) {
+            ca = dcz / ddet;
+            cb = -dcy / ddet;
+            cc = dcx / ddet;
+            const float cdet = cov0 * cov2 - cov1 * cov1;
+            op = opacity * sqrtf(fmaxf(0.000025f, cdet / ddet));
+            if (!(op < cfg.min_alpha)) {
+                maxpow = logf(op / cfg.min_alpha);
+                const float ef = cfg.tight_opacity_bounding ? fminf(3.33f, sqrtf(2.0f * maxpow)) : 3.33f;
+                const float mid = 0.5f * (dcx + dcz);
+                const float lam = mid + sqrtf(fmaxf(0.01f, mid * mid - ddet));
+                const float radius = ef * sqrtf(lam);
+                if (cfg.rect_bounding) {
+                    ex = fminf(ef * sqrtf(dcx), radius);
+                    ey = fminf(ef * sqrtf(dcz), radius);
+                } else {
+                    ex = radius;
+                    ey = radius;
+                }
+                valid_conic = radius > 0.f;
+            }
+        }
+    }
+
+    const bool visible = valid_proj && valid_conic;
+    // the reference stores int 1 into this float tensor (gutProjector.cuh:275, splatRaster.cpp:215,249);
+    // consumers only test it for non-zero, we store the same bit pattern.
+    visibility[i] = __int_as_float(visible ? 1 : 0);
+
+    uint32_t ntiles = 0;
+    if (visible) {
+        const TileBox bb = tile_box(cam.grid_x, cam.grid_y, pcx, pcy, ex, ey);
+        if (cfg.tile_culling) {
+            for (int y = bb.y0; y < bb.y1; ++y)
+                for (int x = bb.x0; x < bb.x1; ++x)
+                    if (tile_min_power(static_cast<float>(x), static_cast<float>(y), ca, cb, cc, pcx, pcy) < maxpow) ntiles++;
+        } else {
+            ntiles = static_cast<uint32_t>((bb.x1 - bb.x0) * (bb.y1 - bb.y0));
+        }
+    }
+    tiles_count[i] = ntiles;
+
+    ProjRecord pr;
+    float zdepth = 0.f, col[3] = {0.f, 0.f, 0.f};
+    if (ntiles == 0) {
+        pr.cx = pr.cy = pr.ex = pr.ey = pr.ca = pr.cb = pr.cc = pr.op = 0.f;
+    } else {
+        const float sx = px - cam.cam_pos[0], sy = py - cam.cam_pos[1], sz = pz - cam.cam_pos[2];
+        const float dist = sqrtf(sx * sx + sy * sy + sz * sz);
+        sph_radiance(sph_degree, sph + i * 48, sx / dist, sy / dist, sz / dist, col);
+        pr.cx = pcx; pr.cy = pcy; pr.ex = ex; pr.ey = ey;
+        pr.ca = ca; pr.cb = cb; pr.cc = cc; pr.op = op;
+        zdepth = cfg.global_z_order ? zc : dist;
+    }
+    proj[i] = pr;
+    depth[i] = zdepth;
+    rgb[i * 3 + 0] = col[0];
+    rgb[i * 3 + 1] = col[1];
+    rgb[i * 3 + 2] = col[2];
+}
+
+// G3: emit (tile << 32 | depth bits, particle) for every surviving tile (GUTProjector::expand, gutProjector.cuh:324-388)
+__global__ void __launch_bounds__(256) expand_kernel(FrameCamera cam, FrameConfig cfg, int64_t n,
+                                                     const uint32_t* __restrict__ offsets, const ProjRecord* __restrict__ proj,
+                                                     const float* __restrict__ depth, uint64_t* __restrict__ keys,
+                                                     uint32_t* __restrict__ values) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ProjRecord pr = proj[i];
+    if (pr.ex <= 1e-06f) return;
+    const uint32_t dkey = __float_as_uint(depth[i]);
+    uint32_t off = (i == 0) ? 0u : offsets[i - 1];
+    const uint32_t maxoff = offsets[i];
+    const TileBox bb = tile_box(cam.grid_x, cam.grid_y, pr.cx, pr.cy, pr.ex, pr.ey);
+    if (cfg.tile_culling) {
+        const float maxpow = logf(pr.op / cfg.min_alpha);
+        for (int y = bb.y0; (y < bb.y1) && (off < maxoff); ++y)
+            for (int x = bb.x0; (x < bb.x1) && (off < maxoff); ++x)
+                if (tile_min_power(static_cast<float>(x), static_cast<float>(y), pr.ca, pr.cb, pr.cc, pr.cx, pr.cy) < maxpow) {
+                    keys[off] = (static_cast<uint64_t>(static_cast<uint32_t>(y * cam.grid_x + x)) << 32) | dkey;
+                    values[off] = static_cast<uint32_t>(i);
+                    off++;
+                }
+        for (; off < maxoff; ++off) {  // padding, never produced when project and expand agree (gutProjector.cuh:372-376)
+            keys[off] = (static_cast<uint64_t>(kInvalid) << 32) | __float_as_uint(3.4028235e+38f);
+            values[off] = kInvalid;
+        }
+    } else {
+        for (int y = bb.y0; y < bb.y1; ++y)
+            for (int x = bb.x0; x < bb.x1; ++x) {
+                keys[off] = (static_cast<uint64_t>(static_cast<uint32_t>(y * cam.grid_x + x)) << 32) | dkey;
+                values[off] = static_cast<uint32_t>(i);
+                off++;
+            }
+    }
+}
+
+// G5: [begin,end) of every tile in the sorted key stream (computeSortedTileRangeIndices, gutRenderer.cu:46-76)
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t num_keys, const uint64_t* __restrict__ keys,
+                                                          uint32_t* __restrict__ ranges) {
+    const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= num_keys) return;
+    const uint32_t tile = static_cast<uint32_t>(keys[k] >> 32);
+    const bool valid = tile != kInvalid;
+    if (k == 0) {
+        if (valid) ranges[tile * 2] = 0u;
+    } else {
+        const uint32_t prev = static_cast<uint32_t>(keys[k - 1] >> 32);
+        if (prev != tile) {
+            if (prev != kInvalid) ranges[prev * 2 + 1] = static_cast<uint32_t>(k);
+            if (valid) ranges[tile * 2] = static_cast<uint32_t>(k);
+        }
+    }
+    if (valid && (k == num_keys - 1)) ranges[tile * 2 + 1] = static_cast<uint32_t>(num_keys);
+}
+
+}  // namespace
+
+void launch_project(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const float* particles,
+                    const float* sph, int sph_degree, uint32_t* tiles_count, ProjRecord* proj, float* depth, float* rgb,
+                    float* visibility) {
+    if (n <= 0) return;
+    const unsigned blocks = static_cast<unsigned>((n + kProjThreads - 1) / kProjThreads);
+    project_kernel<<<blocks, kProjThreads, 0, s>>>(cam, cfg, n, particles, sph, sph_degree, tiles_count, proj, depth, rgb, visibility);
+}
+
+void launch_expand(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const uint32_t* offsets,
+                   const ProjRecord* proj, const float* depth, uint64_t* keys, uint32_t* values) {
+    if (n <= 0) return;
+    const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+    expand_kernel<<<blocks, 256, 0, s>>>(cam, cfg, n, offsets, proj, depth, keys, values);
+}
+
+void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint64_t* sorted_keys, uint32_t* ranges) {
+    if (num_keys <= 0) return;
+    const unsigned blocks = static_cast<unsigned>((num_keys + 255) / 256);
+    tile_ranges_kernel<<<blocks, 256, 0, s>>>(num_keys, sorted_keys, ranges);
+}
+
+}  // namespace gutb200

@@ -1,0 +1,529 @@
+// 3dgrut_b200/csrc/gut_render.cu -- per-tile compositing (G6), its adjoint (G7) and the per-particle
+// spherical-harmonics adjoint (G8) of the 3DGUT path.
+//
+// Reference semantics restated (not copied) from
+//   G6  threedgut_tracer/include/3dgut/kernels/cuda/renderers/gutKBufferRenderer.cuh:274-352 (k-buffer = 0)
+//       + kernels/slang/models/gaussianParticles.slang:96-274 (canonical ray, response, integrate)
+//   G7  gutKBufferRenderer.cuh:642-716 + kernels/cuda/models/gaussianParticles.cuh:484-751 (hand-written adjoint)
+//   G8  kernels/cuda/renderers/gutProjector.cuh:390-430 + slang/common/sphericalHarmonics.slang:21-64
+//
+// Design: one CTA per 16x16 tile (the tile id is part of the sort key, so the tile
+// shape is fixed by parity), 256 threads = 256 pixels, sorted particle lists consumed in batches staged in
+// shared memory as render-ready records (scale folded into the rotation rows once per staged particle
+// instead of once per pixel test).  Both kernels are FP32/SFU-issue bound, not HBM bound.
+// G7 reduces the 14 per-particle gradient floats across the warp with a 16-value transposing butterfly
+// (16 SHFL instead of 70) and lands them with ONE coalesced 64-byte vector RED per (warp, particle) into a
+// [N,16] accumulator that G8 consumes and re-zeroes.
+#include "gut_common.cuh"
+
+namespace gutb200 {
+
+namespace {
+
+constexpr int kBatch = 256;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+struct Ray {
+    float ox, oy, oz, dx, dy, dz, tmin, tmax;
+    bool alive;
+};
+
+// initializeRay (kernels/cuda/common/rayPayload.cuh:76-108) with the +-1e6 scene box of splatRaster.cpp:240
+__device__ __forceinline__ Ray make_ray(const FrameCamera& cam, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                        int64_t pix) {
+    Ray r;
+    const float rox = rays_o[pix * 3 + 0], roy = rays_o[pix * 3 + 1], roz = rays_o[pix * 3 + 2];
+    const float rdx = rays_d[pix * 3 + 0], rdy = rays_d[pix * 3 + 1], rdz = rays_d[pix * 3 + 2];
+    const float* m = cam.s2w;
+    r.ox = m[0] * rox + m[3] * roy + m[6] * roz + m[9];
+    r.oy = m[1] * rox + m[4] * roy + m[7] * roz + m[10];
+    r.oz = m[2] * rox + m[5] * roy + m[8] * roz + m[11];
+    r.dx = m[0] * rdx + m[3] * rdy + m[6] * rdz;
+    r.dy = m[1] * rdx + m[4] * rdy + m[7] * rdz;
+    r.dz = m[2] * rdx + m[5] * rdy + m[8] * rdz;
+    const float lo = -1e06f, hi = 1e06f;
+    float tmin = (lo - r.ox) / r.dx, tmax = (hi - r.ox) / r.dx, t;
+    if (tmin > tmax) { t = tmin; tmin = tmax; tmax = t; }
+    float tymin = (lo - r.oy) / r.dy, tymax = (hi - r.oy) / r.dy;
+    if (tymin > tymax) { t = tymin; tymin = tymax; tymax = t; }
+    bool miss = (tmin > tymax) || (tymin > tmax);
+    tmin = fmaxf(tmin, tymin);
+    tmax = fminf(tmax, tymax);
+    float tzmin = (lo - r.oz) / r.dz, tzmax = (hi - r.oz) / r.dz;
+    if (tzmin > tzmax) { t = tzmin; tzmin = tzmax; tzmax = t; }
+    miss = miss || (tmin > tzmax) || (tzmin > tmax);
+    tmin = fmaxf(tmin, tzmin);
+    tmax = fminf(tmax, tzmax);
+    r.tmin = miss ? 3.4028235e+38f : fmaxf(tmin, 0.0f);
+    r.tmax = miss ? 3.4028235e+38f : tmax;
+    r.alive = r.tmax > r.tmin;
+    return r;
+}
+
+template <int DEG>
+__device__ __forceinline__ float kernel_response(float gray) {
+    // generalized Gaussian exp(-4.5/3^DEG * |x|^DEG) on the squared canonical distance (gaussianParticles.cuh:267-308)
+    if (DEG == 4) return __expf(-0.0555555555556f * gray * gray);
+    return __expf(-0.5f * gray);
+}
+
+template <int DEG>
+__device__ __forceinline__ float kernel_response_grad(float gray, float gres, float gres_grad) {
+    if (DEG == 4) return (-0.0555555555556f * 2.0f) * gray * gres * gres_grad;  // gaussianParticles.cuh:239-243
+    return -0.5f * gres * gres_grad;                                             // :259-263
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// G6 forward
+// staged record, 5 x float4: rows of M = diag(1/s) R^T with the particle position in .w, then (s, density), (rgb)
+
+struct FwdSmem {
+    float4 m0[kBatch], m1[kBatch], m2[kBatch], sd[kBatch], col[kBatch];
+};
+
+template <int DEG>
+__global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera cam, FrameConfig cfg,
+                                                                     const float* __restrict__ rays_o,
+                                                                     const float* __restrict__ rays_d,
+                                                                     const float* __restrict__ particles,
+                                                                     const float* __restrict__ rgb,
+                                                                     const uint32_t* __restrict__ sorted_values,
+                                                                     const uint32_t* __restrict__ ranges, float* __restrict__ out_rgba,
+                                                                     float* __restrict__ out_dist, float* __restrict__ out_hits) {
+    __shared__ FwdSmem sm;
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const int tid = threadIdx.y * kTile + threadIdx.x;
+    const int px = blockIdx.x * kTile + threadIdx.x, py = blockIdx.y * kTile + threadIdx.y;
+    const bool inside = (px < cam.width) && (py < cam.height);
+    const int64_t pix = static_cast<int64_t>(py) * cam.width + px;
+
+    Ray ray;
+    ray.alive = false;
+    if (inside) ray = make_ray(cam, rays_o, rays_d, pix);
+    const bool valid = inside && ray.alive;
+
+    float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, dist = 0.f;
+    uint32_t hits = 0;
+    bool alive = valid;
+
+    const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
+    for (uint32_t base = begin; base < end; base += kBatch) {
+        if (__syncthreads_and(!alive)) break;
+        const uint32_t k = base + tid;
+        if (k < end) {
+            const uint32_t idx = sorted_values[k];
+            const float4* p4 = reinterpret_cast<const float4*>(particles) + static_cast<size_t>(idx) * 3;
+            const float4 a = __ldg(p4), q = __ldg(p4 + 1), s = __ldg(p4 + 2);
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+            const float rx = r * x, ry = r * y, rz = r * z;
+            const float isx = 1.0f / s.x, isy = 1.0f / s.y, isz = 1.0f / s.z;
+            sm.m0[tid] = make_float4(isx * (1.f - 2.f * (yy + zz)), isx * (2.f * (xy + rz)), isx * (2.f * (xz - ry)), a.x);
+            sm.m1[tid] = make_float4(isy * (2.f * (xy - rz)), isy * (1.f - 2.f * (xx + zz)), isy * (2.f * (yz + rx)), a.y);
+            sm.m2[tid] = make_float4(isz * (2.f * (xz + ry)), isz * (2.f * (yz - rx)), isz * (1.f - 2.f * (xx + yy)), a.z);
+            sm.sd[tid] = make_float4(s.x, s.y, s.z, a.w);
+            sm.col[tid] = make_float4(fmaxf(rgb[idx * 3 + 0], 0.f), fmaxf(rgb[idx * 3 + 1], 0.f), fmaxf(rgb[idx * 3 + 2], 0.f), 0.f);
+        }
+        __syncthreads();
+        const int count = min(kBatch, static_cast<int>(end - base));
+        for (int j = 0; alive && j < count; ++j) {
+            const float4 m0 = sm.m0[j], m1 = sm.m1[j], m2 = sm.m2[j];
+            const float vx = ray.ox - m0.w, vy = ray.oy - m1.w, vz = ray.oz - m2.w;
+            const float gox = m0.x * vx + m0.y * vy + m0.z * vz;
+            const float goy = m1.x * vx + m1.y * vy + m1.z * vz;
+            const float goz = m2.x * vx + m2.y * vy + m2.z * vz;
+            const float ax = m0.x * ray.dx + m0.y * ray.dy + m0.z * ray.dz;
+            const float ay = m1.x * ray.dx + m1.y * ray.dy + m1.z * ray.dz;
+            const float az = m2.x * ray.dx + m2.y * ray.dy + m2.z * ray.dz;
+            const float l = ax * ax + ay * ay + az * az;
+            const float il = l > 0.f ? rsqrtf(l) : 1.f;
+            const float gdx = ax * il, gdy = ay * il, gdz = az * il;
+            const float ccx = gdy * goz - gdz * goy, ccy = gdz * gox - gdx * goz, ccz = gdx * goy - gdy * gox;
+            const float gray = ccx * ccx + ccy * ccy + ccz * ccz;
+            const float gres = kernel_response<DEG>(gray);
+            const float4 sd = sm.sd[j];
+            const float alpha = fminf(cfg.max_alpha, gres * sd.w);
+            if ((gres > cfg.min_kernel_density) && (alpha > cfg.min_alpha)) {
+                const float pd = -(gdx * gox + gdy * goy + gdz * goz);
+                const float hx = sd.x * gdx * pd, hy = sd.y * gdy * pd, hz = sd.z * gdz * pd;
+                const float t = sqrtf(hx * hx + hy * hy + hz * hz);
+                if ((t > ray.tmin) && (t < ray.tmax)) {
+                    const float w = alpha * T;
+                    dist += t * w;
+                    T *= (1.f - alpha);
+                    if (w > 0.f) {
+                        const float4 c = sm.col[j];
+                        cr += c.x * w;
+                        cg += c.y * w;
+                        cb += c.z * w;
+                        hits++;
+                    }
+                    if (T < cfg.min_transmittance) alive = false;
+                }
+            }
+        }
+    }
+    if (valid) {  // finalizeRay (rayPayload.cuh:160-193); invalid rays keep the initial buffer values
+        reinterpret_cast<float4*>(out_rgba)[pix] = make_float4(cr, cg, cb, 1.0f - T);
+        out_dist[pix] = dist;
+        out_hits[pix] = static_cast<float>(hits);
+    } else if (inside) {
+        reinterpret_cast<float4*>(out_rgba)[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
+        out_dist[pix] = 1e06f;  // torch::ones(...)*1e6 (splatRaster.cpp:213)
+        out_hits[pix] = 0.f;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// G7 backward
+// staged record, 7 x float4:
+//   r0 = rot row0, pos.x   r1 = rot row1, pos.y   r2 = rot row2, pos.z   (rows of quaternionWXYZToMatrix = columns of R)
+//   sc = scale.xyz, density     is = 1/scale.xyz, _     qt = quat wxyz     cl = clamped rgb, particle index bits
+
+struct BwdSmem {
+    float4 r0[kBatch], r1[kBatch], r2[kBatch], sc[kBatch], is[kBatch], qt[kBatch], cl[kBatch];
+};
+
+// sum 16 per-lane values over the warp; lane L returns the total of component (L >> 1). 16 SHFL in all.
+__device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool up = lane & 16;
+        const float send = up ? v[i] : v[i + 8];
+        const float keep = up ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(kFull, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool up = lane & 8;
+        const float send = up ? v[i] : v[i + 4];
+        const float keep = up ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(kFull, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool up = lane & 4;
+        const float send = up ? v[i] : v[i + 2];
+        const float keep = up ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(kFull, send, 4);
+    }
+    {
+        const bool up = lane & 2;
+        const float send = up ? v[0] : v[1];
+        const float keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(kFull, send, 2);
+    }
+    v[0] += __shfl_xor_sync(kFull, v[0], 1);
+    return v[0];
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(kTilePixels) render_backward_kernel(FrameCamera cam, FrameConfig cfg,
+                                                                      const float* __restrict__ rays_o,
+                                                                      const float* __restrict__ rays_d,
+                                                                      const float* __restrict__ particles,
+                                                                      const float* __restrict__ rgb,
+                                                                      const uint32_t* __restrict__ sorted_values,
+                                                                      const uint32_t* __restrict__ ranges,
+                                                                      const float* __restrict__ out_rgba, const float* __restrict__ d_rgba,
+                                                                      const float* __restrict__ out_dist, const float* __restrict__ d_dist,
+                                                                      float* __restrict__ grad_acc) {
+    __shared__ BwdSmem sm;
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const int tid = threadIdx.y * kTile + threadIdx.x;
+    const int lane = tid & 31;
+    const int px = blockIdx.x * kTile + threadIdx.x, py = blockIdx.y * kTile + threadIdx.y;
+    const bool inside = (px < cam.width) && (py < cam.height);
+    const int64_t pix = static_cast<int64_t>(py) * cam.width + px;
+
+    Ray ray;
+    ray.alive = false;
+    if (inside) ray = make_ray(cam, rays_o, rays_d, pix);
+    bool alive = inside && ray.alive;
+
+    // initializeBackwardRay (kernels/cuda/common/rayPayloadBackward.cuh:31-73)
+    float Cix = 0.f, Ciy = 0.f, Ciz = 0.f, Cgx = 0.f, Cgy = 0.f, Cgz = 0.f, Tint = 1.f, Tgrad = 0.f, Dint = 0.f, Dgrad = 0.f;
+    if (alive) {
+        const float4 o = reinterpret_cast<const float4*>(out_rgba)[pix];
+        const float4 g = reinterpret_cast<const float4*>(d_rgba)[pix];
+        Cix = o.x; Ciy = o.y; Ciz = o.z;
+        Cgx = g.x; Cgy = g.y; Cgz = g.z;
+        Tint = 1.f - o.w;
+        Tgrad = -1.f * g.w;
+        Dint = out_dist[pix];
+        Dgrad = d_dist[pix];
+    }
+    float T = 1.f, Cx = 0.f, Cy = 0.f, Cz = 0.f, D = 0.f;
+
+    const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
+    for (uint32_t base = begin; base < end; base += kBatch) {
+        if (__syncthreads_and(!alive)) break;
+        const uint32_t k = base + tid;
+        if (k < end) {
+            const uint32_t idx = sorted_values[k];
+            const float4* p4 = reinterpret_cast<const float4*>(particles) + static_cast<size_t>(idx) * 3;
+            const float4 a = __ldg(p4), q = __ldg(p4 + 1), s = __ldg(p4 + 2);
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+            const float rx = r * x, ry = r * y, rz = r * z;
+            sm.r0[tid] = make_float4(1.f - 2.f * (yy + zz), 2.f * (xy + rz), 2.f * (xz - ry), a.x);
+            sm.r1[tid] = make_float4(2.f * (xy - rz), 1.f - 2.f * (xx + zz), 2.f * (yz + rx), a.y);
+            sm.r2[tid] = make_float4(2.f * (xz + ry), 2.f * (yz - rx), 1.f - 2.f * (xx + yy), a.z);
+            sm.sc[tid] = make_float4(s.x, s.y, s.z, a.w);
+            sm.is[tid] = make_float4(1.0f / s.x, 1.0f / s.y, 1.0f / s.z, 0.f);
+            sm.qt[tid] = q;
+            sm.cl[tid] = make_float4(fmaxf(rgb[idx * 3 + 0], 0.f), fmaxf(rgb[idx * 3 + 1], 0.f), fmaxf(rgb[idx * 3 + 2], 0.f),
+                                     __uint_as_float(idx));
+        }
+        __syncthreads();
+        const int count = min(kBatch, static_cast<int>(end - base));
+        for (int j = 0; j < count; ++j) {
+            if (__all_sync(kFull, !alive)) break;
+            float g[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) g[i] = 0.f;
+            bool hit = false;
+            if (alive) {
+                const float4 r0 = sm.r0[j], r1 = sm.r1[j], r2 = sm.r2[j], sc = sm.sc[j], is = sm.is[j];
+                // canonical ray (processHitBwd, gaussianParticles.cuh:520-532)
+                const float pcx = ray.ox - r0.w, pcy = ray.oy - r1.w, pcz = ray.oz - r2.w;              // gposc
+                const float prx = r0.x * pcx + r0.y * pcy + r0.z * pcz;                                   // gposcr
+                const float pry = r1.x * pcx + r1.y * pcy + r1.z * pcz;
+                const float prz = r2.x * pcx + r2.y * pcy + r2.z * pcz;
+                const float gox = is.x * prx, goy = is.y * pry, goz = is.z * prz;                         // gro
+                const float drx = r0.x * ray.dx + r0.y * ray.dy + r0.z * ray.dz;                          // rayDirR
+                const float dry = r1.x * ray.dx + r1.y * ray.dy + r1.z * ray.dz;
+                const float drz = r2.x * ray.dx + r2.y * ray.dy + r2.z * ray.dz;
+                const float ux = is.x * drx, uy = is.y * dry, uz = is.z * drz;                            // grdu
+                const float l = ux * ux + uy * uy + uz * uz;
+                const float il = l > 0.f ? rsqrtf(l) : 1.f;
+                const float gdx = ux * il, gdy = uy * il, gdz = uz * il;                                  // grd
+                const float ccx = gdy * goz - gdz * goy, ccy = gdz * gox - gdx * goz, ccz = gdx * goy - gdy * gox;  // gcrod
+                const float gray = ccx * ccx + ccy * ccy + ccz * ccz;
+                const float gres = kernel_response<DEG>(gray);
+                const float dns = sc.w;
+                const float alpha = fminf(cfg.max_alpha, gres * dns);
+                if ((gres > cfg.min_kernel_density) && (alpha > cfg.min_alpha)) {
+                    hit = true;
+                    const float4 cl = sm.cl[j];
+                    const float pd = -(gdx * gox + gdy * goy + gdz * goz);
+                    const float ddx = gdx * pd, ddy = gdy * pd, ddz = gdz * pd;                            // grdd
+                    const float hx = sc.x * ddx, hy = sc.y * ddy, hz = sc.z * ddz;                         // grds
+                    const float gsq = hx * hx + hy * hy + hz * hz;
+                    const float gdist = sqrtf(gsq);
+                    const float weight = alpha * T;
+                    const float nextT = (1.f - alpha) * T;
+                    const bool last = nextT <= cfg.min_transmittance;
+                    const float inv_next = last ? 0.f : 1.0f / nextT;
+
+                    // depth branch (:545-580)
+                    D += weight * gdist;
+                    const float resD = fmaxf((Dint - D) * inv_next, 0.f);
+                    const float a_hit = (gdist - resD) * T * Dgrad;
+                    const float hs = gsq > 0.f ? (weight / gdist) * Dgrad : 0.f;
+                    const float hgx = hx * hs, hgy = hy * hs, hgz = hz * hs;                               // grdsRayHitGrd
+                    const float sd = hgx * sc.x * gdx + hgy * sc.y * gdy + hgz * sc.z * gdz;               // grdScaledDot
+                    // opacity branch (:586-587)
+                    const float resT = alpha < 0.999999f ? Tint / (1.f - alpha) : T;
+                    const float a_dns = resT * -Tgrad;
+                    // radiance branch (:602-612)
+                    g[12] = Cgx * weight; g[13] = Cgy * weight; g[14] = Cgz * weight;
+                    Cx += weight * cl.x; Cy += weight * cl.y; Cz += weight * cl.z;
+                    const float rcx = fmaxf((Cix - Cx) * inv_next, 0.f);
+                    const float rcy = fmaxf((Ciy - Cy) * inv_next, 0.f);
+                    const float rcz = fmaxf((Ciz - Cz) * inv_next, 0.f);
+                    const float common = a_hit + a_dns + T * (cl.x - rcx) * Cgx + T * (cl.y - rcy) * Cgy + T * (cl.z - rcz) * Cgz;
+                    g[3] = gres * common;                                                                 // d density (:624-627)
+                    const float gray_g = kernel_response_grad<DEG>(gray, gres, dns * common);             // (:639-648)
+                    // gray = |grd x gro|^2  (:684-702)
+                    const float kx = 2.f * ccx * gray_g, ky = 2.f * ccy * gray_g, kz = 2.f * ccz * gray_g;  // gcrodGrd
+                    const float gd_gx = kz * goy - ky * goz + (sc.x * hgx * pd - gox * sd);                 // grdGrd + grdRayHitGrd
+                    const float gd_gy = kx * goz - kz * gox + (sc.y * hgy * pd - goy * sd);
+                    const float gd_gz = ky * gox - kx * goy + (sc.z * hgz * pd - goz * sd);
+                    const float go_gx = ky * gdz - kz * gdy - gdx * sd;                                     // groGrd + groRayHitGrd
+                    const float go_gy = kz * gdx - kx * gdz - gdy * sd;
+                    const float go_gz = kx * gdy - ky * gdx - gdz * sd;
+                    // gro = (1/s) gposcr  (:705-713)
+                    const float prg_x = is.x * go_gx, prg_y = is.y * go_gy, prg_z = is.z * go_gz;          // gposcrGrd
+                    float sgx = ddx * hgx - prx * is.x * is.x * go_gx;                                      // gsclRayHitGrd + gsclGrdGro
+                    float sgy = ddy * hgy - pry * is.y * is.y * go_gy;
+                    float sgz = ddz * hgz - prz * is.z * is.z * go_gz;
+                    // gposcr = R^T gposc  (:715-726)
+                    g[0] = -(prg_x * r0.x + prg_y * r1.x + prg_z * r2.x);
+                    g[1] = -(prg_x * r0.y + prg_y * r1.y + prg_z * r2.y);
+                    g[2] = -(prg_x * r0.z + prg_y * r1.z + prg_z * r2.z);
+                    // grd = normalize(grdu)  (:729-731, safe_normalize_bw mathUtils.cuh:410-420)
+                    const float il3 = il * il * il;
+                    const float du = gd_gx * ux + gd_gy * uy + gd_gz * uz;
+                    const float ug_x = l > 0.f ? il * gd_gx - il3 * ux * du : 0.f;                          // grduGrd
+                    const float ug_y = l > 0.f ? il * gd_gy - il3 * uy * du : 0.f;
+                    const float ug_z = l > 0.f ? il * gd_gz - il3 * uz * du : 0.f;
+                    // grdu = (1/s) rayDirR  (:733-738)
+                    sgx -= drx * is.x * is.x * ug_x;
+                    sgy -= dry * is.y * is.y * ug_y;
+                    sgz -= drz * is.z * is.z * ug_z;
+                    g[8] = sgx; g[9] = sgy; g[10] = sgz;
+                    const float rdg_x = is.x * ug_x, rdg_y = is.y * ug_y, rdg_z = is.z * ug_z;             // rayDirRGrd
+                    // rotation rows m_i receive dM_i = prg_i * gposc + rdg_i * d   (matmul_bw_quat twice, :719-747)
+                    const float m00 = prg_x * pcx + rdg_x * ray.dx, m01 = prg_x * pcy + rdg_x * ray.dy, m02 = prg_x * pcz + rdg_x * ray.dz;
+                    const float m10 = prg_y * pcx + rdg_y * ray.dx, m11 = prg_y * pcy + rdg_y * ray.dy, m12 = prg_y * pcz + rdg_y * ray.dz;
+                    const float m20 = prg_z * pcx + rdg_z * ray.dx, m21 = prg_z * pcy + rdg_z * ray.dy, m22 = prg_z * pcz + rdg_z * ray.dz;
+                    const float4 q = sm.qt[j];
+                    const float qr = q.x, qx = q.y, qy = q.z, qz = q.w;
+                    g[4] = 2.f * (qz * (m01 - m10) + qy * (m20 - m02) + qx * (m12 - m21));
+                    g[5] = 2.f * (qy * (m01 + m10) + qz * (m02 + m20) + qr * (m12 - m21)) - 4.f * qx * (m11 + m22);
+                    g[6] = 2.f * (qx * (m01 + m10) + qr * (m20 - m02) + qz * (m12 + m21)) - 4.f * qy * (m00 + m22);
+                    g[7] = 2.f * (qr * (m01 - m10) + qx * (m02 + m20) + qy * (m12 + m21)) - 4.f * qz * (m00 + m11);
+                    T = nextT;
+                    if (T < cfg.min_transmittance) alive = false;
+                }
+            }
+            if (__any_sync(kFull, hit)) {
+                const float total = warp_transpose_reduce16(g, lane);
+                if ((lane & 1) == 0) {
+                    const uint32_t idx = __float_as_uint(sm.cl[j].w);
+                    atomicAdd(grad_acc + static_cast<size_t>(idx) * kGradRow + (lane >> 1), total);
+                }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// G8 per-particle SH adjoint + emission of the final gradient rows; re-zeroes the accumulator for the next frame.
+
+constexpr float kC0 = 0.28209479177387814f;
+constexpr float kC1 = 0.4886025119029199f;
+__constant__ float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
+                             0.5462742152960396f};
+__constant__ float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                             -0.4570457994644658f, 1.445305721320277f,  -0.5900435899266435f};
+
+__global__ void __launch_bounds__(128) project_backward_kernel(FrameCamera cam, int64_t n, const float* __restrict__ particles,
+                                                               const float* __restrict__ sph, int deg, const float* __restrict__ rgb,
+                                                               const uint32_t* __restrict__ tiles_count, float* __restrict__ grad_acc,
+                                                               float* __restrict__ d_particles, float* __restrict__ d_sph) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4* acc4 = reinterpret_cast<float4*>(grad_acc + i * kGradRow);
+    const float4 a0 = acc4[0], a1 = acc4[1], a2 = acc4[2], a3 = acc4[3];
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc4[0] = zero; acc4[1] = zero; acc4[2] = zero; acc4[3] = zero;
+
+    float dpx = a0.x, dpy = a0.y, dpz = a0.z;
+    float4* ds4 = reinterpret_cast<float4*>(d_sph + i * 48);
+    if (tiles_count[i] == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) ds4[k] = zero;
+    } else {
+        // incident direction = normalize(position - sensor position) (gutProjector.cuh:418)
+        const float4 p = __ldg(reinterpret_cast<const float4*>(particles + i * 12));
+        const float vx = p.x - cam.cam_pos[0], vy = p.y - cam.cam_pos[1], vz = p.z - cam.cam_pos[2];
+        const float len = sqrtf(vx * vx + vy * vy + vz * vz);
+        const float inv_len = len > 0.f ? 1.0f / len : 0.f;
+        const float x = len > 0.f ? vx * inv_len : 1.f, y = vy * inv_len, z = vz * inv_len;
+        // clamp mask of max(f + 0.5, 0) (sphericalHarmonics.slang:63); rgb holds the unclamped f + 0.5
+        const float mgr = rgb[i * 3 + 0] > 0.f ? a3.x : 0.f;
+        const float mgg = rgb[i * 3 + 1] > 0.f ? a3.y : 0.f;
+        const float mgb = rgb[i * 3 + 2] > 0.f ? a3.z : 0.f;
+        float b[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) b[k] = 0.f;
+        b[0] = kC0;
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        if (deg > 0) {
+            b[1] = -kC1 * y; b[2] = kC1 * z; b[3] = -kC1 * x;
+            if (deg > 1) {
+                b[4] = kC2[0] * xy; b[5] = kC2[1] * yz; b[6] = kC2[2] * (2.0f * zz - xx - yy); b[7] = kC2[3] * xz; b[8] = kC2[4] * (xx - yy);
+                if (deg > 2) {
+                    b[9] = kC3[0] * y * (3.0f * xx - yy);
+                    b[10] = kC3[1] * xy * z;
+                    b[11] = kC3[2] * y * (4.0f * zz - xx - yy);
+                    b[12] = kC3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                    b[13] = kC3[4] * x * (4.0f * zz - xx - yy);
+                    b[14] = kC3[5] * z * (xx - yy);
+                    b[15] = kC3[6] * x * (xx - 3.0f * yy);
+                }
+            }
+        }
+        float o[48];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            o[k * 3 + 0] = b[k] * mgr;
+            o[k * 3 + 1] = b[k] * mgg;
+            o[k * 3 + 2] = b[k] * mgb;
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) ds4[k] = make_float4(o[k * 4], o[k * 4 + 1], o[k * 4 + 2], o[k * 4 + 3]);
+
+        // d(rgb)/d(direction) . masked gradient, then through normalize (gaussianParticles.slang:545-558)
+        if (deg > 0 && len > 0.f) {
+            float cf[48];
+            const float4* c4 = reinterpret_cast<const float4*>(sph + i * 48);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const float4 v = __ldg(c4 + k);
+                cf[k * 4] = v.x; cf[k * 4 + 1] = v.y; cf[k * 4 + 2] = v.z; cf[k * 4 + 3] = v.w;
+            }
+            // s[j] = sum_c coeff[j][c] * masked_grad[c]
+            float s[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) s[k] = cf[k * 3] * mgr + cf[k * 3 + 1] * mgg + cf[k * 3 + 2] * mgb;
+            float gx = -kC1 * s[3], gy = -kC1 * s[1], gz = kC1 * s[2];
+            if (deg > 1) {
+                gx += kC2[0] * y * s[4] + kC2[2] * (-2.f * x) * s[6] + kC2[3] * z * s[7] + kC2[4] * (2.f * x) * s[8];
+                gy += kC2[0] * x * s[4] + kC2[1] * z * s[5] + kC2[2] * (-2.f * y) * s[6] + kC2[4] * (-2.f * y) * s[8];
+                gz += kC2[1] * y * s[5] + kC2[2] * (4.f * z) * s[6] + kC2[3] * x * s[7];
+                if (deg > 2) {
+                    gx += kC3[0] * (6.f * xy) * s[9] + kC3[1] * yz * s[10] + kC3[2] * (-2.f * xy) * s[11] + kC3[3] * (-6.f * xz) * s[12] +
+                          kC3[4] * (4.f * zz - 3.f * xx - yy) * s[13] + kC3[5] * (2.f * xz) * s[14] + kC3[6] * (3.f * xx - 3.f * yy) * s[15];
+                    gy += kC3[0] * (3.f * xx - 3.f * yy) * s[9] + kC3[1] * xz * s[10] + kC3[2] * (4.f * zz - xx - 3.f * yy) * s[11] +
+                          kC3[3] * (-6.f * yz) * s[12] + kC3[4] * (-2.f * xy) * s[13] + kC3[5] * (-2.f * yz) * s[14] + kC3[6] * (-6.f * xy) * s[15];
+                    gz += kC3[1] * xy * s[10] + kC3[2] * (8.f * yz) * s[11] + kC3[3] * (6.f * zz - 3.f * xx - 3.f * yy) * s[12] +
+                          kC3[4] * (8.f * xz) * s[13] + kC3[5] * (xx - yy) * s[14];
+                }
+            }
+            const float dd = x * gx + y * gy + z * gz;
+            dpx += (gx - x * dd) * inv_len;
+            dpy += (gy - y * dd) * inv_len;
+            dpz += (gz - z * dd) * inv_len;
+        }
+    }
+    float4* dp4 = reinterpret_cast<float4*>(d_particles + i * 12);
+    dp4[0] = make_float4(dpx, dpy, dpz, a0.w);
+    dp4[1] = a1;
+    dp4[2] = make_float4(a2.x, a2.y, a2.z, 0.f);
+}
+
+}  // namespace
+
+void launch_render_forward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
+                           const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
+                           const uint32_t* ranges, float* out_rgba, float* out_dist, float* out_hits) {
+    const dim3 grid(cam.grid_x, cam.grid_y, 1), block(kTile, kTile, 1);
+    if (cfg.kernel_degree == 4)
+        render_forward_kernel<4><<<grid, block, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, out_rgba, out_dist, out_hits);
+    else
+        render_forward_kernel<2><<<grid, block, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, out_rgba, out_dist, out_hits);
+}
+
+void launch_render_backward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
+                            const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
+                            const uint32_t* ranges, const float* out_rgba, const float* d_rgba, const float* out_dist,
+                            const float* d_dist, float* grad_acc) {
+    const dim3 grid(cam.grid_x, cam.grid_y, 1), block(kTile, kTile, 1);
+    if (cfg.kernel_degree == 4)
+        render_backward_kernel<4><<<grid, block, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, out_rgba, d_rgba, out_dist, d_dist, grad_acc);
+    else
+        render_backward_kernel<2><<<grid, block, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, out_rgba, d_rgba, out_dist, d_dist, grad_acc);
+}
+
+void launch_project_backward(cudaStream_t s, const FrameCamera& cam, int64_t n, const float* particles, const float* sph,
+                             int sph_degree, const float* rgb, const uint32_t* tiles_count, float* grad_acc, float* d_particles,
+                             float* d_sph) {
+    if (n <= 0) return;
+    const unsigned blocks = static_cast<unsigned>((n + 127) / 128);
+    project_backward_kernel<<<blocks, 128, 0, s>>>(cam, n, particles, sph, sph_degree, rgb, tiles_count, grad_acc, d_particles, d_sph);
+}
+
+}  // namespace gutb200

@@ -1,0 +1,37 @@
+// 3dgrut_b200/csrc/gut_sort.cu -- G2 prefix sum and G4 (tile,depth) key sort.
+//
+// Round-1 status: these two stages call CUB (header-only CCCL shipped with the CUDA toolkit), exactly the
+// library calls the reference makes (threedgut_tracer/src/gutRenderer.cu:303,356-365); they are LIBRARY code,
+// not counted as ours.  DESIGN.md section 6 describes the planned replacement (depth-sort particles once,
+// then a 2-pass stable tile split over the intersections).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "gut_common.cuh"
+
+namespace gutb200 {
+
+size_t scan_temp_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, bytes, static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                  static_cast<int>(n));
+    return bytes;
+}
+
+void run_inclusive_scan(cudaStream_t s, void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, int64_t n) {
+    cub::DeviceScan::InclusiveSum(temp, temp_bytes, in, out, static_cast<int>(n), s);
+}
+
+size_t sort_temp_bytes(int64_t n, int end_bit) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<const uint64_t*>(nullptr), static_cast<uint64_t*>(nullptr),
+                                    static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), n, 0, end_bit);
+    return bytes;
+}
+
+void run_sort_pairs(cudaStream_t s, void* temp, size_t temp_bytes, const uint64_t* kin, uint64_t* kout, const uint32_t* vin,
+                    uint32_t* vout, int64_t n, int end_bit) {
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, n, 0, end_bit, s);
+}
+
+}  // namespace gutb200

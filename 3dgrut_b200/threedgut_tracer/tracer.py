@@ -1,0 +1,313 @@
+"""Host-side mirror of the reference's 3DGUT tracer surface, backed by libgut_b200.so.
+
+Same names, argument meaning and tensor contracts as the reference:
+  Tracer / Tracer._Autograd            threedgut_tracer/tracer.py:158-349
+  SplatRaster{trace,trace_bwd,collect_times}   threedgut_tracer/bindings.cpp:103-109, src/splatRaster.cpp:184-382
+  fromOpenCVPinholeCameraModelParameters, ShutterType            threedgut_tracer/bindings.cpp:34-101
+PyTorch is used for device memory, streams and autograd only; every kernel is ours (csrc/*.cu).
+"""
+from __future__ import annotations
+
+import enum
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+import b200_native as native
+
+
+class ShutterType(enum.IntEnum):  # bindings.cpp:36-42
+    ROLLING_TOP_TO_BOTTOM = 0
+    ROLLING_LEFT_TO_RIGHT = 1
+    ROLLING_BOTTOM_TO_TOP = 2
+    ROLLING_RIGHT_TO_LEFT = 3
+    GLOBAL = 4
+
+
+@dataclass
+class CameraModelParameters:
+    resolution: np.ndarray
+    shutter_type: ShutterType
+    principal_point: np.ndarray
+    focal_length: np.ndarray
+    radial_coeffs: np.ndarray
+    tangential_coeffs: np.ndarray
+    thin_prism_coeffs: np.ndarray
+
+
+def fromOpenCVPinholeCameraModelParameters(resolution, shutter_type, principal_point, focal_length, radial_coeffs,
+                                            tangential_coeffs, thin_prism_coeffs) -> CameraModelParameters:
+    """bindings.cpp:50-66"""
+    if ShutterType(shutter_type) != ShutterType.GLOBAL:
+        raise NotImplementedError("rolling-shutter projection is not built yet (SURVEY 8f row 4); global shutter only")
+    f32 = lambda a, n: np.asarray(a, dtype=np.float32).reshape(n)  # noqa: E731
+    return CameraModelParameters(np.asarray(resolution, dtype=np.int64).reshape(2), ShutterType(shutter_type), f32(principal_point, 2),
+                                 f32(focal_length, 2), f32(radial_coeffs, 6), f32(tangential_coeffs, 2), f32(thin_prism_coeffs, 4))
+
+
+@dataclass
+class SensorPose3D:  # tracer.py:55-58
+    T_world_sensors: list  # two [t.xyz, q.xyzw] world->sensor poses (shutter open / close)
+    timestamps_us: list
+
+
+def _so3_matrix_to_quat_xyzw(R: np.ndarray) -> np.ndarray:
+    """tracer.py:88-136"""
+    R = np.asarray(R, dtype=np.float64)
+    d = np.array([R[0, 0], R[1, 1], R[2, 2], R[0, 0] + R[1, 1] + R[2, 2]])
+    c = int(np.argmax(d))
+    q = np.zeros(4)
+    if c != 3:
+        i, j, k = c, (c + 1) % 3, (c + 2) % 3
+        q[i] = 1 - d[3] + 2 * R[i, i]
+        q[j] = R[j, i] + R[i, j]
+        q[k] = R[k, i] + R[i, k]
+        q[3] = R[k, j] - R[j, k]
+    else:
+        q[0] = R[2, 1] - R[1, 2]
+        q[1] = R[0, 2] - R[2, 0]
+        q[2] = R[1, 0] - R[0, 1]
+        q[3] = 1 + d[3]
+    return (q / np.linalg.norm(q)).astype(np.float32)
+
+
+def _cfg_get(conf, path, default):
+    cur = conf
+    for key in path.split("."):
+        if cur is None:
+            return default
+        if isinstance(cur, dict):
+            cur = cur.get(key, None)
+        else:
+            cur = getattr(cur, key, None)
+    return default if cur is None else cur
+
+
+def _native_config(conf) -> native.Config:
+    """Config -> what the reference bakes in as -D constants (setup_3dgut.py:64-95)."""
+    cfg = native.default_config()
+    cfg.kernel_degree = int(_cfg_get(conf, "render.particle_kernel_degree", 2))
+    cfg.min_kernel_density = float(_cfg_get(conf, "render.particle_kernel_min_response", 0.0113))
+    cfg.min_alpha = float(_cfg_get(conf, "render.particle_kernel_min_alpha", 1.0 / 255.0))
+    cfg.max_alpha = float(_cfg_get(conf, "render.particle_kernel_max_alpha", 0.99))
+    cfg.min_transmittance = float(_cfg_get(conf, "render.min_transmittance", 0.0001))
+    a = float(_cfg_get(conf, "render.splat.ut_alpha", 1.0))
+    k = float(_cfg_get(conf, "render.splat.ut_kappa", 0.0))
+    cfg.ut_alpha, cfg.ut_beta, cfg.ut_kappa = a, float(_cfg_get(conf, "render.splat.ut_beta", 2.0)), k
+    cfg.ut_delta = math.sqrt(a * a * (3 + k))
+    cfg.ut_margin = float(_cfg_get(conf, "render.splat.ut_in_image_margin_factor", 0.1))
+    cfg.rect_bounding = int(bool(_cfg_get(conf, "render.splat.rect_bounding", True)))
+    cfg.tight_opacity_bounding = int(bool(_cfg_get(conf, "render.splat.tight_opacity_bounding", True)))
+    cfg.tile_culling = int(bool(_cfg_get(conf, "render.splat.tile_based_culling", True)))
+    cfg.global_z_order = int(bool(_cfg_get(conf, "render.splat.global_z_order", True)))
+    cfg.enable_timings = int(bool(_cfg_get(conf, "render.enable_kernel_timings", False)))
+    if int(_cfg_get(conf, "render.splat.k_buffer_size", 0)) != 0:
+        raise NotImplementedError("k_buffer_size > 0 (sorted 3DGUT) is not built yet (SURVEY 8f row 4)")
+    if int(_cfg_get(conf, "render.particle_radiance_sph_degree", 3)) != 3:
+        raise NotImplementedError("this build stores 16 SH coefficients per particle (particle_radiance_sph_degree=3)")
+    return cfg
+
+
+def _ptr(t: torch.Tensor) -> int:
+    return t.data_ptr()
+
+
+class SplatRaster:
+    """Python twin of the pybind class lib3dgut_cc.SplatRaster (bindings.cpp:103-109)."""
+
+    def __init__(self, conf):
+        if not torch.cuda.is_available():
+            raise RuntimeError("threedgut_tracer (B200): CUDA device required; there is no CPU path")
+        self._cfg = _native_config(conf)
+        self._ctx = {}  # one native context per device, like one SplatRaster per process/GPU in the reference
+
+    def _context(self, device: torch.device) -> native.Context:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx not in self._ctx:
+            self._ctx[idx] = native.Context(self._cfg, idx)
+        return self._ctx[idx]
+
+    @staticmethod
+    def _camera(sensor: CameraModelParameters, pose_start, pose_end, width: int, height: int) -> native.Camera:
+        cam = native.Camera()
+        cam.width, cam.height = int(width), int(height)
+        cam.principal[:] = [float(v) for v in sensor.principal_point]
+        cam.focal[:] = [float(v) for v in sensor.focal_length]
+        cam.radial[:] = [float(v) for v in sensor.radial_coeffs]
+        cam.tangential[:] = [float(v) for v in sensor.tangential_coeffs]
+        cam.thin_prism[:] = [float(v) for v in sensor.thin_prism_coeffs]
+        cam.pose_start[:] = [float(v) for v in pose_start]  # .cpu() as in toSensorState (splatRaster.cpp:108-116)
+        cam.pose_end[:] = [float(v) for v in pose_end]
+        return cam
+
+    def trace(self, frame_id, n_active_features, particle_density, particle_radiance, ray_ori, ray_dir, ray_time, sensor_params,
+              timestamp_start, timestamp_end, pose_start, pose_end):
+        """splatRaster.cpp:184-262 -> (feat+alpha [H,W,4], dist [H,W,1], hits [H,W,1], visibility [N,1])"""
+        dev = ray_ori.device
+        h, w = int(ray_ori.shape[1]), int(ray_ori.shape[2])
+        n = int(particle_density.shape[0])
+        particle_density = particle_density.contiguous()
+        particle_radiance = particle_radiance.contiguous()
+        ray_ori, ray_dir = ray_ori.contiguous(), ray_dir.contiguous()
+        for t in (particle_density, particle_radiance, ray_ori, ray_dir):
+            if t.dtype != torch.float32 or not t.is_cuda:
+                raise RuntimeError("trace: tensors must be float32 CUDA tensors")
+        rgba = torch.empty((h, w, 4), dtype=torch.float32, device=dev)
+        dist = torch.empty((h, w, 1), dtype=torch.float32, device=dev)
+        hits = torch.empty((h, w, 1), dtype=torch.float32, device=dev)
+        vis = torch.empty((n, 1), dtype=torch.float32, device=dev)
+        cam = self._camera(sensor_params, pose_start, pose_end, w, h)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._context(dev).forward(stream, cam, n, _ptr(particle_density), _ptr(particle_radiance), int(n_active_features),
+                                   _ptr(ray_ori), _ptr(ray_dir), _ptr(rgba), _ptr(dist), _ptr(hits), _ptr(vis))
+        return rgba, dist, hits, vis
+
+    def trace_bwd(self, frame_id, n_active_features, particle_density, particle_radiance, ray_ori, ray_dir, ray_time, sensor_params,
+                  timestamp_start, timestamp_end, pose_start, pose_end, ray_radiance_density, ray_radiance_density_grd,
+                  ray_hit_distance, ray_hit_distance_grd):
+        """splatRaster.cpp:264-350 -> (dDensity [N,12], dRadiance [N,48])"""
+        dev = ray_ori.device
+        h, w = int(ray_ori.shape[1]), int(ray_ori.shape[2])
+        n = int(particle_density.shape[0])
+        particle_density = particle_density.contiguous()
+        particle_radiance = particle_radiance.contiguous()
+        ray_ori, ray_dir = ray_ori.contiguous(), ray_dir.contiguous()
+        rgba, d_rgba = ray_radiance_density.contiguous(), ray_radiance_density_grd.contiguous().float()
+        dist, d_dist = ray_hit_distance.contiguous(), ray_hit_distance_grd.contiguous().float()
+        d_density = torch.empty((n, 12), dtype=torch.float32, device=dev)
+        d_radiance = torch.empty((n, 48), dtype=torch.float32, device=dev)
+        cam = self._camera(sensor_params, pose_start, pose_end, w, h)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._context(dev).backward(stream, cam, n, _ptr(particle_density), _ptr(particle_radiance), int(n_active_features),
+                                    _ptr(ray_ori), _ptr(ray_dir), _ptr(rgba), _ptr(d_rgba), _ptr(dist), _ptr(d_dist),
+                                    _ptr(d_density), _ptr(d_radiance))
+        return d_density, d_radiance
+
+    def collect_times(self):
+        """splatRaster.cpp:352-382: mean ms of the timers recorded since the last call"""
+        out = {}
+        for ctx in self._ctx.values():
+            f, b = ctx.collect_times()
+            if f > 0:
+                out["forward_render"] = f
+            if b > 0:
+                out["backward_render"] = b
+        return out
+
+    def native_context(self, device=None) -> native.Context:
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        return self._context(dev)
+
+
+class Tracer:
+    class _Autograd(torch.autograd.Function):
+        """tracer.py:159-286 (argument list and returned tensors are identical)"""
+
+        @staticmethod
+        def forward(ctx, tracer_wrapper, frame_id, n_active_features, ray_ori, ray_dir, mog_pos, mog_rot, mog_scl, mog_dns, mog_sph,
+                    sensor_params, sensor_poses):
+            particle_density = torch.concat([mog_pos, mog_dns, mog_rot, mog_scl, torch.zeros_like(mog_dns)], dim=1).contiguous()
+            particle_features = mog_sph.contiguous()
+            ray_features_density, ray_hit_distance, ray_hit_count, mog_visibility = tracer_wrapper.trace(
+                frame_id, n_active_features, particle_density, particle_features, ray_ori.contiguous(), ray_dir.contiguous(), None,
+                sensor_params, sensor_poses.timestamps_us[0], sensor_poses.timestamps_us[1], sensor_poses.T_world_sensors[0],
+                sensor_poses.T_world_sensors[1])
+            ctx.save_for_backward(ray_ori, ray_dir, ray_features_density, ray_hit_distance, particle_density, particle_features)
+            ctx.frame_id = frame_id
+            ctx.n_active_features = n_active_features
+            ctx.sensor_params = sensor_params
+            ctx.sensor_poses = sensor_poses
+            ctx.tracer_wrapper = tracer_wrapper
+            return ray_features_density, ray_hit_distance, ray_hit_count, mog_visibility
+
+        @staticmethod
+        def backward(ctx, ray_features_density_grd, ray_hit_distance_grd, ray_hit_count_grd_UNUSED, mog_visibility_grd_UNUSED):
+            ray_ori, ray_dir, ray_features_density, ray_hit_distance, particle_density, particle_features = ctx.saved_tensors
+            sensor_poses = ctx.sensor_poses
+            particle_density_grd, particle_features_grd = ctx.tracer_wrapper.trace_bwd(
+                ctx.frame_id, ctx.n_active_features, particle_density, particle_features, ray_ori, ray_dir, None, ctx.sensor_params,
+                sensor_poses.timestamps_us[0], sensor_poses.timestamps_us[1], sensor_poses.T_world_sensors[0],
+                sensor_poses.T_world_sensors[1], ray_features_density, ray_features_density_grd, ray_hit_distance, ray_hit_distance_grd)
+            mog_pos_grd, mog_dns_grd, mog_rot_grd, mog_scl_grd, _ = torch.split(particle_density_grd, [3, 1, 4, 3, 1], dim=1)
+            return (None, None, None, None, None, mog_pos_grd.contiguous(), mog_rot_grd.contiguous(), mog_scl_grd.contiguous(),
+                    mog_dns_grd.contiguous(), particle_features_grd.contiguous(), None, None)
+
+    def __init__(self, conf):
+        self.device = "cuda"
+        self.conf = conf
+        torch.zeros(1, device=self.device)  # force the CUDA context, as the reference does (tracer.py:292)
+        self.tracer_wrapper = SplatRaster(conf)
+
+    @property
+    def timings(self):
+        return self.tracer_wrapper.collect_times()
+
+    def build_acc(self, gaussians, rebuild=True):
+        pass  # no-op for 3DGUT (tracer.py:301)
+
+    def render(self, gaussians, gpu_batch, train=False, frame_id=0):
+        """tracer.py:304-349"""
+        rays_o, rays_d = gpu_batch.rays_ori, gpu_batch.rays_dir
+        sensor, poses = Tracer._create_camera_parameters(gpu_batch)
+        pred_features_alpha, pred_dist, hits_count, mog_visibility = Tracer._Autograd.apply(
+            self.tracer_wrapper, frame_id, gaussians.n_active_features, rays_o.contiguous(), rays_d.contiguous(),
+            gaussians.positions.contiguous(), gaussians.get_rotation().contiguous(), gaussians.get_scale().contiguous(),
+            gaussians.get_density().contiguous(), gaussians.get_features().contiguous(), sensor, poses)
+        ray_feature_dim = getattr(gaussians, "ray_feature_dim", 3)
+        pred_features = pred_features_alpha[..., :ray_feature_dim].unsqueeze(0).contiguous()
+        pred_opacity = pred_features_alpha[..., ray_feature_dim:].unsqueeze(0).contiguous()
+        timings = self.tracer_wrapper.collect_times()
+        return {
+            "pred_features": pred_features,
+            "pred_opacity": pred_opacity,
+            "pred_dist": pred_dist.unsqueeze(0).contiguous(),
+            "pred_normals": torch.nn.functional.normalize(torch.ones_like(pred_features), dim=3),
+            "hits_count": hits_count.unsqueeze(0).contiguous(),
+            "frame_time_ms": timings["forward_render"] if "forward_render" in timings else 0.0,
+            "mog_visibility": mog_visibility,
+        }
+
+    @staticmethod
+    def _pose_from_c2w(pose) -> np.ndarray:
+        """tracer.py:404-423 + 360-380: C2W -> world->sensor [t, q.xyzw]"""
+        p = pose.detach().cpu().numpy() if isinstance(pose, torch.Tensor) else np.asarray(pose)
+        C2W = np.concatenate((p[:3, :4].astype(np.float64), np.zeros((1, 4))))
+        C2W[3, 3] = 1.0
+        W2C = np.linalg.inv(C2W)
+        return np.concatenate([W2C[:3, 3].astype(np.float32), _so3_matrix_to_quat_xyzw(np.float32(W2C[:3, :3]))]).astype(np.float32)
+
+    @staticmethod
+    def _create_camera_parameters(gpu_batch):
+        """tracer.py:383-488 (pinhole branches; fisheye / f-theta are a later row of SURVEY 8f)"""
+        if getattr(gpu_batch, "rays_in_world_space", False):
+            pose_start = pose_end = np.array([0, 0, 0, 0, 0, 0, 1], dtype=np.float32)
+        else:
+            start = gpu_batch.T_to_world.squeeze()
+            assert start.ndim == 2
+            end = gpu_batch.T_to_world_end.squeeze() if getattr(gpu_batch, "T_to_world_end", None) is not None else start
+            pose_start, pose_end = Tracer._pose_from_c2w(start), Tracer._pose_from_c2w(end)
+        poses = SensorPose3D(T_world_sensors=[pose_start, pose_end], timestamps_us=[0, 1])
+        K = getattr(gpu_batch, "intrinsics", None)
+        if K is not None:
+            focalx, focaly, cx, cy = float(K[0]), float(K[1]), float(K[2]), float(K[3])
+            orig_w, orig_h = int(2 * cx), int(2 * cy)
+            fovx, fovy = 2 * math.atan(orig_w / (2 * focalx)), 2 * math.atan(orig_h / (2 * focaly))
+            sensor = fromOpenCVPinholeCameraModelParameters(
+                resolution=np.array([orig_w, orig_h], dtype=np.uint32), shutter_type=ShutterType.GLOBAL,
+                principal_point=np.array([orig_w, orig_h], dtype=np.float32) / 2,
+                focal_length=np.array([orig_w / (2.0 * math.tan(fovx * 0.5)), orig_h / (2.0 * math.tan(fovy * 0.5))], dtype=np.float32),
+                radial_coeffs=np.zeros((6,), dtype=np.float32), tangential_coeffs=np.zeros((2,), dtype=np.float32),
+                thin_prism_coeffs=np.zeros((4,), dtype=np.float32))
+            return sensor, poses
+        K = getattr(gpu_batch, "intrinsics_OpenCVPinholeCameraModelParameters", None)
+        if K is not None:
+            shutter = K["shutter_type"]
+            shutter = ShutterType[shutter] if isinstance(shutter, str) else ShutterType(shutter)
+            sensor = fromOpenCVPinholeCameraModelParameters(
+                resolution=K["resolution"], shutter_type=shutter, principal_point=K["principal_point"], focal_length=K["focal_length"],
+                radial_coeffs=K["radial_coeffs"], tangential_coeffs=K["tangential_coeffs"],
+                thin_prism_coeffs=K.get("thin_prism_coeffs", np.zeros((4,), dtype=np.float32)))
+            return sensor, poses
+        raise ValueError("Camera intrinsics unavailable or unsupported (pinhole models only in this build)")

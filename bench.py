@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- train frames/s (forward + backward render) of the B200-native 3DGUT path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c3|c1]
+
+One "step" = one view rendered forward + backward (trace + trace_bwd with dL/d(RGBA, dist) given) over the
+synthetic scene of BASELINE.json `configs[1]` (lego-like: 800x800, 300k Gaussians, 3DGUT) at N=1.  With N>1 every
+rank renders a different camera of the same replicated scene and the per-Gaussian gradients ([N,12]+[N,48] fp32)
+are summed with one NCCL all-reduce per step (view-parallel training); scaling is weak.
+
+Prints ONE JSON line (rank 0).  `value` = device-timed frames/s with inputs resident in HBM; `e2e` = the same
+metric through the public API (threedgut_tracer.Tracer.render + loss.backward) with the step's camera batch coming
+from pinned host memory and the loss read back; `roofline` is for the dominant kernel of the step;
+`cpu_baseline` is the CPU oracle (oracle/gut_oracle.c) on a bounded sample.
+
+--impl reference: the reference has no CPU implementation and its CUDA build cannot be produced in this image
+(needs slangc); per the tier rules this arm times the CPU port (oracle/) of the reference algorithm
+on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "3dgrut_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "train frames/sec (fwd+bwd render)"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_scene(workload: str):
+    import scenes
+
+    if workload == "c1":
+        return scenes.scene_c1()
+    if workload == "c3":
+        return scenes.scene_c3()
+    if workload.startswith("c2:"):  # c2:<n> -- reduced particle count, debugging only
+        return scenes.scene_c2(n=int(workload.split(":")[1]))
+    return scenes.scene_c2()
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_frames_per_s(sc, tile_stride: int, frames: int = 1, warm: int = 0):
+    """Frames/s of the CPU port (oracle) on a bounded sample: projection + binning in full, compositing
+    forward/backward on every `tile_stride`-th tile, extrapolated to the whole frame."""
+    from oracle import gut_oracle as go
+    import scenes
+
+    cfg = go.default_config()
+    ro, rd = sc.rays()
+    rng = np.random.default_rng(0)
+    go.set_tile_stride(tile_stride)
+    times = []
+    try:
+        for f in range(warm + frames):
+            pose = scenes.pose7_from_c2w(sc.camera(f, 100))
+            cam = go.make_camera(sc.width, sc.height, sc.fx, sc.fy, sc.cx, sc.cy, pose)
+            t0 = time.perf_counter()
+            pr = go.project(cfg, cam, sc.particles, sc.sph, sc.sph_degree)
+            bn = go.bin_tiles(cfg, cam, pr)
+            t1 = time.perf_counter()
+            rgba, dist, hits = go.render_forward(cfg, cam, ro, rd, sc.particles, pr, bn)
+            d_rgba = rng.normal(size=rgba.shape).astype(np.float32)
+            d_dist = np.zeros_like(dist)
+            t2 = time.perf_counter()
+            go.render_backward(cfg, cam, ro, rd, sc.particles, sc.sph, sc.sph_degree, pr, bn, rgba, dist, d_rgba, d_dist)
+            t3 = time.perf_counter()
+            if f >= warm:
+                times.append((t1 - t0) + ((t2 - t1) + (t3 - t2)) * tile_stride)
+    finally:
+        go.set_tile_stride(1)
+    return 1.0 / float(np.mean(times)), times
+
+
+def run_reference_arm(args, rank, world):
+    """CPU port of the reference algorithm on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    sc = make_scene(args.workload)
+    stride = args.cpu_tile_stride
+    cores = os.cpu_count() or 1
+    fps, times = cpu_port_frames_per_s(sc, stride, frames=args.steps, warm=args.warmup)
+    sample = f"per step: full projection+binning, compositing fwd+bwd on every {stride}th tile of one {sc.width}x{sc.height} view, extrapolated x{stride}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": sc.name, "gaussians": sc.n, "resolution": [sc.width, sc.height], "path": "3dgut", "note": "CPU port of the reference algorithm (oracle/); the reference ships no CPU path and its CUDA build needs slangc"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--cpu-tile-stride", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import b200_native as nat
+    import scenes
+    import threedgut_tracer
+    from threedgut_tracer.tracer import SensorPose3D, fromOpenCVPinholeCameraModelParameters, ShutterType
+
+    sc = make_scene(args.workload)
+    n, H, W = sc.n, sc.height, sc.width
+    conf = {"render": {"enable_kernel_timings": False}}
+    tracer = threedgut_tracer.Tracer(conf)
+    raster = tracer.tracer_wrapper
+
+    particles = torch.from_numpy(sc.particles).to(dev)
+    sph = torch.from_numpy(sc.sph).to(dev)
+    ro_np, rd_np = sc.rays()
+    rays_o, rays_d = torch.from_numpy(ro_np).to(dev), torch.from_numpy(rd_np).to(dev)
+    sensor = fromOpenCVPinholeCameraModelParameters(np.array([W, H]), ShutterType.GLOBAL, np.array([sc.cx, sc.cy], np.float32),
+                                                    np.array([sc.fx, sc.fy], np.float32), np.zeros(6, np.float32), np.zeros(2, np.float32),
+                                                    np.zeros(4, np.float32))
+    n_views = 100
+    poses = [scenes.pose7_from_c2w(sc.camera(i, n_views)) for i in range(n_views)]
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    d_rgba = torch.randn((H, W, 4), device=dev, generator=gen)
+    d_dist = 0.05 * torch.randn((H, W, 1), device=dev, generator=gen)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def view_of(step):  # disjoint cameras per rank
+        return (step * world + rank) % n_views
+
+    def step_device(step):
+        pose = poses[view_of(step)]
+        rgba, dst, hits, vis = raster.trace(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose)
+        dp, ds = raster.trace_bwd(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose, rgba, d_rgba, dst, d_dist)
+        if world > 1:
+            dist.all_reduce(dp)
+            dist.all_reduce(ds)
+        return dp, ds
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    ctx = raster.native_context(dev)
+    for s in range(args.warmup):
+        step_device(s)
+    barrier()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):
+        flush.fill_(float(s))  # L2 flush between timed iterations, outside the per-step event pair
+        ev[s][0].record()
+        step_device(args.warmup + s)
+        ev[s][1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev], dtype=np.float64)
+    total_ms = torch.tensor([float(step_ms.sum())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    launches = ctx.launch_count() - launches0
+    stats = ctx.stats()
+    # separate short pass with per-stage CUDA events (they add host syncs, so never inside the timed region)
+    ctx.set_timings(2)
+    ctx.collect_stage_times()
+    for s in range(min(args.steps, 20)):
+        flush.fill_(float(s))
+        step_device(args.warmup + s)
+    barrier()
+    stage_ms = ctx.collect_stage_times()
+    ctx.set_timings(0)
+    value = world * args.steps / (total_ms / 1000.0)
+
+    # ---- end to end through the public API: Tracer.render + loss.backward, camera batch from pinned host memory
+    class _G:
+        positions = particles[:, 0:3].clone().requires_grad_(True)
+        _d = particles[:, 3:4].clone().requires_grad_(True)
+        _r = particles[:, 4:8].clone().requires_grad_(True)
+        _s = particles[:, 8:11].clone().requires_grad_(True)
+        _f = sph.clone().requires_grad_(True)
+        n_active_features = sc.sph_degree
+        ray_feature_dim = 3
+        num_gaussians = n
+        get_rotation = staticmethod(lambda: _G._r)
+        get_scale = staticmethod(lambda: _G._s)
+        get_density = staticmethod(lambda: _G._d)
+        get_features = staticmethod(lambda: _G._f)
+
+    pin_o, pin_d = torch.from_numpy(ro_np).pin_memory(), torch.from_numpy(rd_np).pin_memory()
+    pin_gt = torch.rand((1, H, W, 3)).pin_memory()
+    intr = dict(resolution=np.array([W, H]), shutter_type="GLOBAL", principal_point=np.array([sc.cx, sc.cy], np.float32),
+                focal_length=np.array([sc.fx, sc.fy], np.float32), radial_coeffs=np.zeros(6, np.float32),
+                tangential_coeffs=np.zeros(2, np.float32), thin_prism_coeffs=np.zeros(4, np.float32))
+
+    class _B:
+        T_to_world_end = None
+        rays_in_world_space = False
+        intrinsics = None
+        intrinsics_OpenCVPinholeCameraModelParameters = intr
+
+    c2ws = [torch.from_numpy(np.asarray(sc.camera(i, n_views), np.float32))[None] for i in range(n_views)]
+    grads = [_G.positions, _G._d, _G._r, _G._s, _G._f]
+
+    def step_e2e(step):
+        b = _B()
+        b.rays_ori = pin_o.to(dev, non_blocking=True)
+        b.rays_dir = pin_d.to(dev, non_blocking=True)
+        gt = pin_gt.to(dev, non_blocking=True)
+        b.T_to_world = c2ws[view_of(step)]
+        for g in grads:
+            g.grad = None
+        out = tracer.render(_G, b, train=True, frame_id=step)
+        loss = (out["pred_features"] - gt).abs().mean() + 0.01 * out["pred_opacity"].mean()
+        loss.backward()
+        if world > 1:
+            for g in grads:
+                dist.all_reduce(g.grad)
+        return float(loss.item())  # D2H read of the step's result
+
+    e2e_steps = max(10, args.steps // 2)
+    for s in range(min(args.warmup, 5)):
+        step_e2e(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        step_e2e(args.warmup + s)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps / float(e2e_s.item())
+    h2d = int(pin_o.numel() * 4 + pin_d.numel() * 4 + pin_gt.numel() * 4)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        N_, I_, V_, T_, P_ = stats["N"], stats["I"], stats["V"], stats["T"], H * W
+        # algorithmic bytes per launch (SURVEY.md 8d bracketed terms)
+        stage_bytes = {
+            "project": 92 * N_ + 204 * V_,
+            "scan": 8 * N_,
+            "expand": 8 * N_ + 36 * V_ + 12 * I_,
+            "sort": (8 + 24 * ((32 + int(np.ceil(np.log2(max(T_, 2)))) + 7) // 8)) * I_,
+            "tile_ranges": 8 * I_ + 8 * T_,
+            "render": 8 * T_ + 64 * I_ + 48 * P_,
+            "render_backward": 8 * T_ + 64 * I_ + 64 * P_ + 112 * V_,
+            "project_backward": 4 * N_ + 444 * V_ + 112 * N_,
+        }
+        dom = max(stage_ms, key=lambda k: stage_ms[k])
+        dom_ms = stage_ms[dom]
+        achieved = stage_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        frame_bytes = 356 * N_ + 796 * V_ + (156 + 24 * 6) * I_ + 24 * T_ + 136 * P_
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": sc.name, "gaussians": n, "resolution": [W, H], "path": "3dgut", "views_per_step": world,
+                       "parallelism": f"view-parallel dp{world}" if world > 1 else "single", "l2": "flushed between timed steps (256 MiB fill)",
+                       "N": N_, "V": V_, "I": I_, "T": T_, "P": P_},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                    "api": "threedgut_tracer.Tracer.render + loss.backward"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(stage_bytes[dom]),
+                         "kernel_ms": dom_ms,
+                         "note": "render/render_backward are FP32-issue bound (SURVEY 7); the HBM fraction is reported as required"},
+            "stage_ms": stage_ms,
+            "frame_algorithmic_gbs": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9,
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            fps, _ = cpu_port_frames_per_s(sc, args.cpu_tile_stride, frames=1, warm=0)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"1 view: full projection+binning, compositing fwd+bwd on every {args.cpu_tile_stride}th tile, extrapolated"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,118 @@
+/*
+ * include/gut_b200.h -- C ABI of the B200-native 3DGUT renderer (lib: 3dgrut_b200/libgut_b200.so).
+ *
+ * Drop-in boundary.  The reference's FFI for this path is pybind11 + ATen, not extern "C"
+ * (threedgut_tracer/bindings.cpp:103-109): class SplatRaster{trace, trace_bwd, collect_times}.
+ * This header is the raw-pointer core a maintainer binds instead: every entry
+ * point takes plain device/host pointers, sizes and a cudaStream_t passed as void*; no torch types.
+ *
+ *   gutb200_create / destroy      <- SplatRaster::SplatRaster / ~SplatRaster   (threedgut_tracer/src/splatRaster.cpp:163-182)
+ *   gutb200_forward               <- SplatRaster::trace                         (src/splatRaster.cpp:184-262) -> GUTRenderer::renderForward (src/gutRenderer.cu:241-421)
+ *   gutb200_backward              <- SplatRaster::traceBwd                      (src/splatRaster.cpp:264-350) -> GUTRenderer::renderBackward (src/gutRenderer.cu:423-519)
+ *   gutb200_collect_times         <- SplatRaster::collectTimes                  (src/splatRaster.cpp:352-382)
+ *   gutb200_forward_host/_backward_host : same calls with HOST buffers (copies inside), used for the e2e metric.
+ *   gutb200_debug_copy            : test-only read-back of the binning artefacts (tile counts, sort keys, ranges).
+ *
+ * Data layouts (all fp32 unless noted; identical to the reference tensors):
+ *   particles [N,12] = pos3, density, quat(w,x,y,z), scale3, pad     (threedgut_tracer/tracer.py:176-178)
+ *   sph       [N,48] = 16 SH coefficients x rgb                       (gaussianParticles.cuh:208-221)
+ *   rays_o/d  [H,W,3] sensor space                                    (tracer.py:317-330)
+ *   out_rgba  [H,W,4], out_dist [H,W], out_hits [H,W], visibility [N] (src/splatRaster.cpp:212-216)
+ *   d_particles [N,12], d_sph [N,48]                                  (src/splatRaster.cpp:291-293)
+ * Errors: every call returns 0 on success, non-zero on failure; gutb200_last_error() gives the message
+ * (the reference logs and drops its Status codes, src/splatRaster.cpp:242,254; we surface them).
+ */
+#ifndef GUT_B200_H
+#define GUT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* OpenCV pinhole + global shutter (CameraModelParameters, include/3dgut/sensors/cameraModels.h:22-72).
+ * Poses are world->sensor [t.xyz, q.xyzw] at shutter open / close (include/3dgut/sensors/sensors.h:33-42). */
+typedef struct gutb200_camera {
+    int32_t width, height;
+    float principal[2];
+    float focal[2];
+    float radial[6];
+    float tangential[2];
+    float thin_prism[4];
+    float pose_start[7];
+    float pose_end[7];
+} gutb200_camera;
+
+/* Render configuration == the reference's compile-time -D constants (threedgut_tracer/setup_3dgut.py:64-95). */
+typedef struct gutb200_config {
+    int32_t kernel_degree;    /* GAUSSIAN_PARTICLE_KERNEL_DEGREE: 2 (3DGUT default) or 4          */
+    float min_kernel_density; /* GAUSSIAN_PARTICLE_MIN_KERNEL_DENSITY                              */
+    float min_alpha;          /* GAUSSIAN_PARTICLE_MIN_ALPHA                                       */
+    float max_alpha;          /* GAUSSIAN_PARTICLE_MAX_ALPHA                                       */
+    float min_transmittance;  /* GAUSSIAN_MIN_TRANSMITTANCE_THRESHOLD                               */
+    float ut_alpha, ut_beta, ut_kappa, ut_delta;
+    float ut_margin;          /* GAUSSIAN_UT_IN_IMAGE_MARGIN_FACTOR                                */
+    int32_t rect_bounding, tight_opacity_bounding, tile_culling;
+    int32_t global_z_order;
+    int32_t enable_timings;   /* render.enable_kernel_timings (src/splatRaster.cpp:168-169); 2 = also per-stage events */
+} gutb200_config;
+
+typedef struct gutb200_ctx gutb200_ctx;
+
+void gutb200_default_config(gutb200_config* cfg);
+int gutb200_create(const gutb200_config* cfg, int device, gutb200_ctx** out);
+void gutb200_destroy(gutb200_ctx* ctx);
+const char* gutb200_last_error(const gutb200_ctx* ctx);
+const char* gutb200_version(void);
+
+int gutb200_forward(gutb200_ctx* ctx, void* stream, const gutb200_camera* cam, int64_t n, const float* particles,
+                    const float* sph, int32_t sph_degree, const float* rays_o, const float* rays_d, float* out_rgba,
+                    float* out_dist, float* out_hits, float* visibility);
+
+int gutb200_backward(gutb200_ctx* ctx, void* stream, const gutb200_camera* cam, int64_t n, const float* particles,
+                     const float* sph, int32_t sph_degree, const float* rays_o, const float* rays_d,
+                     const float* out_rgba, const float* d_rgba, const float* out_dist, const float* d_dist,
+                     float* d_particles, float* d_sph);
+
+/* Host-buffer variants: pinned or pageable host pointers; H2D/D2H copies happen inside on the context's stream. */
+int gutb200_forward_host(gutb200_ctx* ctx, const gutb200_camera* cam, int64_t n, const float* particles,
+                         const float* sph, int32_t sph_degree, const float* rays_o, const float* rays_d,
+                         float* out_rgba, float* out_dist, float* out_hits, float* visibility);
+int gutb200_backward_host(gutb200_ctx* ctx, const gutb200_camera* cam, int64_t n, const float* particles,
+                          const float* sph, int32_t sph_degree, const float* rays_o, const float* rays_d,
+                          const float* out_rgba, const float* d_rgba, const float* out_dist, const float* d_dist,
+                          float* d_particles, float* d_sph);
+
+/* Statistics of the last forward: N, I (= particle/tile intersections), V (= particles with tiles_count>0), T tiles. */
+int gutb200_last_stats(gutb200_ctx* ctx, int64_t* n, int64_t* num_intersections, int64_t* num_visible, int64_t* num_tiles);
+
+/* Test-only read-back (synchronises).  `what`: */
+enum {
+    GUTB200_DBG_TILES_COUNT = 0,   /* u32 [N]   */
+    GUTB200_DBG_SORTED_KEYS = 1,   /* u64 [I]   */
+    GUTB200_DBG_SORTED_VALUES = 2, /* u32 [I]   */
+    GUTB200_DBG_TILE_RANGES = 3,   /* u32 [T,2] */
+    GUTB200_DBG_DEPTH = 4,         /* f32 [N]   */
+    GUTB200_DBG_RGB = 5,           /* f32 [N,3] (unclamped precomputed radiance) */
+    GUTB200_DBG_PROJ = 6           /* f32 [N,8] = centre2, extent2, conic3, opacity */
+};
+int gutb200_debug_copy(gutb200_ctx* ctx, int what, void* host_dst, size_t bytes);
+
+/* Mean device time (ms) of the forward / backward calls since the last collect (needs enable_timings). */
+int gutb200_collect_times(gutb200_ctx* ctx, float* forward_ms, float* backward_ms);
+
+/* Change the timing level of a live context: 0 off, 1 forward/backward events, 2 also per-stage events. */
+int gutb200_set_timings(gutb200_ctx* ctx, int level);
+
+/* Mean device time (ms) per stage since the last collect (needs enable_timings >= 2); order:
+ * project, scan, expand, sort, tile_ranges, render, render_backward, project_backward. */
+int gutb200_collect_stage_times(gutb200_ctx* ctx, float* mean_ms /*[8]*/);
+
+/* Number of kernels this library launched since the context was created (bench.py's gpu_launches). */
+int64_t gutb200_launch_count(const gutb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -708,6 +708,10 @@ int gut_oracle_hit_forward(const gut_oracle_config* cfg, const float ro[3], cons
     return h.accept;
 }
 
+/* bench-only: process every k-th tile in the render loops (bounded CPU sample of a full-size frame) */
+static int g_tile_stride = 1;
+void gut_oracle_set_tile_stride(int k) { g_tile_stride = k > 0 ? k : 1; }
+
 /* G6 */
 void gut_oracle_render_forward(const gut_oracle_config* cfg, const gut_oracle_camera* cam, const float* rays_o,
                                const float* rays_d, const float* particles, const float* rgb,
@@ -719,6 +723,7 @@ void gut_oracle_render_forward(const gut_oracle_config* cfg, const gut_oracle_ca
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int tile = 0; tile < gx * gy; ++tile) {
+        if (tile % g_tile_stride) continue;
         const int tx = tile % gx, ty = tile / gx;
         const uint32_t b = ranges[tile * 2], e = ranges[tile * 2 + 1];
         for (int py = ty * TILE; py < imin(H, (ty + 1) * TILE); ++py)
@@ -931,6 +936,7 @@ void gut_oracle_render_backward(const gut_oracle_config* cfg, const gut_oracle_c
         tid = omp_get_thread_num();
 #endif
         double* a = acc + (size_t)tid * stride;
+        if (tile % g_tile_stride) continue;
         const int tx = tile % gx, ty = tile / gx;
         const uint32_t b = ranges[tile * 2], e = ranges[tile * 2 + 1];
         for (int py = ty * TILE; py < imin(H, (ty + 1) * TILE); ++py)

@@ -90,6 +90,9 @@ void gut_oracle_render_backward(const gut_oracle_config* cfg, const gut_oracle_c
                                 const float* d_rgba, const float* d_dist,
                                 float* d_particles, float* d_sph);
 
+/* bench-only: render loops visit every k-th tile (bounded CPU sample of a full-size frame); default 1 */
+void gut_oracle_set_tile_stride(int k);
+
 /* Single-hit primitives exposed for unit pinning against oracle/_ref. */
 int gut_oracle_hit_forward(const gut_oracle_config* cfg, const float ray_o[3], const float ray_d[3],
                            const float particle[12], float* alpha, float* hit_t);

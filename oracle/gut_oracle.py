@@ -195,3 +195,7 @@ def sph_eval(degree, coeffs, direction):
     out = np.zeros(3, np.float32)
     lib().gut_oracle_sph_eval(C.c_int32(degree), _p(_f32(coeffs), C.c_float), _p(_f32(direction), C.c_float), _p(out, C.c_float))
     return out
+
+
+def set_tile_stride(k: int):
+    lib().gut_oracle_set_tile_stride(C.c_int(int(k)))
