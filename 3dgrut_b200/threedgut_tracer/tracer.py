@@ -54,14 +54,15 @@ class SensorPose3D:  # tracer.py:55-58
 
 
 def _so3_matrix_to_quat_xyzw(R: np.ndarray) -> np.ndarray:
-    """tracer.py:88-136"""
-    R = np.asarray(R, dtype=np.float64)
-    d = np.array([R[0, 0], R[1, 1], R[2, 2], R[0, 0] + R[1, 1] + R[2, 2]])
+    """tracer.py:88-136, evaluated in float32 like the reference's torch code (it receives a float32 matrix)."""
+    R = np.asarray(R, dtype=np.float32)
+    f = np.float32
+    d = np.array([R[0, 0], R[1, 1], R[2, 2], f(f(R[0, 0] + R[1, 1]) + R[2, 2])], dtype=np.float32)
     c = int(np.argmax(d))
-    q = np.zeros(4)
+    q = np.zeros(4, dtype=np.float32)
     if c != 3:
         i, j, k = c, (c + 1) % 3, (c + 2) % 3
-        q[i] = 1 - d[3] + 2 * R[i, i]
+        q[i] = f(f(f(1) - d[3]) + f(f(2) * R[i, i]))
         q[j] = R[j, i] + R[i, j]
         q[k] = R[k, i] + R[i, k]
         q[3] = R[k, j] - R[j, k]
@@ -69,8 +70,8 @@ def _so3_matrix_to_quat_xyzw(R: np.ndarray) -> np.ndarray:
         q[0] = R[2, 1] - R[1, 2]
         q[1] = R[0, 2] - R[2, 0]
         q[2] = R[1, 0] - R[0, 1]
-        q[3] = 1 + d[3]
-    return (q / np.linalg.norm(q)).astype(np.float32)
+        q[3] = f(1) + d[3]
+    return (q / np.sqrt(np.sum(q * q, dtype=np.float32), dtype=np.float32)).astype(np.float32)
 
 
 def _cfg_get(conf, path, default):

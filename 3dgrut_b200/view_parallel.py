@@ -1,0 +1,63 @@
+"""View-parallel training plumbing: replicate the Gaussians, give every rank disjoint
+cameras, sum the per-Gaussian gradients once per step.  The reference has no multi-GPU path; this is new.
+
+One process per GPU (torchrun); `torch.distributed` with NCCL over NVLink on the B200 box, gloo in the CPU tests.
+The only exchange of the path is the gradient sum, so the only collective is one all-reduce over a single flat
+bucket holding [N,3]+[N,4]+[N,3]+[N,1]+[N,48] = 59 floats per Gaussian (236 B x N per rank)."""
+from __future__ import annotations
+
+from typing import Iterable, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def views_for_rank(step: int, rank: int, world: int, num_views: int, views_per_rank: int = 1) -> List[int]:
+    """Disjoint camera indices of global step `step`: the step's batch is world*views_per_rank consecutive views
+    (mod num_views) dealt round-robin, rank r takes {i : i mod world == r}."""
+    base = step * world * views_per_rank
+    return [(base + j * world + rank) % num_views for j in range(views_per_rank)]
+
+
+class GradientBucket:
+    """Flat fp32 bucket over a fixed list of parameter shapes; one collective per step, buffers allocated once."""
+
+    def __init__(self, shapes: Sequence[Sequence[int]], device, dtype=torch.float32):
+        self.shapes = [tuple(s) for s in shapes]
+        self.sizes = [int(torch.Size(s).numel()) for s in self.shapes]
+        self.flat = torch.zeros(sum(self.sizes), device=device, dtype=dtype)
+        self.views, off = [], 0
+        for s, n in zip(self.shapes, self.sizes):
+            self.views.append(self.flat[off:off + n].view(s))
+            off += n
+
+    def pack(self, grads: Iterable[torch.Tensor]):
+        for v, g in zip(self.views, grads):
+            v.copy_(g)
+
+    def all_reduce(self, group=None, average: bool = False, async_op: bool = False):
+        work = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+            if average and not async_op:
+                self.flat.div_(dist.get_world_size(group))
+        return work
+
+    def unpack(self) -> List[torch.Tensor]:
+        return self.views
+
+
+def allreduce_gradients(grads: Sequence[torch.Tensor], bucket: GradientBucket | None = None, group=None, average: bool = False):
+    """Sum `grads` (list of tensors, same shapes on every rank) over all ranks; returns the reduced tensors."""
+    if bucket is None:
+        bucket = GradientBucket([g.shape for g in grads], grads[0].device, grads[0].dtype)
+    bucket.pack(grads)
+    bucket.all_reduce(group=group, average=average)
+    return bucket.unpack()
+
+
+def broadcast_parameters(params: Sequence[torch.Tensor], src: int = 0, group=None):
+    """Make replicas bit-identical at start-up (same seed already gives that; this is the belt to the braces)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for p in params:
+            dist.broadcast(p.data, src=src, group=group)

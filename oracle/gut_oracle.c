@@ -26,14 +26,31 @@
 #define TILE 16
 #define INVALID_U32 0xFFFFFFFFu
 
-typedef struct { float x, y, z; } v3;
+/* `real` is float in the oracle proper.  Building with -DORACLE_F64 (libgut_oracle_f64.so) evaluates the
+ * per-ray compositing maths in double on the SAME fp32 inputs and sorted lists: that is the "ground truth" the
+ * tests use to size the fp32 tolerance (how far two valid fp32 evaluation orders may drift apart). */
+#ifdef ORACLE_F64
+typedef double real;
+#define R_SQRT sqrt
+#define R_EXP exp
+#define R_FMAX fmax
+#define R_FMIN fmin
+#else
+typedef float real;
+#define R_SQRT sqrtf
+#define R_EXP expf
+#define R_FMAX fmaxf
+#define R_FMIN fminf
+#endif
 
-static inline v3 V3(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+typedef struct { real x, y, z; } v3;
+
+static inline v3 V3(real x, real y, real z) { v3 r = {x, y, z}; return r; }
 static inline v3 add3(v3 a, v3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
 static inline v3 sub3(v3 a, v3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
 static inline v3 mul3(v3 a, v3 b) { return V3(a.x * b.x, a.y * b.y, a.z * b.z); }
-static inline v3 scl3(v3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
-static inline float dot3(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline v3 scl3(v3 a, real s) { return V3(a.x * s, a.y * s, a.z * s); }
+static inline real dot3(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 static inline v3 cross3(v3 a, v3 b) {
     return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
@@ -201,7 +218,7 @@ uint32_t gut_oracle_higher_msb(uint32_t n) { /* src/gutRenderer.cu:79-94 */
 /* particle record helpers: include/3dgut/kernels/cuda/models/gaussianParticles.cuh:24-59       */
 
 typedef struct {
-    v3 pos; float dns; float qw, qx, qy, qz; v3 scl;
+    v3 pos; real dns; real qw, qx, qy, qz; v3 scl;
     v3 rot[3]; /* rows of quaternionWXYZToMatrix == columns of the standard rotation R */
 } particle;
 
@@ -211,9 +228,9 @@ static particle load_particle(const float* p) {
     g.dns = p[3];
     g.qw = p[4]; g.qx = p[5]; g.qy = p[6]; g.qz = p[7];
     g.scl = V3(p[8], p[9], p[10]);
-    const float r = g.qw, x = g.qx, y = g.qy, z = g.qz;
-    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
-    const float rx = r * x, ry = r * y, rz = r * z;
+    const real r = g.qw, x = g.qx, y = g.qy, z = g.qz;
+    const real xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+    const real rx = r * x, ry = r * y, rz = r * z;
     g.rot[0] = V3(1.f - 2.f * (yy + zz), 2.f * (xy + rz), 2.f * (xz - ry));
     g.rot[1] = V3(2.f * (xy - rz), 1.f - 2.f * (xx + zz), 2.f * (yz + rx));
     g.rot[2] = V3(2.f * (xz + ry), 2.f * (yz - rx), 1.f - 2.f * (xx + yy));
@@ -233,14 +250,14 @@ static const float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.3153
 static const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
                                -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
 
-static void sh_basis(int deg, v3 d, float b[16]) {
-    const float x = d.x, y = d.y, z = d.z;
+static void sh_basis(int deg, v3 d, real b[16]) {
+    const real x = d.x, y = d.y, z = d.z;
     for (int i = 0; i < 16; ++i) b[i] = 0.f;
     b[0] = SH_C0;
     if (deg > 0) {
         b[1] = -SH_C1 * y; b[2] = SH_C1 * z; b[3] = -SH_C1 * x;
         if (deg > 1) {
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            const real xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
             b[4] = SH_C2[0] * xy; b[5] = SH_C2[1] * yz; b[6] = SH_C2[2] * (2.0f * zz - xx - yy);
             b[7] = SH_C2[3] * xz; b[8] = SH_C2[4] * (xx - yy);
             if (deg > 2) {
@@ -611,16 +628,16 @@ int64_t gut_oracle_bin(const gut_oracle_config* cfg, const gut_oracle_camera* ca
 /* ------------------------------------------------------------------------------------------ */
 /* ray setup: kernels/cuda/common/rayPayload.cuh:76-108, utils/bounding_box.h:89-134            */
 
-static void aabb_intersect(v3 o, v3 d, float* tmin_o, float* tmax_o) {
-    const float lo = -1e06f, hi = 1e06f; /* src/splatRaster.cpp:240 */
-    float tmin = (lo - o.x) / d.x, tmax = (hi - o.x) / d.x, t;
+static void aabb_intersect(v3 o, v3 d, real* tmin_o, real* tmax_o) {
+    const real lo = -1e06f, hi = 1e06f; /* src/splatRaster.cpp:240 */
+    real tmin = (lo - o.x) / d.x, tmax = (hi - o.x) / d.x, t;
     if (tmin > tmax) { t = tmin; tmin = tmax; tmax = t; }
-    float tymin = (lo - o.y) / d.y, tymax = (hi - o.y) / d.y;
+    real tymin = (lo - o.y) / d.y, tymax = (hi - o.y) / d.y;
     if (tymin > tymax) { t = tymin; tymin = tymax; tymax = t; }
     if (tmin > tymax || tymin > tmax) { *tmin_o = FLT_MAX; *tmax_o = FLT_MAX; return; }
     if (tymin > tmin) tmin = tymin;
     if (tymax < tmax) tmax = tymax;
-    float tzmin = (lo - o.z) / d.z, tzmax = (hi - o.z) / d.z;
+    real tzmin = (lo - o.z) / d.z, tzmax = (hi - o.z) / d.z;
     if (tzmin > tzmax) { t = tzmin; tzmin = tzmax; tzmax = t; }
     if (tmin > tzmax || tzmin > tmax) { *tmin_o = FLT_MAX; *tmax_o = FLT_MAX; return; }
     if (tzmin > tmin) tmin = tzmin;
@@ -628,19 +645,19 @@ static void aabb_intersect(v3 o, v3 d, float* tmin_o, float* tmax_o) {
     *tmin_o = tmin; *tmax_o = tmax;
 }
 
-typedef struct { v3 o, d; float tmin, tmax; int alive; } ray_t;
+typedef struct { v3 o, d; real tmin, tmax; int alive; } ray_t;
 
 static ray_t init_ray(const float inv[12], const float* ro, const float* rd) {
     ray_t r;
-    float o[3], d[3];
+    real o[3], d[3];
     for (int j = 0; j < 3; ++j) {
-        float acc = 0.f;
+        real acc = 0.f;
         acc += inv[0 * 3 + j] * ro[0];
         acc += inv[1 * 3 + j] * ro[1];
         acc += inv[2 * 3 + j] * ro[2];
         acc += inv[3 * 3 + j] * 1.0f;
         o[j] = acc;
-        float acd = 0.f;
+        real acd = 0.f;
         acd += inv[0 * 3 + j] * rd[0];
         acd += inv[1 * 3 + j] * rd[1];
         acd += inv[2 * 3 + j] * rd[2];
@@ -649,7 +666,7 @@ static ray_t init_ray(const float inv[12], const float* ro, const float* rd) {
     r.o = V3(o[0], o[1], o[2]);
     r.d = V3(d[0], d[1], d[2]);
     aabb_intersect(r.o, r.d, &r.tmin, &r.tmax);
-    r.tmin = fmaxf(r.tmin, 0.0f);
+    r.tmin = R_FMAX(r.tmin, 0.0f);
     r.alive = r.tmax > r.tmin;
     return r;
 }
@@ -658,24 +675,24 @@ static ray_t init_ray(const float inv[12], const float* ro, const float* rd) {
 /* per-hit math: slang/models/gaussianParticles.slang:96-274 (forward), CUDA twin
  * models/gaussianParticles.cuh:350-422                                                         */
 
-static inline float kernel_response(int degree, float gray) {
+static inline real kernel_response(int degree, real gray) {
     switch (degree) { /* models/gaussianParticles.cuh:267-308 */
-    case 8: { const float g2 = gray * gray; return expf(-0.000685871056241f * g2 * g2); }
-    case 5: return expf(-0.0185185185185f * gray * gray * sqrtf(gray));
-    case 4: return expf(-0.0555555555556f * gray * gray);
-    case 3: return expf(-0.166666666667f * gray * sqrtf(gray));
-    case 1: return expf(-1.5f * sqrtf(gray));
-    case 0: return fmaxf(1.f + -0.329630334487f * sqrtf(gray), 0.f);
-    default: return expf(-0.5f * gray);
+    case 8: { const real g2 = gray * gray; return R_EXP(-0.000685871056241f * g2 * g2); }
+    case 5: return R_EXP(-0.0185185185185f * gray * gray * R_SQRT(gray));
+    case 4: return R_EXP(-0.0555555555556f * gray * gray);
+    case 3: return R_EXP(-0.166666666667f * gray * R_SQRT(gray));
+    case 1: return R_EXP(-1.5f * R_SQRT(gray));
+    case 0: return R_FMAX(1.f + -0.329630334487f * R_SQRT(gray), 0.f);
+    default: return R_EXP(-0.5f * gray);
     }
 }
 
 static inline v3 safe_normalize(v3 v) { /* mathUtils.cuh:380-383 */
-    const float l = v.x * v.x + v.y * v.y + v.z * v.z;
-    return l > 0.0f ? scl3(v, 1.0f / sqrtf(l)) : v;
+    const real l = v.x * v.x + v.y * v.y + v.z * v.z;
+    return l > 0.0f ? scl3(v, 1.0f / R_SQRT(l)) : v;
 }
 
-typedef struct { v3 giscl, gposc, gposcr, gro, rayDirR, grdu, grd, gcrod; float gray, gres, galpha; int accept; } hit_t;
+typedef struct { v3 giscl, gposc, gposcr, gro, rayDirR, grdu, grd, gcrod; real gray, gres, galpha; int accept; } hit_t;
 
 static hit_t eval_hit(const gut_oracle_config* cfg, const particle* g, v3 ro, v3 rd) {
     hit_t h;
@@ -689,22 +706,22 @@ static hit_t eval_hit(const gut_oracle_config* cfg, const particle* g, v3 ro, v3
     h.gcrod = cross3(h.grd, h.gro);
     h.gray = dot3(h.gcrod, h.gcrod);
     h.gres = kernel_response(cfg->kernel_degree, h.gray);
-    h.galpha = fminf(cfg->max_alpha, h.gres * g->dns);
+    h.galpha = R_FMIN(cfg->max_alpha, h.gres * g->dns);
     h.accept = (h.gres > cfg->min_kernel_density) && (h.galpha > cfg->min_alpha);
     return h;
 }
 
-static inline float hit_distance(const particle* g, const hit_t* h) {
+static inline real hit_distance(const particle* g, const hit_t* h) {
     const v3 grds = mul3(g->scl, scl3(h->grd, dot3(h->grd, scl3(h->gro, -1.f))));
-    return sqrtf(dot3(grds, grds));
+    return R_SQRT(dot3(grds, grds));
 }
 
 int gut_oracle_hit_forward(const gut_oracle_config* cfg, const float ro[3], const float rd[3], const float p[12],
                            float* alpha, float* hit_t_out) {
     const particle g = load_particle(p);
     const hit_t h = eval_hit(cfg, &g, V3(ro[0], ro[1], ro[2]), V3(rd[0], rd[1], rd[2]));
-    *alpha = h.galpha;
-    *hit_t_out = h.accept ? hit_distance(&g, &h) : 0.f;
+    *alpha = (float)h.galpha;
+    *hit_t_out = h.accept ? (float)hit_distance(&g, &h) : 0.f;
     return h.accept;
 }
 
@@ -735,7 +752,7 @@ void gut_oracle_render_forward(const gut_oracle_config* cfg, const gut_oracle_ca
                 out_dist[pix] = 1e06f;
                 out_hits[pix] = 0.f;
                 if (!r.alive) continue;
-                float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, dist = 0.f;
+                real T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, dist = 0.f;
                 uint32_t hits = 0;
                 for (uint32_t k = b; k < e; ++k) {
                     const uint32_t idx = svals[k];
@@ -743,15 +760,15 @@ void gut_oracle_render_forward(const gut_oracle_config* cfg, const gut_oracle_ca
                     const particle g = load_particle(particles + (int64_t)idx * 12);
                     const hit_t h = eval_hit(cfg, &g, r.o, r.d);
                     if (!h.accept) continue;
-                    const float t = hit_distance(&g, &h);
+                    const real t = hit_distance(&g, &h);
                     if (!(t > r.tmin && t < r.tmax)) continue;
-                    const float w = h.galpha * T;
+                    const real w = h.galpha * T;
                     dist += t * w;
                     T *= (1 - h.galpha);
                     if (w > 0.0f) {
-                        cr += fmaxf(rgb[idx * 3], 0.f) * w;
-                        cg += fmaxf(rgb[idx * 3 + 1], 0.f) * w;
-                        cb += fmaxf(rgb[idx * 3 + 2], 0.f) * w;
+                        cr += R_FMAX(rgb[idx * 3], 0.f) * w;
+                        cg += R_FMAX(rgb[idx * 3 + 1], 0.f) * w;
+                        cb += R_FMAX(rgb[idx * 3 + 2], 0.f) * w;
                         hits++;
                     }
                     if (T < cfg->min_transmittance) break;
@@ -759,7 +776,7 @@ void gut_oracle_render_forward(const gut_oracle_config* cfg, const gut_oracle_ca
                 out_rgba[pix * 4] = cr; out_rgba[pix * 4 + 1] = cg; out_rgba[pix * 4 + 2] = cb;
                 out_rgba[pix * 4 + 3] = 1.0f - T;
                 out_dist[pix] = dist;
-                out_hits[pix] = (float)hits;
+                out_hits[pix] = (real)hits;
             }
     }
 }
@@ -767,23 +784,23 @@ void gut_oracle_render_forward(const gut_oracle_config* cfg, const gut_oracle_ca
 /* ------------------------------------------------------------------------------------------ */
 /* G7 processHitBwd<degree,false,false> (models/gaussianParticles.cuh:484-751)                  */
 
-static inline float response_grad(int degree, float gray, float gres, float gresGrd) {
+static inline real response_grad(int degree, real gray, real gres, real gresGrd) {
     switch (degree) { /* models/gaussianParticles.cuh:223-265 */
-    case 8: { const float s = (float)(-0.000685871056241 * (0.5f * 8)); return s * (gray * gray) * gray * gres * gresGrd; }
-    case 5: { const float s = (float)(-0.0185185185185 * (0.5f * 5)); return s * gray * sqrtf(gray) * gres * gresGrd; }
-    case 4: { const float s = (float)(-0.0555555555556 * (0.5f * 4)); return s * gray * gres * gresGrd; }
-    case 3: { const float s = (float)(-0.166666666667 * (0.5f * 3)); return s * sqrtf(gray) * gres * gresGrd; }
-    case 1: { const float s = -1.5f * (0.5f * 1); return s * sqrtf(gray) * gres * gresGrd; }
-    case 0: { const float s = -0.329630334487f; return gres > 0.f ? (0.5f * s * (1.0f / sqrtf(gray))) * gresGrd : 0.f; }
+    case 8: { const real s = (real)(-0.000685871056241 * (0.5f * 8)); return s * (gray * gray) * gray * gres * gresGrd; }
+    case 5: { const real s = (real)(-0.0185185185185 * (0.5f * 5)); return s * gray * R_SQRT(gray) * gres * gresGrd; }
+    case 4: { const real s = (real)(-0.0555555555556 * (0.5f * 4)); return s * gray * gres * gresGrd; }
+    case 3: { const real s = (real)(-0.166666666667 * (0.5f * 3)); return s * R_SQRT(gray) * gres * gresGrd; }
+    case 1: { const real s = -1.5f * (0.5f * 1); return s * R_SQRT(gray) * gres * gresGrd; }
+    case 0: { const real s = -0.329630334487f; return gres > 0.f ? (0.5f * s * (1.0f / R_SQRT(gray))) * gresGrd : 0.f; }
     default: return -0.5f * gres * gresGrd;
     }
 }
 
 static inline v3 safe_normalize_bw(v3 v, v3 d) { /* mathUtils.cuh:410-420 */
-    const float l = v.x * v.x + v.y * v.y + v.z * v.z;
+    const real l = v.x * v.x + v.y * v.y + v.z * v.z;
     if (l > 0.0f) {
-        const float il = 1.0f / sqrtf(l);
-        const float il3 = il * il * il;
+        const real il = 1.0f / R_SQRT(l);
+        const real il3 = il * il * il;
         const v3 a = scl3(d, il);
         const v3 b = V3(d.x * (v.x * v.x) + d.y * (v.y * v.x) + d.z * (v.z * v.x),
                         d.x * (v.x * v.y) + d.y * (v.y * v.y) + d.z * (v.z * v.y),
@@ -798,10 +815,10 @@ static inline v3 matmul_bw_vec(const v3 m[3], v3 g) { /* mathUtils.cuh:451-456 *
               g.x * m[0].z + g.y * m[1].z + g.z * m[2].z);
 }
 
-static inline void matmul_bw_quat(v3 p, v3 g, float r, float x, float y, float z, float out[4]) {
+static inline void matmul_bw_quat(v3 p, v3 g, real r, real x, real y, real z, real out[4]) {
     /* mathUtils.cuh:458-523 */
     const v3 d0 = scl3(p, g.x), d1 = scl3(p, g.y), d2 = scl3(p, g.z);
-    float dr = 0, dx = 0, dy = 0, dz = 0;
+    real dr = 0, dx = 0, dy = 0, dz = 0;
     dy += -4 * y * d0.x; dz += -4 * z * d0.x;
     dr += 2 * z * d0.y; dx += 2 * y * d0.y; dy += 2 * x * d0.y; dz += 2 * r * d0.y;
     dr += -2 * y * d0.z; dx += 2 * z * d0.z; dy += -2 * r * d0.z; dz += 2 * x * d0.z;
@@ -816,44 +833,44 @@ static inline void matmul_bw_quat(v3 p, v3 g, float r, float x, float y, float z
 
 /* One accepted/rejected hit of the backward replay.  Returns 1 if accepted and fills grads
  * (pos3,dns1,quat4,scl3) and rgbgrad3; advances T, C (radiance), Dp (depth). */
-static int hit_backward(const gut_oracle_config* cfg, const particle* g, v3 ro, v3 rd, const float prgb[3],
-                        float Tint, float* T, float Tgrad, const float Cint[3], float C[3], const float Cgrad[3],
-                        float Dint, float* Dp, float Dgrad, float grad[11], float rgbgrad[3]) {
+static int hit_backward(const gut_oracle_config* cfg, const particle* g, v3 ro, v3 rd, const real prgb[3],
+                        real Tint, real* T, real Tgrad, const real Cint[3], real C[3], const real Cgrad[3],
+                        real Dint, real* Dp, real Dgrad, real grad[11], real rgbgrad[3]) {
     const hit_t h = eval_hit(cfg, g, ro, rd);
     if (!h.accept) return 0;
     const v3 gscl = g->scl;
     const v3 grdd = scl3(h.grd, dot3(h.grd, scl3(h.gro, -1.f)));
     const v3 grds = mul3(gscl, grdd);
-    const float gsqdist = dot3(grds, grds);
-    const float gdist = sqrtf(gsqdist);
-    const float trm = *T;
-    const float weight = h.galpha * trm;
-    const float nextT = (1 - h.galpha) * trm;
+    const real gsqdist = dot3(grds, grds);
+    const real gdist = R_SQRT(gsqdist);
+    const real trm = *T;
+    const real weight = h.galpha * trm;
+    const real nextT = (1 - h.galpha) * trm;
 
     *Dp += weight * gdist;
-    const float resHitT = fmaxf((nextT <= cfg->min_transmittance ? 0 : (Dint - *Dp) / nextT), 0);
-    const float galphaRayHitGrd = (gdist - resHitT) * trm * Dgrad;
+    const real resHitT = R_FMAX((nextT <= cfg->min_transmittance ? 0 : (Dint - *Dp) / nextT), 0);
+    const real galphaRayHitGrd = (gdist - resHitT) * trm * Dgrad;
     const v3 grdsRayHitGrd = gsqdist > 0.0f ? scl3(scl3(scl3(grds, 2 * weight), 1.0f / (2 * gdist)), Dgrad) : V3(0, 0, 0);
     const v3 gsclRayHitGrd = mul3(grdd, grdsRayHitGrd);
-    const float grdScaledDot = dot3(mul3(grdsRayHitGrd, gscl), h.grd);
+    const real grdScaledDot = dot3(mul3(grdsRayHitGrd, gscl), h.grd);
     const v3 grdRayHitGrd = sub3(scl3(mul3(gscl, grdsRayHitGrd), dot3(h.grd, scl3(h.gro, -1.f))), scl3(h.gro, grdScaledDot));
     const v3 groRayHitGrd = scl3(scl3(h.grd, -1.f), grdScaledDot);
 
-    const float resTrm = h.galpha < 0.999999f ? Tint / (1 - h.galpha) : trm;
-    const float galphaRayDnsGrd = resTrm * -Tgrad;
+    const real resTrm = h.galpha < 0.999999f ? Tint / (1 - h.galpha) : trm;
+    const real galphaRayDnsGrd = resTrm * -Tgrad;
 
-    const float gr[3] = {prgb[0], prgb[1], prgb[2]}; /* already clamped (gutKBufferRenderer.cuh:658) */
+    const real gr[3] = {prgb[0], prgb[1], prgb[2]}; /* already clamped (gutKBufferRenderer.cuh:658) */
     rgbgrad[0] = Cgrad[0] * weight; rgbgrad[1] = Cgrad[1] * weight; rgbgrad[2] = Cgrad[2] * weight;
-    float resC[3];
+    real resC[3];
     for (int k = 0; k < 3; ++k) {
         C[k] += weight * gr[k];
-        resC[k] = fmaxf((nextT <= cfg->min_transmittance ? 0.f : (Cint[k] - C[k]) / nextT), 0.f);
+        resC[k] = R_FMAX((nextT <= cfg->min_transmittance ? 0.f : (Cint[k] - C[k]) / nextT), 0.f);
     }
-    const float common = galphaRayHitGrd + galphaRayDnsGrd + trm * (gr[0] - resC[0]) * Cgrad[0] +
+    const real common = galphaRayHitGrd + galphaRayDnsGrd + trm * (gr[0] - resC[0]) * Cgrad[0] +
                          trm * (gr[1] - resC[1]) * Cgrad[1] + trm * (gr[2] - resC[2]) * Cgrad[2];
     grad[3] = h.gres * common;
-    const float gresGrd = g->dns * common;
-    const float grayGrd = response_grad(cfg->kernel_degree, h.gray, h.gres, gresGrd);
+    const real gresGrd = g->dns * common;
+    const real grayGrd = response_grad(cfg->kernel_degree, h.gray, h.gres, gresGrd);
 
     const v3 gcrodGrd = scl3(scl3(h.gcrod, 2.f), grayGrd);
     const v3 grdGrd = V3(gcrodGrd.z * h.gro.y - gcrodGrd.y * h.gro.z, gcrodGrd.x * h.gro.z - gcrodGrd.z * h.gro.x,
@@ -865,7 +882,7 @@ static int hit_backward(const gut_oracle_config* cfg, const particle* g, v3 ro, 
     const v3 gsclGrdGro = mul3(V3(-h.gposcr.x / (gscl.x * gscl.x), -h.gposcr.y / (gscl.y * gscl.y), -h.gposcr.z / (gscl.z * gscl.z)), groTot);
     const v3 gposcrGrd = mul3(h.giscl, groTot);
     const v3 gposcGrd = matmul_bw_vec(g->rot, gposcrGrd);
-    float qa[4], qb[4];
+    real qa[4], qb[4];
     matmul_bw_quat(h.gposc, gposcrGrd, g->qw, g->qx, g->qy, g->qz, qa);
     grad[0] = -gposcGrd.x; grad[1] = -gposcGrd.y; grad[2] = -gposcGrd.z;
 
@@ -882,11 +899,11 @@ static int hit_backward(const gut_oracle_config* cfg, const particle* g, v3 ro, 
 
 /* d(rgb_c)/d(dir) for the SH polynomial of gut_oracle_sph_eval (closed form of what Slang's
  * bwd_diff(sphericalHarmonics.decode) generates; slang/common/sphericalHarmonics.slang:21-64) */
-static void sh_dir_jacobian(int deg, const float* c, v3 d, float drgb_dx[3], float drgb_dy[3], float drgb_dz[3]) {
-    const float x = d.x, y = d.y, z = d.z;
+static void sh_dir_jacobian(int deg, const float* c, v3 d, real drgb_dx[3], real drgb_dy[3], real drgb_dz[3]) {
+    const real x = d.x, y = d.y, z = d.z;
     for (int k = 0; k < 3; ++k) {
 #define CF(i) c[(i) * 3 + k]
-        float gx = 0.f, gy = 0.f, gz = 0.f;
+        real gx = 0.f, gy = 0.f, gz = 0.f;
         if (deg > 0) {
             gx += -SH_C1 * CF(3); gy += -SH_C1 * CF(1); gz += SH_C1 * CF(2);
             if (deg > 1) {
@@ -894,7 +911,7 @@ static void sh_dir_jacobian(int deg, const float* c, v3 d, float drgb_dx[3], flo
                 gy += SH_C2[0] * x * CF(4) + SH_C2[1] * z * CF(5) + SH_C2[2] * (-2.f * y) * CF(6) + SH_C2[4] * (-2.f * y) * CF(8);
                 gz += SH_C2[1] * y * CF(5) + SH_C2[2] * (4.f * z) * CF(6) + SH_C2[3] * x * CF(7);
                 if (deg > 2) {
-                    const float xx = x * x, yy = y * y, zz = z * z;
+                    const real xx = x * x, yy = y * y, zz = z * z;
                     gx += SH_C3[0] * (6.f * x * y) * CF(9) + SH_C3[1] * (y * z) * CF(10) + SH_C3[2] * (-2.f * x * y) * CF(11) +
                           SH_C3[3] * (-6.f * x * z) * CF(12) + SH_C3[4] * (4.f * zz - 3.f * xx - yy) * CF(13) +
                           SH_C3[5] * (2.f * x * z) * CF(14) + SH_C3[6] * (3.f * xx - 3.f * yy) * CF(15);
@@ -945,18 +962,18 @@ void gut_oracle_render_backward(const gut_oracle_config* cfg, const gut_oracle_c
                 ray_t r = init_ray(inv, rays_o + pix * 3, rays_d + pix * 3);
                 if (!r.alive) continue;
                 /* initializeBackwardRay (common/rayPayloadBackward.cuh:31-73) */
-                const float Cint[3] = {out_rgba[pix * 4], out_rgba[pix * 4 + 1], out_rgba[pix * 4 + 2]};
-                const float Cgrad[3] = {d_rgba[pix * 4], d_rgba[pix * 4 + 1], d_rgba[pix * 4 + 2]};
-                const float Tint = 1.f - out_rgba[pix * 4 + 3];
-                const float Tgrad = -1.f * d_rgba[pix * 4 + 3];
-                const float Dint = out_dist[pix], Dgrad = d_dist[pix];
-                float T = 1.f, C[3] = {0.f, 0.f, 0.f}, Dp = 0.f;
+                const real Cint[3] = {out_rgba[pix * 4], out_rgba[pix * 4 + 1], out_rgba[pix * 4 + 2]};
+                const real Cgrad[3] = {d_rgba[pix * 4], d_rgba[pix * 4 + 1], d_rgba[pix * 4 + 2]};
+                const real Tint = 1.f - out_rgba[pix * 4 + 3];
+                const real Tgrad = -1.f * d_rgba[pix * 4 + 3];
+                const real Dint = out_dist[pix], Dgrad = d_dist[pix];
+                real T = 1.f, C[3] = {0.f, 0.f, 0.f}, Dp = 0.f;
                 for (uint32_t k = b; k < e; ++k) {
                     const uint32_t idx = svals[k];
                     if (idx == INVALID_U32) break;
                     const particle g = load_particle(particles + (int64_t)idx * 12);
-                    const float prgb[3] = {fmaxf(rgb[idx * 3], 0.f), fmaxf(rgb[idx * 3 + 1], 0.f), fmaxf(rgb[idx * 3 + 2], 0.f)};
-                    float grad[11], rg[3];
+                    const real prgb[3] = {R_FMAX(rgb[idx * 3], 0.f), R_FMAX(rgb[idx * 3 + 1], 0.f), R_FMAX(rgb[idx * 3 + 2], 0.f)};
+                    real grad[11], rg[3];
                     if (hit_backward(cfg, &g, r.o, r.d, prgb, Tint, &T, Tgrad, Cint, C, Cgrad, Dint, &Dp, Dgrad, grad, rg)) {
                         double* ai = a + (size_t)idx * 14;
                         for (int q = 0; q < 11; ++q) ai[q] += (double)grad[q];
@@ -977,26 +994,26 @@ void gut_oracle_render_backward(const gut_oracle_config* cfg, const gut_oracle_c
         for (int t = 0; t < nthreads; ++t)
             for (int q = 0; q < 14; ++q) s[q] += acc[(size_t)t * stride + (size_t)i * 14 + q];
         float* dp = d_particles + i * 12;
-        for (int q = 0; q < 11; ++q) dp[q] = (float)s[q];
+        for (int q = 0; q < 11; ++q) dp[q] = (real)s[q];
         if (tiles_count[i] == 0) continue;
-        const float frg[3] = {(float)s[11], (float)s[12], (float)s[13]};
+        const real frg[3] = {(real)s[11], (real)s[12], (real)s[13]};
         const float* p = particles + i * 12;
         const v3 vraw = V3(p[0] - campos[0], p[1] - campos[1], p[2] - campos[2]);
-        const float len = sqrtf(dot3(vraw, vraw));
+        const real len = R_SQRT(dot3(vraw, vraw));
         const v3 dir = len > 0.f ? scl3(vraw, 1.0f / len) : V3(1.f, 0.f, 0.f);
-        float basis[16];
+        real basis[16];
         sh_basis(sph_degree, dir, basis);
-        float mg[3];
+        real mg[3];
         for (int k = 0; k < 3; ++k) mg[k] = (rgb[i * 3 + k] > 0.0f) ? frg[k] : 0.f; /* clamp mask of max(f+0.5,0) */
         for (int j = 0; j < 16; ++j)
             for (int k = 0; k < 3; ++k) d_sph[i * 48 + j * 3 + k] = basis[j] * mg[k];
-        float jx[3], jy[3], jz[3];
+        real jx[3], jy[3], jz[3];
         sh_dir_jacobian(sph_degree, sph + i * 48, dir, jx, jy, jz);
         const v3 ddir = V3(jx[0] * mg[0] + jx[1] * mg[1] + jx[2] * mg[2], jy[0] * mg[0] + jy[1] * mg[1] + jy[2] * mg[2],
                            jz[0] * mg[0] + jz[1] * mg[1] + jz[2] * mg[2]);
         /* normalize(pos - cam) adjoint: (ddir - dir (dir.ddir)) / len   (gaussianParticles.slang:545-558) */
         if (len > 0.f) {
-            const float dd = dot3(dir, ddir);
+            const real dd = dot3(dir, ddir);
             dp[0] += (ddir.x - dir.x * dd) / len;
             dp[1] += (ddir.y - dir.y * dd) / len;
             dp[2] += (ddir.z - dir.z * dd) / len;
@@ -1010,6 +1027,13 @@ int gut_oracle_hit_backward(const gut_oracle_config* cfg, const float ro[3], con
                             const float prgb[3], float Tint, float* T, float Tgrad, const float Cint[3], float C[3],
                             const float Cgrad[3], float Dint, float* D, float Dgrad, float grad[11], float rgbgrad[3]) {
     const particle g = load_particle(p);
-    return hit_backward(cfg, &g, V3(ro[0], ro[1], ro[2]), V3(rd[0], rd[1], rd[2]), prgb, Tint, T, Tgrad, Cint, C, Cgrad, Dint,
-                        D, Dgrad, grad, rgbgrad);
+    const real prgb_[3] = {prgb[0], prgb[1], prgb[2]}, Cint_[3] = {Cint[0], Cint[1], Cint[2]}, Cgrad_[3] = {Cgrad[0], Cgrad[1], Cgrad[2]};
+    real T_ = *T, D_ = *D, C_[3] = {C[0], C[1], C[2]}, grad_[11], rg_[3] = {0, 0, 0};
+    for (int q = 0; q < 11; ++q) grad_[q] = 0;
+    const int acc = hit_backward(cfg, &g, V3(ro[0], ro[1], ro[2]), V3(rd[0], rd[1], rd[2]), prgb_, Tint, &T_, Tgrad, Cint_, C_, Cgrad_,
+                                 Dint, &D_, Dgrad, grad_, rg_);
+    *T = (float)T_; *D = (float)D_;
+    for (int q = 0; q < 3; ++q) { C[q] = (float)C_[q]; rgbgrad[q] = (float)rg_[q]; }
+    for (int q = 0; q < 11; ++q) grad[q] = (float)grad_[q];
+    return acc;
 }

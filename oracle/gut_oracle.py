@@ -14,6 +14,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_LIB64 = None
 
 
 class Camera(C.Structure):
@@ -36,21 +37,31 @@ class Config(C.Structure):
     ]
 
 
-def build(force: bool = False) -> str:
-    so = os.path.join(_HERE, "libgut_oracle.so")
+def build(force: bool = False, name: str = "libgut_oracle.so") -> str:
+    so = os.path.join(_HERE, name)
     src = os.path.join(_HERE, "gut_oracle.c")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "libgut_oracle.so"], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", _HERE, name], stdout=subprocess.DEVNULL)
     return so
 
 
-def lib():
-    global _LIB
+def _setup(l):
+    l.gut_oracle_bin.restype = C.c_int64
+    l.gut_oracle_higher_msb.restype = C.c_uint32
+    l.gut_oracle_hit_forward.restype = C.c_int
+    return l
+
+
+def lib(f64: bool = False):
+    """The oracle proper (fp32), or with f64=True the variant whose per-ray compositing maths runs in double
+    on the same fp32 inputs and sorted lists (used only to size tolerances)."""
+    global _LIB, _LIB64
+    if f64:
+        if _LIB64 is None:
+            _LIB64 = _setup(C.CDLL(build(name="libgut_oracle_f64.so")))
+        return _LIB64
     if _LIB is None:
-        _LIB = C.CDLL(build())
-        _LIB.gut_oracle_bin.restype = C.c_int64
-        _LIB.gut_oracle_higher_msb.restype = C.c_uint32
-        _LIB.gut_oracle_hit_forward.restype = C.c_int
+        _LIB = _setup(C.CDLL(build()))
     return _LIB
 
 
@@ -136,21 +147,21 @@ def bin_tiles(cfg, cam, pr: Projection) -> Binning:
     return b
 
 
-def render_forward(cfg, cam, rays_o, rays_d, particles, pr: Projection, bn: Binning):
+def render_forward(cfg, cam, rays_o, rays_d, particles, pr: Projection, bn: Binning, f64: bool = False):
     rays_o, rays_d, particles = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3), _f32(particles)
     h, w = cam.height, cam.width
     rgba = np.zeros((h, w, 4), np.float32)
     dist = np.zeros((h, w, 1), np.float32)
     hits = np.zeros((h, w, 1), np.float32)
     sv = bn.sorted_values if bn.sorted_values.size else np.zeros(1, np.uint32)
-    lib().gut_oracle_render_forward(C.byref(cfg), C.byref(cam), _p(rays_o, C.c_float), _p(rays_d, C.c_float),
+    lib(f64).gut_oracle_render_forward(C.byref(cfg), C.byref(cam), _p(rays_o, C.c_float), _p(rays_d, C.c_float),
                                     _p(particles, C.c_float), _p(pr.rgb, C.c_float), _p(sv, C.c_uint32),
                                     _p(bn.ranges, C.c_uint32), _p(rgba, C.c_float), _p(dist, C.c_float),
                                     _p(hits, C.c_float))
     return rgba, dist, hits
 
 
-def render_backward(cfg, cam, rays_o, rays_d, particles, sph, sph_degree, pr, bn, rgba, dist, d_rgba, d_dist):
+def render_backward(cfg, cam, rays_o, rays_d, particles, sph, sph_degree, pr, bn, rgba, dist, d_rgba, d_dist, f64: bool = False):
     rays_o, rays_d = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
     particles, sph = _f32(particles), _f32(sph)
     rgba, dist, d_rgba, d_dist = _f32(rgba), _f32(dist), _f32(d_rgba), _f32(d_dist)
@@ -158,7 +169,7 @@ def render_backward(cfg, cam, rays_o, rays_d, particles, sph, sph_degree, pr, bn
     dp = np.zeros((n, 12), np.float32)
     ds = np.zeros((n, 48), np.float32)
     sv = bn.sorted_values if bn.sorted_values.size else np.zeros(1, np.uint32)
-    lib().gut_oracle_render_backward(C.byref(cfg), C.byref(cam), C.c_int64(n), _p(rays_o, C.c_float), _p(rays_d, C.c_float),
+    lib(f64).gut_oracle_render_backward(C.byref(cfg), C.byref(cam), C.c_int64(n), _p(rays_o, C.c_float), _p(rays_d, C.c_float),
                                      _p(particles, C.c_float), _p(sph, C.c_float), C.c_int32(sph_degree),
                                      _p(pr.rgb, C.c_float), _p(pr.tiles_count, C.c_uint32), _p(sv, C.c_uint32),
                                      _p(bn.ranges, C.c_uint32), _p(rgba, C.c_float), _p(dist, C.c_float),
