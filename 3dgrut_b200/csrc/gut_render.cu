@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
     __shared__ FwdSmem sm;
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
     const int tid = threadIdx.y * kTile + threadIdx.x;
-    const int px = blockIdx.x * kTile + threadIdx.x, py = blockIdx.y * kTile + threadIdx.y;
+    // a warp covers an 8x4 pixel block (not a 16x2 strip): hits are spatially coherent, so a compact footprint
+    // keeps more lanes on the same side of the accept branch
+    const int px = blockIdx.x * kTile + ((tid >> 5) & 1) * 8 + (tid & 7), py = blockIdx.y * kTile + (tid >> 6) * 4 + ((tid >> 3) & 3);
     const bool inside = (px < cam.width) && (py < cam.height);
     const int64_t pix = static_cast<int64_t>(py) * cam.width + px;
 
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(kTilePixels) render_backward_kernel(FrameCamer
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
     const int tid = threadIdx.y * kTile + threadIdx.x;
     const int lane = tid & 31;
-    const int px = blockIdx.x * kTile + threadIdx.x, py = blockIdx.y * kTile + threadIdx.y;
+    const int px = blockIdx.x * kTile + ((tid >> 5) & 1) * 8 + (tid & 7), py = blockIdx.y * kTile + (tid >> 6) * 4 + ((tid >> 3) & 3);
     const bool inside = (px < cam.width) && (py < cam.height);
     const int64_t pix = static_cast<int64_t>(py) * cam.width + px;
 
