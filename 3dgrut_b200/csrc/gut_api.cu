@@ -160,7 +160,7 @@ struct gutb200_ctx {
     // per intersection
     DeviceBuffer keys_in, keys_out, vals_in, vals_out, sort_temp;
     // per tile
-    DeviceBuffer ranges;
+    DeviceBuffer ranges, tile_order;
     // host staging for the *_host entry points
     DeviceBuffer h_particles, h_sph, h_rays_o, h_rays_d, h_rgba, h_dist, h_hits, h_vis, h_drgba, h_ddist, h_dpart, h_dsph;
     uint32_t* pinned_total = nullptr;
@@ -350,7 +350,7 @@ void gutb200_destroy(gutb200_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DeviceBuffer* bufs[] = {&c->tiles_count, &c->offsets, &c->proj, &c->depth, &c->rgb, &c->grad_acc, &c->scan_temp, &c->keys_in,
-                            &c->keys_out, &c->vals_in, &c->vals_out, &c->sort_temp, &c->ranges, &c->h_particles, &c->h_sph,
+                            &c->keys_out, &c->vals_in, &c->vals_out, &c->sort_temp, &c->ranges, &c->tile_order, &c->h_particles, &c->h_sph,
                             &c->h_rays_o, &c->h_rays_d, &c->h_rgba, &c->h_dist, &c->h_hits, &c->h_vis, &c->h_drgba, &c->h_ddist,
                             &c->h_dpart, &c->h_dsph};
     for (DeviceBuffer* b : bufs) b->release();
@@ -390,6 +390,7 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     GUT_CUDA(c, c->depth.reserve(nn * 4, s));
     GUT_CUDA(c, c->rgb.reserve(nn * 12, s));
     GUT_CUDA(c, c->ranges.reserve(static_cast<size_t>(tiles) * 8, s));
+    GUT_CUDA(c, c->tile_order.reserve(static_cast<size_t>(tiles) * 4, s));
     GUT_CUDA(c, c->scan_temp.reserve(scan_temp_bytes(n) + 16, s));
 
     uint32_t total = 0;
@@ -437,10 +438,11 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     }
     {
         StageTimer t(c, 5, s);
+        launch_tile_order(s, c->cam, c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>());
         launch_render_forward(s, c->cam, c->fcfg, rays_o, rays_d, particles, c->rgb.as<float>(), c->vals_out.as<uint32_t>(),
-                              c->ranges.as<uint32_t>(), out_rgba, out_dist, out_hits);
+                              c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), out_rgba, out_dist, out_hits);
     }
-    c->launches++;
+    c->launches += 2;
     GUT_CUDA(c, cudaGetLastError());
     if (c->cfg.enable_timings) {
         GUT_CUDA(c, cudaEventRecord(c->ev[1], s));
@@ -471,7 +473,8 @@ int gutb200_backward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, in
     if (c->num_isect > 0) {
         StageTimer t(c, 6, s);
         launch_render_backward(s, c->cam, c->fcfg, rays_o, rays_d, particles, c->rgb.as<float>(), c->vals_out.as<uint32_t>(),
-                               c->ranges.as<uint32_t>(), out_rgba, d_rgba, out_dist, d_dist, c->grad_acc.as<float>());
+                               c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), out_rgba, d_rgba, out_dist, d_dist,
+                               c->grad_acc.as<float>());
         c->launches++;
     }
     if (n > 0) {

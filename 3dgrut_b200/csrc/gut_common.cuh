@@ -49,13 +49,14 @@ void launch_expand(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cf
                    const ProjRecord* proj, const float* depth, uint64_t* keys, uint32_t* values);
 void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint64_t* sorted_keys, uint32_t* ranges);
 
+void launch_tile_order(cudaStream_t s, const FrameCamera& cam, const uint32_t* ranges, uint32_t* tile_order);
 void launch_render_forward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
                            const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
-                           const uint32_t* ranges, float* out_rgba, float* out_dist, float* out_hits);
+                           const uint32_t* ranges, const uint32_t* tile_order, float* out_rgba, float* out_dist, float* out_hits);
 void launch_render_backward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
                             const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
-                            const uint32_t* ranges, const float* out_rgba, const float* d_rgba, const float* out_dist,
-                            const float* d_dist, float* grad_acc);
+                            const uint32_t* ranges, const uint32_t* tile_order, const float* out_rgba, const float* d_rgba,
+                            const float* out_dist, const float* d_dist, float* grad_acc);
 void launch_project_backward(cudaStream_t s, const FrameCamera& cam, int64_t n, const float* particles, const float* sph,
                              int sph_degree, const float* rgb, const uint32_t* tiles_count, float* grad_acc,
                              float* d_particles, float* d_sph);

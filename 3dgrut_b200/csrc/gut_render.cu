@@ -81,34 +81,36 @@ struct FwdSmem {
     float4 m0[kBatch], m1[kBatch], m2[kBatch], sd[kBatch], col[kBatch];
 };
 
-template <int DEG>
-__global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera cam, FrameConfig cfg,
-                                                                     const float* __restrict__ rays_o,
-                                                                     const float* __restrict__ rays_d,
-                                                                     const float* __restrict__ particles,
-                                                                     const float* __restrict__ rgb,
-                                                                     const uint32_t* __restrict__ sorted_values,
-                                                                     const uint32_t* __restrict__ ranges, float* __restrict__ out_rgba,
-                                                                     float* __restrict__ out_dist, float* __restrict__ out_hits) {
-    __shared__ FwdSmem sm;
-    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-    const int tid = threadIdx.y * kTile + threadIdx.x;
-    // a warp covers an 8x4 pixel block (not a 16x2 strip): hits are spatially coherent, so a compact footprint
-    // keeps more lanes on the same side of the accept branch
-    const int px = blockIdx.x * kTile + ((tid >> 5) & 1) * 8 + (tid & 7), py = blockIdx.y * kTile + (tid >> 6) * 4 + ((tid >> 3) & 3);
-    const bool inside = (px < cam.width) && (py < cam.height);
-    const int64_t pix = static_cast<int64_t>(py) * cam.width + px;
+// pixel of thread `tid` in tile (tx,ty): a warp covers an 8x4 pixel block (not a 16x2 strip) -- hits are spatially
+// coherent, so a compact footprint keeps more lanes on the same side of the accept branch
+__device__ __forceinline__ void tile_pixel(int tile, int grid_x, int tid, int& px, int& py) {
+    const int tx = tile % grid_x, ty = tile / grid_x;
+    px = tx * kTile + ((tid >> 5) & 1) * 8 + (tid & 7);
+    py = ty * kTile + (tid >> 6) * 4 + ((tid >> 3) & 3);
+}
 
-    Ray ray;
-    ray.alive = false;
-    if (inside) ray = make_ray(cam, rays_o, rays_d, pix);
-    const bool valid = inside && ray.alive;
+// world-space origin of the tile's first pixel; when every ray of the tile starts there (always the case for the
+// camera rays the projection stage assumes) the canonical origin S^-1 R^T (o - mu) is computed once per staged
+// particle instead of once per (pixel, particle)
+__device__ __forceinline__ bool tile_common_origin(const FrameCamera& cam, const float* __restrict__ rays_o, int tile, bool inside,
+                                                   int64_t pix, float& ox, float& oy, float& oz) {
+    const int tx = tile % cam.grid_x, ty = tile / cam.grid_x;
+    const int64_t pix0 = static_cast<int64_t>(ty * kTile) * cam.width + tx * kTile;
+    const float ax = rays_o[pix0 * 3 + 0], ay = rays_o[pix0 * 3 + 1], az = rays_o[pix0 * 3 + 2];
+    bool same = true;
+    if (inside) same = (rays_o[pix * 3 + 0] == ax) && (rays_o[pix * 3 + 1] == ay) && (rays_o[pix * 3 + 2] == az);
+    const float* m = cam.s2w;
+    ox = m[0] * ax + m[3] * ay + m[6] * az + m[9];
+    oy = m[1] * ax + m[4] * ay + m[7] * az + m[10];
+    oz = m[2] * ax + m[5] * ay + m[8] * az + m[11];
+    return __syncthreads_and(same);
+}
 
-    float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, dist = 0.f;
-    uint32_t hits = 0;
-    bool alive = valid;
-
-    const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
+template <int DEG, bool UNIFORM>
+__device__ __forceinline__ void forward_tile(const FrameConfig& cfg, FwdSmem& sm, const Ray& ray, float o0x, float o0y, float o0z, int tid,
+                                             uint32_t begin, uint32_t end, const float* __restrict__ particles,
+                                             const float* __restrict__ rgb, const uint32_t* __restrict__ sorted_values, bool& alive,
+                                             float& T, float& cr, float& cg, float& cb, float& dist, uint32_t& hits) {
     for (uint32_t base = begin; base < end; base += kBatch) {
         if (__syncthreads_and(!alive)) break;
         const uint32_t k = base + tid;
@@ -120,9 +122,18 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
             const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
             const float rx = r * x, ry = r * y, rz = r * z;
             const float isx = 1.0f / s.x, isy = 1.0f / s.y, isz = 1.0f / s.z;
-            sm.m0[tid] = make_float4(isx * (1.f - 2.f * (yy + zz)), isx * (2.f * (xy + rz)), isx * (2.f * (xz - ry)), a.x);
-            sm.m1[tid] = make_float4(isy * (2.f * (xy - rz)), isy * (1.f - 2.f * (xx + zz)), isy * (2.f * (yz + rx)), a.y);
-            sm.m2[tid] = make_float4(isz * (2.f * (xz + ry)), isz * (2.f * (yz - rx)), isz * (1.f - 2.f * (xx + yy)), a.z);
+            float4 m0 = make_float4(isx * (1.f - 2.f * (yy + zz)), isx * (2.f * (xy + rz)), isx * (2.f * (xz - ry)), a.x);
+            float4 m1 = make_float4(isy * (2.f * (xy - rz)), isy * (1.f - 2.f * (xx + zz)), isy * (2.f * (yz + rx)), a.y);
+            float4 m2 = make_float4(isz * (2.f * (xz + ry)), isz * (2.f * (yz - rx)), isz * (1.f - 2.f * (xx + yy)), a.z);
+            if (UNIFORM) {  // .w carries the canonical origin instead of the particle position
+                const float vx = o0x - a.x, vy = o0y - a.y, vz = o0z - a.z;
+                m0.w = m0.x * vx + m0.y * vy + m0.z * vz;
+                m1.w = m1.x * vx + m1.y * vy + m1.z * vz;
+                m2.w = m2.x * vx + m2.y * vy + m2.z * vz;
+            }
+            sm.m0[tid] = m0;
+            sm.m1[tid] = m1;
+            sm.m2[tid] = m2;
             sm.sd[tid] = make_float4(s.x, s.y, s.z, a.w);
             sm.col[tid] = make_float4(fmaxf(rgb[idx * 3 + 0], 0.f), fmaxf(rgb[idx * 3 + 1], 0.f), fmaxf(rgb[idx * 3 + 2], 0.f), 0.f);
         }
@@ -130,10 +141,15 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
         const int count = min(kBatch, static_cast<int>(end - base));
         for (int j = 0; alive && j < count; ++j) {
             const float4 m0 = sm.m0[j], m1 = sm.m1[j], m2 = sm.m2[j];
-            const float vx = ray.ox - m0.w, vy = ray.oy - m1.w, vz = ray.oz - m2.w;
-            const float gox = m0.x * vx + m0.y * vy + m0.z * vz;
-            const float goy = m1.x * vx + m1.y * vy + m1.z * vz;
-            const float goz = m2.x * vx + m2.y * vy + m2.z * vz;
+            float gox, goy, goz;
+            if (UNIFORM) {
+                gox = m0.w; goy = m1.w; goz = m2.w;
+            } else {
+                const float vx = ray.ox - m0.w, vy = ray.oy - m1.w, vz = ray.oz - m2.w;
+                gox = m0.x * vx + m0.y * vy + m0.z * vz;
+                goy = m1.x * vx + m1.y * vy + m1.z * vz;
+                goz = m2.x * vx + m2.y * vy + m2.z * vz;
+            }
             const float ax = m0.x * ray.dx + m0.y * ray.dy + m0.z * ray.dz;
             const float ay = m1.x * ray.dx + m1.y * ray.dy + m1.z * ray.dz;
             const float az = m2.x * ray.dx + m2.y * ray.dy + m2.z * ray.dz;
@@ -165,6 +181,42 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
             }
         }
     }
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera cam, FrameConfig cfg,
+                                                                     const float* __restrict__ rays_o,
+                                                                     const float* __restrict__ rays_d,
+                                                                     const float* __restrict__ particles,
+                                                                     const float* __restrict__ rgb,
+                                                                     const uint32_t* __restrict__ sorted_values,
+                                                                     const uint32_t* __restrict__ ranges,
+                                                                     const uint32_t* __restrict__ tile_order, float* __restrict__ out_rgba,
+                                                                     float* __restrict__ out_dist, float* __restrict__ out_hits) {
+    __shared__ FwdSmem sm;
+    const int tile = tile_order[blockIdx.x];  // heaviest tiles first (tile_order_kernel): shortens the tail of the grid
+    const int tid = threadIdx.x;
+    int px, py;
+    tile_pixel(tile, cam.grid_x, tid, px, py);
+    const bool inside = (px < cam.width) && (py < cam.height);
+    const int64_t pix = static_cast<int64_t>(py) * cam.width + px;
+
+    Ray ray;
+    ray.alive = false;
+    if (inside) ray = make_ray(cam, rays_o, rays_d, pix);
+    const bool valid = inside && ray.alive;
+    float o0x, o0y, o0z;
+    const bool uniform = tile_common_origin(cam, rays_o, tile, inside, pix, o0x, o0y, o0z);
+
+    float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, dist = 0.f;
+    uint32_t hits = 0;
+    bool alive = valid;
+    const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
+    if (uniform)
+        forward_tile<DEG, true>(cfg, sm, ray, o0x, o0y, o0z, tid, begin, end, particles, rgb, sorted_values, alive, T, cr, cg, cb, dist, hits);
+    else
+        forward_tile<DEG, false>(cfg, sm, ray, o0x, o0y, o0z, tid, begin, end, particles, rgb, sorted_values, alive, T, cr, cg, cb, dist, hits);
+
     if (valid) {  // finalizeRay (rayPayload.cuh:160-193); invalid rays keep the initial buffer values
         reinterpret_cast<float4*>(out_rgba)[pix] = make_float4(cr, cg, cb, 1.0f - T);
         out_dist[pix] = dist;
@@ -176,6 +228,31 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
     }
 }
 
+// Order tiles by decreasing list length (bucketed by log2): one small single-CTA kernel per frame.
+__global__ void __launch_bounds__(1024) tile_order_kernel(int num_tiles, const uint32_t* __restrict__ ranges, uint32_t* __restrict__ order) {
+    __shared__ uint32_t hist[34];
+    if (threadIdx.x < 34) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < num_tiles; t += blockDim.x) {
+        const uint32_t c = ranges[t * 2 + 1] - ranges[t * 2];
+        atomicAdd(&hist[__clz(c) + 1], 1u);  // __clz(0) = 32 -> last bucket; long lists -> small bucket index
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int b = 1; b < 34; ++b) {
+            const uint32_t h = hist[b];
+            hist[b] = run;
+            run += h;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < num_tiles; t += blockDim.x) {
+        const uint32_t c = ranges[t * 2 + 1] - ranges[t * 2];
+        order[atomicAdd(&hist[__clz(c) + 1], 1u)] = static_cast<uint32_t>(t);
+    }
+}
+
 // ----------------------------------------------------------------------------------------------------------
 // G7 backward
 // staged record, 7 x float4:
@@ -184,6 +261,7 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
 
 struct BwdSmem {
     float4 r0[kBatch], r1[kBatch], r2[kBatch], sc[kBatch], is[kBatch], qt[kBatch], cl[kBatch];
+    float4 go[kBatch];  // canonical origin of the tile's common ray origin (UNIFORM path)
 };
 
 // sum 16 per-lane values over the warp; lane L returns the total of component (L >> 1). 16 SHFL in all.
@@ -219,45 +297,13 @@ __device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lan
     return v[0];
 }
 
-template <int DEG>
-__global__ void __launch_bounds__(kTilePixels) render_backward_kernel(FrameCamera cam, FrameConfig cfg,
-                                                                      const float* __restrict__ rays_o,
-                                                                      const float* __restrict__ rays_d,
-                                                                      const float* __restrict__ particles,
-                                                                      const float* __restrict__ rgb,
-                                                                      const uint32_t* __restrict__ sorted_values,
-                                                                      const uint32_t* __restrict__ ranges,
-                                                                      const float* __restrict__ out_rgba, const float* __restrict__ d_rgba,
-                                                                      const float* __restrict__ out_dist, const float* __restrict__ d_dist,
-                                                                      float* __restrict__ grad_acc) {
-    __shared__ BwdSmem sm;
-    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-    const int tid = threadIdx.y * kTile + threadIdx.x;
-    const int lane = tid & 31;
-    const int px = blockIdx.x * kTile + ((tid >> 5) & 1) * 8 + (tid & 7), py = blockIdx.y * kTile + (tid >> 6) * 4 + ((tid >> 3) & 3);
-    const bool inside = (px < cam.width) && (py < cam.height);
-    const int64_t pix = static_cast<int64_t>(py) * cam.width + px;
-
-    Ray ray;
-    ray.alive = false;
-    if (inside) ray = make_ray(cam, rays_o, rays_d, pix);
-    bool alive = inside && ray.alive;
-
-    // initializeBackwardRay (kernels/cuda/common/rayPayloadBackward.cuh:31-73)
-    float Cix = 0.f, Ciy = 0.f, Ciz = 0.f, Cgx = 0.f, Cgy = 0.f, Cgz = 0.f, Tint = 1.f, Tgrad = 0.f, Dint = 0.f, Dgrad = 0.f;
-    if (alive) {
-        const float4 o = reinterpret_cast<const float4*>(out_rgba)[pix];
-        const float4 g = reinterpret_cast<const float4*>(d_rgba)[pix];
-        Cix = o.x; Ciy = o.y; Ciz = o.z;
-        Cgx = g.x; Cgy = g.y; Cgz = g.z;
-        Tint = 1.f - o.w;
-        Tgrad = -1.f * g.w;
-        Dint = out_dist[pix];
-        Dgrad = d_dist[pix];
-    }
+template <int DEG, bool UNIFORM>
+__device__ __forceinline__ void backward_tile(const FrameConfig& cfg, BwdSmem& sm, const Ray& ray, float o0x, float o0y, float o0z, int tid,
+                                              int lane, uint32_t begin, uint32_t end, const float* __restrict__ particles,
+                                              const float* __restrict__ rgb, const uint32_t* __restrict__ sorted_values, bool alive,
+                                              float Cix, float Ciy, float Ciz, float Cgx, float Cgy, float Cgz, float Tint, float Tgrad,
+                                              float Dint, float Dgrad, float* __restrict__ grad_acc) {
     float T = 1.f, Cx = 0.f, Cy = 0.f, Cz = 0.f, D = 0.f;
-
-    const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
     for (uint32_t base = begin; base < end; base += kBatch) {
         if (__syncthreads_and(!alive)) break;
         const uint32_t k = base + tid;
@@ -276,6 +322,12 @@ __global__ void __launch_bounds__(kTilePixels) render_backward_kernel(FrameCamer
             sm.qt[tid] = q;
             sm.cl[tid] = make_float4(fmaxf(rgb[idx * 3 + 0], 0.f), fmaxf(rgb[idx * 3 + 1], 0.f), fmaxf(rgb[idx * 3 + 2], 0.f),
                                      __uint_as_float(idx));
+            if (UNIFORM) {
+                const float vx = o0x - a.x, vy = o0y - a.y, vz = o0z - a.z;
+                const float4 t0 = sm.r0[tid], t1 = sm.r1[tid], t2 = sm.r2[tid];
+                sm.go[tid] = make_float4((t0.x * vx + t0.y * vy + t0.z * vz) / s.x, (t1.x * vx + t1.y * vy + t1.z * vz) / s.y,
+                                         (t2.x * vx + t2.y * vy + t2.z * vz) / s.z, 0.f);
+            }
         }
         __syncthreads();
         const int count = min(kBatch, static_cast<int>(end - base));
@@ -289,10 +341,15 @@ __global__ void __launch_bounds__(kTilePixels) render_backward_kernel(FrameCamer
                 const float4 r0 = sm.r0[j], r1 = sm.r1[j], r2 = sm.r2[j], sc = sm.sc[j], is = sm.is[j];
                 // canonical ray (processHitBwd, gaussianParticles.cuh:520-532)
                 const float pcx = ray.ox - r0.w, pcy = ray.oy - r1.w, pcz = ray.oz - r2.w;              // gposc
-                const float prx = r0.x * pcx + r0.y * pcy + r0.z * pcz;                                   // gposcr
-                const float pry = r1.x * pcx + r1.y * pcy + r1.z * pcz;
-                const float prz = r2.x * pcx + r2.y * pcy + r2.z * pcz;
-                const float gox = is.x * prx, goy = is.y * pry, goz = is.z * prz;                         // gro
+                float gox, goy, goz;                                                                      // gro
+                if (UNIFORM) {
+                    const float4 g0 = sm.go[j];
+                    gox = g0.x; goy = g0.y; goz = g0.z;
+                } else {
+                    gox = is.x * (r0.x * pcx + r0.y * pcy + r0.z * pcz);
+                    goy = is.y * (r1.x * pcx + r1.y * pcy + r1.z * pcz);
+                    goz = is.z * (r2.x * pcx + r2.y * pcy + r2.z * pcz);
+                }
                 const float drx = r0.x * ray.dx + r0.y * ray.dy + r0.z * ray.dz;                          // rayDirR
                 const float dry = r1.x * ray.dx + r1.y * ray.dy + r1.z * ray.dz;
                 const float drz = r2.x * ray.dx + r2.y * ray.dy + r2.z * ray.dz;
@@ -347,9 +404,9 @@ __global__ void __launch_bounds__(kTilePixels) render_backward_kernel(FrameCamer
                     const float go_gz = kx * gdy - ky * gdx - gdz * sd;
                     // gro = (1/s) gposcr  (:705-713)
                     const float prg_x = is.x * go_gx, prg_y = is.y * go_gy, prg_z = is.z * go_gz;          // gposcrGrd
-                    float sgx = ddx * hgx - prx * is.x * is.x * go_gx;                                      // gsclRayHitGrd + gsclGrdGro
-                    float sgy = ddy * hgy - pry * is.y * is.y * go_gy;
-                    float sgz = ddz * hgz - prz * is.z * is.z * go_gz;
+                    float sgx = ddx * hgx - gox * prg_x;               // gsclRayHitGrd + gsclGrdGro (gposcr/s^2 = gro/s)
+                    float sgy = ddy * hgy - goy * prg_y;
+                    float sgz = ddz * hgz - goz * prg_z;
                     // gposcr = R^T gposc  (:715-726)
                     g[0] = -(prg_x * r0.x + prg_y * r1.x + prg_z * r2.x);
                     g[1] = -(prg_x * r0.y + prg_y * r1.y + prg_z * r2.y);
@@ -361,11 +418,11 @@ __global__ void __launch_bounds__(kTilePixels) render_backward_kernel(FrameCamer
                     const float ug_y = l > 0.f ? il * gd_gy - il3 * uy * du : 0.f;
                     const float ug_z = l > 0.f ? il * gd_gz - il3 * uz * du : 0.f;
                     // grdu = (1/s) rayDirR  (:733-738)
-                    sgx -= drx * is.x * is.x * ug_x;
-                    sgy -= dry * is.y * is.y * ug_y;
-                    sgz -= drz * is.z * is.z * ug_z;
-                    g[8] = sgx; g[9] = sgy; g[10] = sgz;
                     const float rdg_x = is.x * ug_x, rdg_y = is.y * ug_y, rdg_z = is.z * ug_z;             // rayDirRGrd
+                    sgx -= ux * rdg_x;                                  // rayDirR/s^2 = grdu/s
+                    sgy -= uy * rdg_y;
+                    sgz -= uz * rdg_z;
+                    g[8] = sgx; g[9] = sgy; g[10] = sgz;
                     // rotation rows m_i receive dM_i = prg_i * gposc + rdg_i * d   (matmul_bw_quat twice, :719-747)
                     const float m00 = prg_x * pcx + rdg_x * ray.dx, m01 = prg_x * pcy + rdg_x * ray.dy, m02 = prg_x * pcz + rdg_x * ray.dz;
                     const float m10 = prg_y * pcx + rdg_y * ray.dx, m11 = prg_y * pcy + rdg_y * ray.dy, m12 = prg_y * pcz + rdg_y * ray.dz;
@@ -389,6 +446,56 @@ __global__ void __launch_bounds__(kTilePixels) render_backward_kernel(FrameCamer
             }
         }
     }
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(kTilePixels, 3) render_backward_kernel(FrameCamera cam, FrameConfig cfg,
+                                                                      const float* __restrict__ rays_o,
+                                                                      const float* __restrict__ rays_d,
+                                                                      const float* __restrict__ particles,
+                                                                      const float* __restrict__ rgb,
+                                                                      const uint32_t* __restrict__ sorted_values,
+                                                                      const uint32_t* __restrict__ ranges,
+                                                                      const uint32_t* __restrict__ tile_order,
+                                                                      const float* __restrict__ out_rgba, const float* __restrict__ d_rgba,
+                                                                      const float* __restrict__ out_dist, const float* __restrict__ d_dist,
+                                                                      float* __restrict__ grad_acc) {
+    __shared__ BwdSmem sm;
+    const int tile = tile_order[blockIdx.x];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    int px, py;
+    tile_pixel(tile, cam.grid_x, tid, px, py);
+    const bool inside = (px < cam.width) && (py < cam.height);
+    const int64_t pix = static_cast<int64_t>(py) * cam.width + px;
+
+    Ray ray;
+    ray.alive = false;
+    if (inside) ray = make_ray(cam, rays_o, rays_d, pix);
+    bool alive = inside && ray.alive;
+
+    // initializeBackwardRay (kernels/cuda/common/rayPayloadBackward.cuh:31-73)
+    float Cix = 0.f, Ciy = 0.f, Ciz = 0.f, Cgx = 0.f, Cgy = 0.f, Cgz = 0.f, Tint = 1.f, Tgrad = 0.f, Dint = 0.f, Dgrad = 0.f;
+    if (alive) {
+        const float4 o = reinterpret_cast<const float4*>(out_rgba)[pix];
+        const float4 g = reinterpret_cast<const float4*>(d_rgba)[pix];
+        Cix = o.x; Ciy = o.y; Ciz = o.z;
+        Cgx = g.x; Cgy = g.y; Cgz = g.z;
+        Tint = 1.f - o.w;
+        Tgrad = -1.f * g.w;
+        Dint = out_dist[pix];
+        Dgrad = d_dist[pix];
+    }
+
+    float o0x, o0y, o0z;
+    const bool uniform = tile_common_origin(cam, rays_o, tile, inside, pix, o0x, o0y, o0z);
+    const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
+    if (uniform)
+        backward_tile<DEG, true>(cfg, sm, ray, o0x, o0y, o0z, tid, lane, begin, end, particles, rgb, sorted_values, alive, Cix, Ciy, Ciz, Cgx,
+                                 Cgy, Cgz, Tint, Tgrad, Dint, Dgrad, grad_acc);
+    else
+        backward_tile<DEG, false>(cfg, sm, ray, o0x, o0y, o0z, tid, lane, begin, end, particles, rgb, sorted_values, alive, Cix, Ciy, Ciz, Cgx,
+                                  Cgy, Cgz, Tint, Tgrad, Dint, Dgrad, grad_acc);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -499,25 +606,29 @@ __global__ void __launch_bounds__(128) project_backward_kernel(FrameCamera cam, 
 
 }  // namespace
 
+void launch_tile_order(cudaStream_t s, const FrameCamera& cam, const uint32_t* ranges, uint32_t* tile_order) {
+    tile_order_kernel<<<1, 1024, 0, s>>>(cam.grid_x * cam.grid_y, ranges, tile_order);
+}
+
 void launch_render_forward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
                            const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
-                           const uint32_t* ranges, float* out_rgba, float* out_dist, float* out_hits) {
-    const dim3 grid(cam.grid_x, cam.grid_y, 1), block(kTile, kTile, 1);
+                           const uint32_t* ranges, const uint32_t* tile_order, float* out_rgba, float* out_dist, float* out_hits) {
+    const unsigned grid = cam.grid_x * cam.grid_y;
     if (cfg.kernel_degree == 4)
-        render_forward_kernel<4><<<grid, block, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, out_rgba, out_dist, out_hits);
+        render_forward_kernel<4><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, out_rgba, out_dist, out_hits);
     else
-        render_forward_kernel<2><<<grid, block, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, out_rgba, out_dist, out_hits);
+        render_forward_kernel<2><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, out_rgba, out_dist, out_hits);
 }
 
 void launch_render_backward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
                             const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
-                            const uint32_t* ranges, const float* out_rgba, const float* d_rgba, const float* out_dist,
-                            const float* d_dist, float* grad_acc) {
-    const dim3 grid(cam.grid_x, cam.grid_y, 1), block(kTile, kTile, 1);
+                            const uint32_t* ranges, const uint32_t* tile_order, const float* out_rgba, const float* d_rgba,
+                            const float* out_dist, const float* d_dist, float* grad_acc) {
+    const unsigned grid = cam.grid_x * cam.grid_y;
     if (cfg.kernel_degree == 4)
-        render_backward_kernel<4><<<grid, block, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, out_rgba, d_rgba, out_dist, d_dist, grad_acc);
+        render_backward_kernel<4><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, out_rgba, d_rgba, out_dist, d_dist, grad_acc);
     else
-        render_backward_kernel<2><<<grid, block, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, out_rgba, d_rgba, out_dist, d_dist, grad_acc);
+        render_backward_kernel<2><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, out_rgba, d_rgba, out_dist, d_dist, grad_acc);
 }
 
 void launch_project_backward(cudaStream_t s, const FrameCamera& cam, int64_t n, const float* particles, const float* sph,

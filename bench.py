@@ -70,7 +70,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -233,13 +233,13 @@ def main():
         torch.cuda.synchronize(dev)
 
     ctx = raster.native_context(dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # runs through warm-up and the timed region (both under load)
     for s in range(args.warmup):
         step_device(s)
     barrier()
     launches0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for s in range(args.steps):
