@@ -166,3 +166,92 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._lib.gutb200_launch_count(self._h))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# include/grt_b200.h (3DGRT: LBVH build + ordered ray tracing), same shared library
+
+class GrtConfig(C.Structure):
+    """grtb200_config"""
+
+    _fields_ = [("kernel_degree", C.c_int32), ("min_response", C.c_float), ("min_alpha", C.c_float), ("max_alpha", C.c_float),
+                ("density_clamping", C.c_int32)]
+
+
+GRT_EXPORTS = ["grtb200_default_config", "grtb200_create", "grtb200_destroy", "grtb200_last_error", "grtb200_build_bvh", "grtb200_trace",
+               "grtb200_trace_bwd", "grtb200_scene_aabb", "grtb200_launch_count"]
+
+
+def _grt_lib():
+    lib = load()
+    if not getattr(lib, "_grt_ready", False):
+        vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+        lib.grtb200_last_error.restype = C.c_char_p
+        lib.grtb200_last_error.argtypes = [vp]
+        lib.grtb200_launch_count.restype = i64
+        lib.grtb200_launch_count.argtypes = [vp]
+        lib.grtb200_create.argtypes = [C.POINTER(GrtConfig), C.c_int, C.POINTER(vp)]
+        lib.grtb200_destroy.argtypes = [vp]
+        lib.grtb200_build_bvh.argtypes = [vp, vp, i64, vp, vp, vp, vp, i32, i32]
+        lib.grtb200_trace.argtypes = [vp, vp, i64, vp, vp, i32, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.grtb200_trace_bwd.argtypes = [vp, vp, i64, vp, vp, i32, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.grtb200_scene_aabb.argtypes = [vp, vp]
+        lib._grt_ready = True
+    return lib
+
+
+def grt_default_config() -> GrtConfig:
+    cfg = GrtConfig()
+    _grt_lib().grtb200_default_config(C.byref(cfg))
+    return cfg
+
+
+class GrtContext:
+    """Owning wrapper of a grtb200_ctx*."""
+
+    def __init__(self, cfg: GrtConfig, device: int = 0):
+        self._lib = _grt_lib()
+        self._h = C.c_void_p()
+        rc = self._lib.grtb200_create(C.byref(cfg), int(device), C.byref(self._h))
+        if rc != 0 or not self._h:
+            raise RuntimeError(f"grtb200_create failed (rc={rc}): a CUDA device is required, there is no CPU path")
+        self.cfg = cfg
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.grtb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: {self._lib.grtb200_last_error(self._h).decode()}")
+
+    def build_bvh(self, stream, n, pos, rot, scl, dns, rebuild=True, allow_update=False):
+        self._check(self._lib.grtb200_build_bvh(self._h, stream, n, pos, rot, scl, dns, int(rebuild), int(allow_update)), "grtb200_build_bvh")
+
+    def trace(self, stream, n, particles, sph, sph_degree, min_t, batch, height, width, rays_o, rays_d, r2w_host, out_rgb, out_alpha,
+              out_dist, out_hits, visibility):
+        self._check(self._lib.grtb200_trace(self._h, stream, n, particles, sph, sph_degree, min_t, batch, height, width, rays_o, rays_d,
+                                            r2w_host, out_rgb, out_alpha, out_dist, out_hits, visibility), "grtb200_trace")
+
+    def trace_bwd(self, stream, n, particles, sph, sph_degree, min_t, batch, height, width, rays_o, rays_d, r2w_host, out_rgb, out_alpha,
+                  out_dist, d_rgb, d_alpha, d_dist, d_particles, d_sph):
+        self._check(self._lib.grtb200_trace_bwd(self._h, stream, n, particles, sph, sph_degree, min_t, batch, height, width, rays_o, rays_d,
+                                                r2w_host, out_rgb, out_alpha, out_dist, d_rgb, d_alpha, d_dist, d_particles, d_sph),
+                    "grtb200_trace_bwd")
+
+    def scene_aabb(self):
+        import numpy as np
+
+        out = np.zeros(6, np.float32)
+        self._check(self._lib.grtb200_scene_aabb(self._h, out.ctypes.data), "grtb200_scene_aabb")
+        return out
+
+    def launch_count(self) -> int:
+        return int(self._lib.grtb200_launch_count(self._h))

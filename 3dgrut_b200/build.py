@@ -23,6 +23,7 @@ UNITS = {
     # flush-to-zero, approximate div/sqrt/exp; parity is tolerance-based for these
     "gut_render.cu": ["--use_fast_math"],
     "gut_api.cu": ["-fmad=false"],
+    "grt.cu": ["--use_fast_math"],
 }
 
 
@@ -34,7 +35,7 @@ def _nvcc() -> str:
 
 
 def sources():
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "gut_b200.h"), os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "gut_b200.h"), os.path.join(HERE, "..", "include", "grt_b200.h"), os.path.abspath(__file__)]
     return deps
 
 

@@ -34,4 +34,17 @@ void run_sort_pairs(cudaStream_t s, void* temp, size_t temp_bytes, const uint64_
     cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, n, 0, end_bit, s);
 }
 
+// 32-bit (Morton code, particle) pairs of the 3DGRT LBVH build (grt.cu)
+size_t sort32_temp_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr),
+                                    static_cast<const uint32_t*>(nullptr), static_cast<uint32_t*>(nullptr), n, 0, 30);
+    return bytes;
+}
+
+void run_sort32_pairs(cudaStream_t s, void* temp, size_t temp_bytes, const uint32_t* kin, uint32_t* kout, const uint32_t* vin,
+                      uint32_t* vout, int64_t n) {
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, n, 0, 30, s);
+}
+
 }  // namespace gutb200

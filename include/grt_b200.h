@@ -1,0 +1,67 @@
+/*
+ * include/grt_b200.h -- C ABI of the B200-native 3DGRT tracer (same shared library: 3dgrut_b200/libgut_b200.so).
+ *
+ * Replaces the OptiX-backed pybind class of the reference (threedgrt_tracer/bindings.cpp:32-38,
+ * include/3dgrt/optixTracer.h:128-177) -- B200 has no RT cores, so the acceleration structure is a Morton-code
+ * LBVH built and traversed by our own kernels:
+ *
+ *   grtb200_create / destroy   <- OptixTracer::OptixTracer / ~OptixTracer        (src/optixTracer.cpp:153-343)
+ *   grtb200_build_bvh          <- OptixTracer::buildBVH                           (src/optixTracer.cpp:616-890)
+ *   grtb200_trace              <- OptixTracer::trace   -> __raygen__rg            (src/optixTracer.cpp:893-960, src/kernels/cuda/referenceOptix.cu:103-186)
+ *   grtb200_trace_bwd          <- OptixTracer::traceBwd -> bwd __raygen__rg        (src/optixTracer.cpp:962-1031, src/kernels/cuda/referenceBwdOptix.cu:103-170)
+ *
+ * Layouts (fp32): particles [N,12] = pos3, density, quat(wxyz), scale3, pad; sph [N,48]; rays_o/rays_d [B,H,W,3]
+ * (R = B*H*W rays, ray space); ray_to_world = first three rows of T_to_world, row major [3,4], HOST pointer
+ * (the reference copies it to the host too, optixTracer.cpp:931); out_rgb [R,3], out_alpha [R], out_dist [R,2] =
+ * (integrated distance, distance of the last processed hit), out_hits [R], visibility [N].
+ * All other pointers are device pointers; `stream` is a cudaStream_t.  Returns 0 on success.
+ */
+#ifndef GRT_B200_H
+#define GRT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct grtb200_config {
+    int32_t kernel_degree;   /* render.particle_kernel_degree: 4 (3DGRT default) or 2   */
+    float min_response;      /* render.particle_kernel_min_response  0.0113              */
+    float min_alpha;         /* alphaMinThreshold 1/255 (optixTracer.cpp:928)            */
+    float max_alpha;         /* render.particle_kernel_max_alpha 0.99                    */
+    int32_t density_clamping; /* render.particle_kernel_density_clamping (true)          */
+} grtb200_config;
+
+typedef struct grtb200_ctx grtb200_ctx;
+
+void grtb200_default_config(grtb200_config* cfg);
+int grtb200_create(const grtb200_config* cfg, int device, grtb200_ctx** out);
+void grtb200_destroy(grtb200_ctx* ctx);
+const char* grtb200_last_error(const grtb200_ctx* ctx);
+
+/* (Re)build the LBVH over the particles' bounding proxies.  `rebuild`/`allow_update` are accepted for API
+ * compatibility; every call is a full rebuild (the reference's default config also rebuilds every step). */
+int grtb200_build_bvh(grtb200_ctx* ctx, void* stream, int64_t n, const float* pos, const float* rot, const float* scl,
+                      const float* dns, int32_t rebuild, int32_t allow_update);
+
+int grtb200_trace(grtb200_ctx* ctx, void* stream, int64_t n, const float* particles, const float* sph, int32_t sph_degree,
+                  float min_transmittance, int32_t batch, int32_t height, int32_t width, const float* rays_o,
+                  const float* rays_d, const float* ray_to_world_host, float* out_rgb, float* out_alpha, float* out_dist,
+                  float* out_hits, float* visibility);
+
+int grtb200_trace_bwd(grtb200_ctx* ctx, void* stream, int64_t n, const float* particles, const float* sph, int32_t sph_degree,
+                      float min_transmittance, int32_t batch, int32_t height, int32_t width, const float* rays_o,
+                      const float* rays_d, const float* ray_to_world_host, const float* out_rgb, const float* out_alpha,
+                      const float* out_dist, const float* d_rgb, const float* d_alpha, const float* d_dist, float* d_particles,
+                      float* d_sph);
+
+/* Scene bounding box of the last build: min xyz, max xyz (host array of 6 floats; synchronises). */
+int grtb200_scene_aabb(grtb200_ctx* ctx, float* aabb6);
+
+int64_t grtb200_launch_count(const grtb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

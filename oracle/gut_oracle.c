@@ -1037,3 +1037,265 @@ int gut_oracle_hit_backward(const gut_oracle_config* cfg, const float ro[3], con
     for (int q = 0; q < 11; ++q) grad[q] = (float)grad_[q];
     return acc;
 }
+
+/* ========================================================================================== */
+/* 3DGRT (threedgrt_tracer/): brute-force restatement of the ordered ray tracer.               */
+/* No BVH here: every ray tests every particle proxy, which is what "all AABB-overlapping      */
+/* candidates reach the intersection program" means for OptiX.          */
+/* ========================================================================================== */
+
+#define GRT_K 16 /* PipelineParameters::MaxNumHitPerTrace (include/3dgrt/pipelineParameters.h:82) */
+
+/* kernelScale (threedgrt_tracer/src/particlePrimitives.cu:27-51), generalized Gaussian branch */
+static float grt_kernel_scale(float density, float min_response, int clamping, float degree) {
+    const float modulation = clamping ? density : 1.0f;
+    const float minr = fminf(min_response / modulation, 0.97f);
+    const float b = degree;
+    const float a = -4.5f / powf(3.0f, b);
+    return powf(logf(minr) / a, 1.0f / b);
+}
+
+/* proxy of one particle: instance transform A = [R diag(kscl) | mu] (particlePrimitives.cu:543-610) */
+void grt_oracle_proxies(const gut_oracle_config* cfg, int32_t clamping, int64_t n, const float* particles, float* kscl /*[N,3]*/,
+                        float* scene_aabb /*[6] min xyz, max xyz*/) {
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int64_t i = 0; i < n; ++i) {
+        const float* p = particles + i * 12;
+        const float ks = grt_kernel_scale(p[3], cfg->min_kernel_density, clamping, (float)cfg->kernel_degree);
+        const float k[3] = {ks * p[8], ks * p[9], ks * p[10]};
+        kscl[i * 3] = k[0]; kscl[i * 3 + 1] = k[1]; kscl[i * 3 + 2] = k[2];
+        /* rows of R (quaternionWXYZToMatrixTranspose, include/3dgrt/mathUtils.h) */
+        const float r = p[4], x = p[5], y = p[6], z = p[7];
+        const float R[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                               {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                               {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+        for (int c = 0; c < 8; ++c) {
+            const float v[3] = {((c & 4) ? 1.f : -1.f) * k[0], ((c & 2) ? 1.f : -1.f) * k[1], ((c & 1) ? 1.f : -1.f) * k[2]};
+            for (int a = 0; a < 3; ++a) {
+                const float w = (R[a][0] * v[0] + R[a][1] * v[1] + R[a][2] * v[2]) + p[a];
+                lo[a] = fminf(lo[a], w);
+                hi[a] = fmaxf(hi[a], w);
+            }
+        }
+    }
+    for (int a = 0; a < 3; ++a) { scene_aabb[a] = lo[a]; scene_aabb[3 + a] = hi[a]; }
+}
+
+typedef struct { float t, t_out; uint32_t pid; } grt_cand;
+
+static int grt_cand_cmp(const void* a, const void* b) {
+    const grt_cand* x = (const grt_cand*)a; const grt_cand* y = (const grt_cand*)b;
+    if (x->t < y->t) return -1;
+    if (x->t > y->t) return 1;
+    return (x->pid > y->pid) - (x->pid < y->pid);
+}
+
+/* Candidates of one ray on (tmin, tmax): the ray segment meets the proxy box (OptiX traversal), the custom
+ * intersection accepts (intersectInstanceParticle, include/3dgrt/kernels/cuda/gaussianParticles.cuh:449-465). */
+static int64_t grt_candidates(int64_t n, const float* particles, const float* kscl, const float o[3], const float d[3], float tmin,
+                              float tmax, grt_cand* out) {
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float* p = particles + i * 12;
+        const float r = p[4], x = p[5], y = p[6], z = p[7];
+        /* rows of the inverse rotation = columns of R */
+        const float Rt[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y + r * z), 2.f * (x * z - r * y)},
+                                {2.f * (x * y - r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + r * x)},
+                                {2.f * (x * z + r * y), 2.f * (y * z - r * x), 1.f - 2.f * (x * x + y * y)}};
+        const float v[3] = {o[0] - p[0], o[1] - p[1], o[2] - p[2]};
+        float oi[3], di[3];
+        for (int a = 0; a < 3; ++a) {
+            oi[a] = (Rt[a][0] * v[0] + Rt[a][1] * v[1] + Rt[a][2] * v[2]) / kscl[i * 3 + a];
+            di[a] = (Rt[a][0] * d[0] + Rt[a][1] * d[1] + Rt[a][2] * d[2]) / kscl[i * 3 + a];
+        }
+        /* unit-cube slab test on [tmin, tmax] */
+        float tin = tmin, tout = tmax;
+        for (int a = 0; a < 3; ++a) {
+            const float t0 = (-1.f - oi[a]) / di[a], t1 = (1.f - oi[a]) / di[a];
+            tin = fmaxf(tin, fminf(t0, t1));
+            tout = fminf(tout, fmaxf(t0, t1));
+        }
+        if (!(tin <= tout)) continue;
+        const float num = -(oi[0] * di[0] + oi[1] * di[1] + oi[2] * di[2]);
+        const float den = 1.f / (di[0] * di[0] + di[1] * di[1] + di[2] * di[2]);
+        const float t = num * den;
+        if (!((t > tmin) && (t < tmax))) continue;
+        const float l = di[0] * di[0] + di[1] * di[1] + di[2] * di[2];
+        const float il = l > 0.f ? 1.0f / sqrtf(l) : 1.f;
+        const float n0 = di[0] * il, n1 = di[1] * il, n2 = di[2] * il;
+        const float c0 = n1 * oi[2] - n2 * oi[1], c1 = n2 * oi[0] - n0 * oi[2], c2 = n0 * oi[1] - n1 * oi[0];
+        if (!((c0 * c0 + c1 * c1 + c2 * c2) * den < 9.f)) continue; /* hitMaxParticleSquaredDistance (pipelineParameters.h:69) */
+        out[m].t = t; out[m].t_out = tout; out[m].pid = (uint32_t)i; m++;
+    }
+    qsort(out, (size_t)m, sizeof(grt_cand), grt_cand_cmp);
+    return m;
+}
+
+static void grt_ray(const float* r2w /*[3,4] row major*/, const float* ro, const float* rd, float o[3], float d[3]) {
+    /* rayWorldOrigin / rayWorldDirection (pipelineParameters.h:96-114) */
+    for (int a = 0; a < 3; ++a) {
+        o[a] = r2w[a * 4] * ro[0] + r2w[a * 4 + 1] * ro[1] + r2w[a * 4 + 2] * ro[2] + r2w[a * 4 + 3];
+        d[a] = r2w[a * 4] * rd[0] + r2w[a * 4 + 1] * rd[1] + r2w[a * 4 + 2] * rd[2];
+    }
+}
+
+static void grt_aabb(const float* bb, const float o[3], const float d[3], float* tmin, float* tmax) {
+    /* intersectAABB (src/kernels/cuda/referenceOptix.cu:33-39) */
+    float mn = -FLT_MAX, mx = FLT_MAX;
+    for (int a = 0; a < 3; ++a) {
+        const float t0 = (bb[a] - o[a]) / d[a], t1 = (bb[3 + a] - o[a]) / d[a];
+        mn = fmaxf(mn, fminf(t0, t1));
+        mx = fminf(mx, fmaxf(t0, t1));
+    }
+    *tmin = fmaxf(0.f, mn);
+    *tmax = mx;
+}
+
+static void grt_sh_basis_f(int deg, const float d[3], float b[16]) {
+    real br[16];
+    sh_basis(deg, V3(d[0], d[1], d[2]), br);
+    for (int k = 0; k < 16; ++k) b[k] = (float)br[k];
+}
+
+/* forward: __raygen__rg of referenceOptix.cu:103-186 */
+void grt_oracle_trace(const gut_oracle_config* cfg, int32_t clamping, int64_t n, const float* particles, const float* sph,
+                      int32_t sph_degree, int64_t n_rays, const float* rays_o, const float* rays_d, const float* ray_to_world,
+                      float* out_rgb, float* out_alpha, float* out_dist /*[R,2]*/, float* out_hits, float* visibility) {
+    float* kscl = (float*)malloc((size_t)(n > 0 ? n : 1) * 3 * sizeof(float));
+    float bb[6];
+    grt_oracle_proxies(cfg, clamping, n, particles, kscl, bb);
+    memset(visibility, 0, (size_t)n * sizeof(float));
+    const float eps = 1e-9f;
+#pragma omp parallel
+    {
+        grt_cand* cand = (grt_cand*)malloc((size_t)(n > 0 ? n : 1) * sizeof(grt_cand));
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t ri = 0; ri < n_rays; ++ri) {
+            float o[3], d[3], t0, t1;
+            grt_ray(ray_to_world, rays_o + ri * 3, rays_d + ri * 3, o, d);
+            grt_aabb(bb, o, d, &t0, &t1);
+            float last = fmaxf(0.0f, t0 - eps);
+            real T = 1.f, C[3] = {0.f, 0.f, 0.f}, D = 0.f;
+            float hits = 0.f;
+            const int64_t m = (last <= t1) ? grt_candidates(n, particles, kscl, o, d, last + eps, t1 + eps, cand) : 0;
+            int64_t cur = 0;
+            while ((last <= t1) && (T > cfg->min_transmittance)) {
+                const float tmin = last + eps;
+                /* the (up to) 16 nearest candidates beyond tmin: one optixTrace of the reference */
+                int64_t sel[GRT_K];
+                int ns = 0;
+                for (int64_t c = cur; c < m && ns < GRT_K; ++c)
+                    if (cand[c].t > tmin && cand[c].t_out >= tmin) sel[ns++] = c;
+                if (ns == 0) break;
+                for (int s = 0; s < ns; ++s) {
+                    if (!(T > cfg->min_transmittance)) continue;
+                    const grt_cand h = cand[sel[s]];
+                    const particle g = load_particle(particles + (int64_t)h.pid * 12);
+                    const hit_t e = eval_hit(cfg, &g, V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]));
+                    if (e.accept) {
+                        const real w = e.galpha * T;
+                        const real t = hit_distance(&g, &e);
+                        float rad[3];
+                        gut_oracle_sph_eval(sph_degree, sph + (int64_t)h.pid * 48, d, rad);
+                        for (int k = 0; k < 3; ++k) C[k] += R_FMAX((real)rad[k], (real)0.f) * w;
+                        T *= (1 - e.galpha);
+                        D += t * w;
+                        hits += 1.f;
+#pragma omp atomic write
+                        visibility[h.pid] = 1.0f;
+                    }
+                    last = fmaxf(last, h.t);
+                }
+                while (cur < m && cand[cur].t <= last) cur++;
+            }
+            out_rgb[ri * 3] = (float)C[0]; out_rgb[ri * 3 + 1] = (float)C[1]; out_rgb[ri * 3 + 2] = (float)C[2];
+            out_alpha[ri] = (float)(1 - T);
+            out_dist[ri * 2] = (float)D;
+            out_dist[ri * 2 + 1] = last;
+            out_hits[ri] = hits;
+        }
+        free(cand);
+    }
+    free(kscl);
+}
+
+/* backward: __raygen__rg of referenceBwdOptix.cu:103-170 */
+void grt_oracle_trace_bwd(const gut_oracle_config* cfg, int32_t clamping, int64_t n, const float* particles, const float* sph,
+                          int32_t sph_degree, int64_t n_rays, const float* rays_o, const float* rays_d, const float* ray_to_world,
+                          const float* out_rgb, const float* out_alpha, const float* out_dist, const float* d_rgb,
+                          const float* d_alpha, const float* d_dist, float* d_particles, float* d_sph) {
+    float* kscl = (float*)malloc((size_t)(n > 0 ? n : 1) * 3 * sizeof(float));
+    float bb[6];
+    grt_oracle_proxies(cfg, clamping, n, particles, kscl, bb);
+    const float eps = 1e-9f;
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    const size_t stride = (size_t)n * 59; /* 11 density-record grads + 48 SH grads */
+    double* acc = (double*)calloc((size_t)nthreads * (stride ? stride : 1), sizeof(double));
+#pragma omp parallel
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        double* a = acc + (size_t)tid * stride;
+        grt_cand* cand = (grt_cand*)malloc((size_t)(n > 0 ? n : 1) * sizeof(grt_cand));
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t ri = 0; ri < n_rays; ++ri) {
+            float o[3], d[3], t0, t1;
+            grt_ray(ray_to_world, rays_o + ri * 3, rays_d + ri * 3, o, d);
+            grt_aabb(bb, o, d, &t0, &t1);
+            float start = fmaxf(0.0f, t0 - eps);
+            const float end = fminf(out_dist[ri * 2 + 1], t1) + eps;
+            const real Cint[3] = {out_rgb[ri * 3], out_rgb[ri * 3 + 1], out_rgb[ri * 3 + 2]};
+            const real Cgrad[3] = {d_rgb[ri * 3], d_rgb[ri * 3 + 1], d_rgb[ri * 3 + 2]};
+            const real Tint = 1.0f - out_alpha[ri], Tgrad = -1.0f * d_alpha[ri];
+            const real Dint = out_dist[ri * 2], Dgrad = d_dist[ri];
+            real T = 1.f, C[3] = {0.f, 0.f, 0.f}, Dp = 0.f;
+            const int64_t m = (start < end) ? grt_candidates(n, particles, kscl, o, d, start + eps, end, cand) : 0;
+            int64_t cur = 0;
+            float basis[16];
+            grt_sh_basis_f(sph_degree, d, basis);
+            while (start < end) {
+                const float tmin = start + eps;
+                int64_t sel[GRT_K];
+                int ns = 0;
+                for (int64_t c = cur; c < m && ns < GRT_K; ++c)
+                    if (cand[c].t > tmin && cand[c].t_out >= tmin) sel[ns++] = c;
+                if (ns == 0) break;
+                for (int s = 0; s < ns; ++s) {
+                    const grt_cand h = cand[sel[s]];
+                    const particle g = load_particle(particles + (int64_t)h.pid * 12);
+                    float rad[3];
+                    gut_oracle_sph_eval(sph_degree, sph + (int64_t)h.pid * 48, d, rad);
+                    const real prgb[3] = {R_FMAX((real)rad[0], (real)0.f), R_FMAX((real)rad[1], (real)0.f), R_FMAX((real)rad[2], (real)0.f)};
+                    real grad[11], rg[3];
+                    if (hit_backward(cfg, &g, V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]), prgb, Tint, &T, Tgrad, Cint, C, Cgrad, Dint, &Dp, Dgrad, grad, rg)) {
+                        double* ai = a + (size_t)h.pid * 59;
+                        for (int q = 0; q < 11; ++q) ai[q] += (double)grad[q];
+                        /* radianceFromSpHBwd<true> (gaussianParticles.cuh:101-177): coefficient grads, clamp mask on the unclamped radiance */
+                        for (int j = 0; j < 16; ++j)
+                            for (int k = 0; k < 3; ++k)
+                                if (rad[k] > 0.0f) ai[11 + j * 3 + k] += (double)((real)basis[j] * rg[k]);
+                    }
+                    start = fmaxf(start, h.t);
+                }
+                while (cur < m && cand[cur].t <= start) cur++;
+            }
+        }
+        free(cand);
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        double s[59];
+        for (int q = 0; q < 59; ++q) s[q] = 0.0;
+        for (int t = 0; t < nthreads; ++t)
+            for (int q = 0; q < 59; ++q) s[q] += acc[(size_t)t * stride + (size_t)i * 59 + q];
+        for (int q = 0; q < 11; ++q) d_particles[i * 12 + q] = (float)s[q];
+        d_particles[i * 12 + 11] = 0.f;
+        for (int q = 0; q < 48; ++q) d_sph[i * 48 + q] = (float)s[11 + q];
+    }
+    free(acc);
+    free(kscl);
+}

@@ -101,6 +101,18 @@ int gut_oracle_hit_backward(const gut_oracle_config* cfg, const float ro[3], con
                             const float Cgrad[3], float Dint, float* D, float Dgrad, float grad[11], float rgbgrad[3]);
 void gut_oracle_sph_eval(int32_t degree, const float coeffs[48], const float dir[3], float rgb_unclamped[3]);
 
+/* ---- 3DGRT (threedgrt_tracer/): brute-force ordered ray tracer, k = 16 hits per trace ----
+ * particles/sph as above; rays [R,3] in ray space; ray_to_world = first 3 rows of T_to_world, row major [3,4].
+ * out_dist is [R,2] = (integrated distance, last processed hit distance) as in referenceOptix.cu:176-177. */
+void grt_oracle_proxies(const gut_oracle_config* cfg, int32_t clamping, int64_t n, const float* particles, float* kscl, float* scene_aabb);
+void grt_oracle_trace(const gut_oracle_config* cfg, int32_t clamping, int64_t n, const float* particles, const float* sph,
+                      int32_t sph_degree, int64_t n_rays, const float* rays_o, const float* rays_d, const float* ray_to_world,
+                      float* out_rgb, float* out_alpha, float* out_dist, float* out_hits, float* visibility);
+void grt_oracle_trace_bwd(const gut_oracle_config* cfg, int32_t clamping, int64_t n, const float* particles, const float* sph,
+                          int32_t sph_degree, int64_t n_rays, const float* rays_o, const float* rays_d, const float* ray_to_world,
+                          const float* out_rgb, const float* out_alpha, const float* out_dist, const float* d_rgb,
+                          const float* d_alpha, const float* d_dist, float* d_particles, float* d_sph);
+
 #ifdef __cplusplus
 }
 #endif

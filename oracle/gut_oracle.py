@@ -210,3 +210,52 @@ def sph_eval(degree, coeffs, direction):
 
 def set_tile_stride(k: int):
     lib().gut_oracle_set_tile_stride(C.c_int(int(k)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 3DGRT brute-force oracle (grt_oracle_* in gut_oracle.c)
+
+def grt_config() -> Config:
+    """configs/render/3dgrt.yaml: degree-4 kernel, min transmittance 1e-3."""
+    cfg = default_config()
+    cfg.kernel_degree = 4
+    cfg.min_transmittance = 0.001
+    return cfg
+
+
+def grt_proxies(cfg, particles, clamping=True):
+    particles = _f32(particles)
+    n = particles.shape[0]
+    kscl, bb = np.zeros((n, 3), np.float32), np.zeros(6, np.float32)
+    lib().grt_oracle_proxies(C.byref(cfg), C.c_int32(int(clamping)), C.c_int64(n), _p(particles, C.c_float), _p(kscl, C.c_float), _p(bb, C.c_float))
+    return kscl, bb
+
+
+def grt_trace(cfg, particles, sph, sph_degree, rays_o, rays_d, ray_to_world, clamping=True, f64=False):
+    particles, sph = _f32(particles), _f32(sph)
+    shape = np.asarray(rays_o).shape[:-1]
+    ro, rd = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
+    r2w = _f32(np.asarray(ray_to_world)[:3, :4])
+    n, r = particles.shape[0], ro.shape[0]
+    rgb, alpha, dist, hits, vis = (np.zeros((r, 3), np.float32), np.zeros(r, np.float32), np.zeros((r, 2), np.float32),
+                                   np.zeros(r, np.float32), np.zeros(max(n, 1), np.float32))
+    lib(f64).grt_oracle_trace(C.byref(cfg), C.c_int32(int(clamping)), C.c_int64(n), _p(particles, C.c_float), _p(sph, C.c_float),
+                              C.c_int32(sph_degree), C.c_int64(r), _p(ro, C.c_float), _p(rd, C.c_float), _p(r2w, C.c_float),
+                              _p(rgb, C.c_float), _p(alpha, C.c_float), _p(dist, C.c_float), _p(hits, C.c_float), _p(vis, C.c_float))
+    return (rgb.reshape(*shape, 3), alpha.reshape(*shape, 1), dist.reshape(*shape, 2), hits.reshape(*shape, 1), vis[:n].reshape(n, 1))
+
+
+def grt_trace_bwd(cfg, particles, sph, sph_degree, rays_o, rays_d, ray_to_world, rgb, alpha, dist, d_rgb, d_alpha, d_dist,
+                  clamping=True, f64=False):
+    particles, sph = _f32(particles), _f32(sph)
+    ro, rd = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
+    r2w = _f32(np.asarray(ray_to_world)[:3, :4])
+    n, r = particles.shape[0], ro.shape[0]
+    rgb, alpha, dist = _f32(rgb).reshape(r, 3), _f32(alpha).reshape(r), _f32(dist).reshape(r, 2)
+    d_rgb, d_alpha, d_dist = _f32(d_rgb).reshape(r, 3), _f32(d_alpha).reshape(r), _f32(d_dist).reshape(r)
+    dp, ds = np.zeros((max(n, 1), 12), np.float32), np.zeros((max(n, 1), 48), np.float32)
+    lib(f64).grt_oracle_trace_bwd(C.byref(cfg), C.c_int32(int(clamping)), C.c_int64(n), _p(particles, C.c_float), _p(sph, C.c_float),
+                                  C.c_int32(sph_degree), C.c_int64(r), _p(ro, C.c_float), _p(rd, C.c_float), _p(r2w, C.c_float),
+                                  _p(rgb, C.c_float), _p(alpha, C.c_float), _p(dist, C.c_float), _p(d_rgb, C.c_float),
+                                  _p(d_alpha, C.c_float), _p(d_dist, C.c_float), _p(dp, C.c_float), _p(ds, C.c_float))
+    return dp[:n], ds[:n]
