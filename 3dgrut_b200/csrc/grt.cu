@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(128) trace_kernel(TraceParams P) {
                 }
                 last = fmaxf(last, lt[i]);
             }
+            if (li[kK - 1] == kNone) break;  // fewer than 16 hits: the ray is exhausted, the reference's next trace would return nothing
         }
         P.out_rgb[ray * 3] = Cx; P.out_rgb[ray * 3 + 1] = Cy; P.out_rgb[ray * 3 + 2] = Cz;
         P.out_alpha[ray] = 1.f - T;
@@ -464,6 +465,7 @@ __global__ void __launch_bounds__(128) trace_kernel(TraceParams P) {
                 }
                 start = fmaxf(start, lt[i]);
             }
+            if (li[kK - 1] == kNone) break;
         }
     }
 }

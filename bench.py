@@ -50,6 +50,10 @@ def load_peaks():
 def make_scene(workload: str):
     import scenes
 
+    if workload == "c4":  # C2's scene through the 3DGRT path
+        return scenes.scene_c2()
+    if workload.startswith("c4:"):
+        return scenes.scene_c2(n=int(workload.split(":")[1]))
     if workload == "c1":
         return scenes.scene_c1()
     if workload == "c3":
@@ -139,11 +143,44 @@ def cpu_port_frames_per_s(sc, tile_stride: int, frames: int = 1, warm: int = 0):
     return 1.0 / float(np.mean(times)), times
 
 
+def grt_cpu_port_frames_per_s(sc, ray_stride: int, frames: int = 1, warm: int = 0):
+    """3DGRT CPU port (brute-force oracle) on a bounded sample: every `ray_stride`-th ray of one view, extrapolated."""
+    from oracle import gut_oracle as go
+
+    cfg = go.grt_config()
+    ro, rd = sc.rays()
+    ro, rd = ro.reshape(-1, 3)[::ray_stride], rd.reshape(-1, 3)[::ray_stride]
+    rng = np.random.default_rng(0)
+    times = []
+    for f in range(warm + frames):
+        c2w = np.asarray(sc.camera(f, 100), np.float32)
+        t0 = time.perf_counter()
+        rgb, alpha, dist, hits, vis = go.grt_trace(cfg, sc.particles, sc.sph, sc.sph_degree, ro, rd, c2w)
+        d_rgb = rng.normal(size=rgb.shape).astype(np.float32)
+        go.grt_trace_bwd(cfg, sc.particles, sc.sph, sc.sph_degree, ro, rd, c2w, rgb, alpha, dist, d_rgb, np.zeros_like(alpha), np.zeros_like(alpha))
+        if f >= warm:
+            times.append((time.perf_counter() - t0) * ray_stride)
+    return 1.0 / float(np.mean(times)), times
+
+
 def run_reference_arm(args, rank, world):
     """CPU port of the reference algorithm on the host cores (rank 0 only)."""
     if rank != 0:
         return
     sc = make_scene(args.workload)
+    if args.workload.startswith("c4"):
+        stride = args.cpu_ray_stride
+        cores = os.cpu_count() or 1
+        fps, _ = grt_cpu_port_frames_per_s(sc, stride, frames=args.steps, warm=args.warmup)
+        sample = f"per step: every {stride}th ray of one {sc.width}x{sc.height} view, brute force over all {sc.n} particles (no BVH), fwd+bwd, extrapolated x{stride}"
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": sc.name, "gaussians": sc.n, "resolution": [sc.width, sc.height], "path": "3dgrt",
+                       "note": "CPU port of the reference algorithm (oracle/); the reference needs OptiX + slangc"},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
     stride = args.cpu_tile_stride
     cores = os.cpu_count() or 1
     fps, times = cpu_port_frames_per_s(sc, stride, frames=args.steps, warm=args.warmup)
@@ -159,6 +196,169 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def run_grt(args, rank, local_rank, world, dev, dist):
+    """C4: the C2 scene through the 3DGRT path.  A step = build_bvh (the reference's default config rebuilds every
+    step, configs/render/3dgrt.yaml:6 + base_gs.yaml:88) + trace + trace_bwd."""
+    import torch
+
+    import threedgrt_tracer
+
+    sc = make_scene(args.workload)
+    n, H, W = sc.n, sc.height, sc.width
+    tracer = threedgrt_tracer.Tracer({"render": {"min_transmittance": 0.001}})
+    ot = tracer.tracer_wrapper
+    particles = torch.from_numpy(sc.particles).to(dev)
+    sph = torch.from_numpy(sc.sph).to(dev)
+    pos, dns, rot, scl = (particles[:, 0:3].contiguous(), particles[:, 3:4].contiguous(), particles[:, 4:8].contiguous(),
+                          particles[:, 8:11].contiguous())
+    ro_np, rd_np = sc.rays()
+    rays_o, rays_d = torch.from_numpy(ro_np).to(dev), torch.from_numpy(rd_np).to(dev)
+    n_views = 100
+    c2ws = [torch.from_numpy(np.asarray(sc.camera(i, n_views), np.float32))[None] for i in range(n_views)]
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    d_rgb = torch.randn((1, H, W, 3), device=dev, generator=gen)
+    d_alpha = torch.randn((1, H, W, 1), device=dev, generator=gen)
+    d_dist = 0.05 * torch.randn((1, H, W, 1), device=dev, generator=gen)
+    d_nrm = torch.zeros((1, H, W, 3), device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    stage = {"build_bvh": [], "trace": [], "trace_bwd": []}
+
+    def view_of(step):
+        return (step * world + rank) % n_views
+
+    def step_device(step, timed=False):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
+        if timed:
+            evs[0].record()
+        ot.build_bvh(pos, rot, scl, dns, True, False)
+        if timed:
+            evs[1].record()
+        c2w = c2ws[view_of(step)]
+        feat, alpha, hit, nrm, hits, vis = ot.trace(step, c2w, rays_o, rays_d, particles, sph, 0, sc.sph_degree, 0.001)
+        if timed:
+            evs[2].record()
+        dp, ds = ot.trace_bwd(step, c2w, rays_o, rays_d, feat, alpha, hit, nrm, particles, sph, d_rgb, d_alpha, d_dist, d_nrm, 0, sc.sph_degree, 0.001)
+        if timed:
+            evs[3].record()
+            torch.cuda.synchronize(dev)
+            for k, (a, b) in zip(stage, zip(evs[:-1], evs[1:])):
+                stage[k].append(a.elapsed_time(b))
+        if world > 1:
+            dist.all_reduce(dp)
+            dist.all_reduce(ds)
+        return feat
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for s in range(args.warmup):
+        step_device(s)
+    barrier()
+    ctx = ot.native_context(dev)
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s in range(args.steps):
+        flush.fill_(float(s))
+        ev[s][0].record()
+        step_device(args.warmup + s)
+        ev[s][1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = torch.tensor([float(sum(a.elapsed_time(b) for a, b in ev))], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    launches = ctx.launch_count() - launches0
+    for s in range(min(args.steps, 10)):
+        flush.fill_(float(s))
+        step_device(args.warmup + s, timed=True)
+    value = world * args.steps / (total_ms / 1000.0)
+
+    # e2e through Tracer.build_acc + Tracer.render + loss.backward with the camera batch from pinned host memory
+    class _G:
+        positions = pos.clone().requires_grad_(True)
+        density = dns.clone().requires_grad_(True)
+        rotation = rot.clone().requires_grad_(True)
+        scale = scl.clone().requires_grad_(True)
+        _f = sph.clone().requires_grad_(True)
+        n_active_features = sc.sph_degree
+        num_gaussians = n
+        rotation_activation = scale_activation = density_activation = staticmethod(lambda t: t)
+        get_rotation = staticmethod(lambda: _G.rotation)
+        get_scale = staticmethod(lambda: _G.scale)
+        get_density = staticmethod(lambda: _G.density)
+        get_features = staticmethod(lambda: _G._f)
+
+    pin_o, pin_d = torch.from_numpy(ro_np).pin_memory(), torch.from_numpy(rd_np).pin_memory()
+    pin_gt = torch.rand((1, H, W, 3)).pin_memory()
+    grads = [_G.positions, _G.density, _G.rotation, _G.scale, _G._f]
+
+    class _B:
+        pass
+
+    def step_e2e(step):
+        b = _B()
+        b.rays_ori = pin_o.to(dev, non_blocking=True)
+        b.rays_dir = pin_d.to(dev, non_blocking=True)
+        gt = pin_gt.to(dev, non_blocking=True)
+        b.T_to_world = c2ws[view_of(step)].to(dev)
+        for g in grads:
+            g.grad = None
+        tracer.build_acc(_G, rebuild=True)
+        out = tracer.render(_G, b, train=True, frame_id=step)
+        loss = (out["pred_features"] - gt).abs().mean() + 0.01 * out["pred_opacity"].mean()
+        loss.backward()
+        if world > 1:
+            for g in grads:
+                dist.all_reduce(g.grad)
+        return float(loss.item())
+
+    e2e_steps = max(5, args.steps // 2)
+    for s in range(min(args.warmup, 3)):
+        step_e2e(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        step_e2e(args.warmup + s)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps / float(e2e_s.item())
+    h2d = int(pin_o.numel() * 4 + pin_d.numel() * 4 + pin_gt.numel() * 4)
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        stage_ms = {k: float(np.mean(v)) for k, v in stage.items()}
+        dom = max(stage_ms, key=lambda k: stage_ms[k])
+        P_ = H * W
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": sc.name + " via 3dgrt", "gaussians": n, "resolution": [W, H], "path": "3dgrt (software LBVH)",
+                       "step": "build_bvh + trace + trace_bwd", "l2": "flushed between timed steps (256 MiB fill)", "N": n, "P": P_},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                    "api": "threedgrt_tracer.Tracer.build_acc + render + loss.backward"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                         "peak_source": peak_src, "kernel_ms": stage_ms[dom],
+                         "note": "traversal is latency / L2 bound; hits and node visits are not counted yet, so no algorithmic-byte figure"},
+            "stage_ms": stage_ms,
+        }
+        if not args.no_cpu_baseline:
+            fps, _ = grt_cpu_port_frames_per_s(sc, args.cpu_ray_stride, frames=1)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": f"every {args.cpu_ray_stride}th ray of one view, brute force over all particles, fwd+bwd, extrapolated"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,6 +367,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--cpu-tile-stride", type=int, default=16)
+    ap.add_argument("--cpu-ray-stride", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -195,6 +396,9 @@ def main():
     import threedgut_tracer
     from threedgut_tracer.tracer import SensorPose3D, fromOpenCVPinholeCameraModelParameters, ShutterType
 
+    if args.workload.startswith("c4"):
+        run_grt(args, rank, local_rank, world, dev, dist)
+        return
     sc = make_scene(args.workload)
     n, H, W = sc.n, sc.height, sc.width
     conf = {"render": {"enable_kernel_timings": False}}

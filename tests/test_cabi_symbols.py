@@ -9,10 +9,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
-    text = open(os.path.join(ROOT, "include", "gut_b200.h")).read()
+def _declared(header="gut_b200.h", prefix="gutb200_"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(gutb200_[a-z_0-9]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z_0-9]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -25,6 +25,10 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/gut_b200.h but not exported"
     assert set(nat.EXPORTS) == set(names)
     assert b"sm_100a" in lib.gutb200_version()
+    grt = _declared("grt_b200.h", "grtb200_")
+    assert len(grt) >= 9 and set(nat.GRT_EXPORTS) == set(grt)
+    for name in grt:
+        assert hasattr(lib, name), f"{name} declared in include/grt_b200.h but not exported"
 
 
 def test_struct_layouts_match_header():
@@ -44,10 +48,16 @@ def test_no_cpu_fallback_without_gpu():
     import b200_native as nat
     import threedgut_tracer
 
+    import threedgrt_tracer
+
     with pytest.raises(RuntimeError):
         nat.Context(nat.default_config(), 0)
+    with pytest.raises(RuntimeError):
+        nat.GrtContext(nat.grt_default_config(), 0)
     with pytest.raises(Exception):
         threedgut_tracer.Tracer({})
+    with pytest.raises(Exception):
+        threedgrt_tracer.Tracer({})
 
 
 def test_product_never_imports_the_oracle():
