@@ -10,40 +10,14 @@
 // TMA bulk copy (cp.async.bulk + mbarrier) into shared memory instead of 3 strided LDG.128 per thread; record
 // reads from shared memory are conflict-free (stride 12 words, LDS.128 phases of 8 lanes).
 #include "gut_common.cuh"
+#include "tma.cuh"
 
 namespace gutb200 {
 
 namespace {
 
 constexpr int kProjThreads = 256;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
+constexpr int kSmallBox = 8;  // footprints above this many tiles are walked by the whole warp
 
 struct TileBox {
     int x0, y0, x1, y1;
@@ -201,11 +175,12 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
     mbar_wait(&s_bar, 0);
 
     const int64_t i = base + threadIdx.x;
-    if (i >= n) return;
+    const bool in_range = i < n;  // out-of-range lanes stay alive: the warp-cooperative tile count below needs every lane
+    const int slot = in_range ? threadIdx.x : 0;
 
-    const float4 r0 = s_rec[threadIdx.x * 3 + 0];  // pos.xyz, density
-    const float4 r1 = s_rec[threadIdx.x * 3 + 1];  // quat wxyz
-    const float4 r2 = s_rec[threadIdx.x * 3 + 2];  // scale.xyz, pad
+    const float4 r0 = s_rec[slot * 3 + 0];  // pos.xyz, density
+    const float4 r1 = s_rec[slot * 3 + 1];  // quat wxyz
+    const float4 r2 = s_rec[slot * 3 + 2];  // scale.xyz, pad
     const float px = r0.x, py = r0.y, pz = r0.z, opacity = r0.w;
 
     // rows of quaternionWXYZToMatrix == columns of R (models/gaussianParticles.cuh:39-59)
@@ -225,7 +200,7 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
     const float zc = px * cam.view[0 * 3 + 2] + py * cam.view[1 * 3 + 2] + pz * cam.view[2 * 3 + 2] + cam.view[3 * 3 + 2];
 
     // unscentedParticleProjection (gutProjector.cuh:118-215): 7 sigma points, lambda = 0
-    if (!(opacity < cfg.min_alpha) && !(zc < 0.2f)) {
+    if (in_range && !(opacity < cfg.min_alpha) && !(zc < 0.2f)) {
         float spx[7], spy[7];
         int nvalid = 0;
         nvalid += project_world(cam, cfg.ut_margin, px, py, pz, spx[0], spy[0]) ? 1 : 0;
@@ -292,19 +267,50 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
     const bool visible = valid_proj && valid_conic;
     // the reference stores int 1 into this float tensor (gutProjector.cuh:275, splatRaster.cpp:215,249);
     // consumers only test it for non-zero, we store the same bit pattern.
-    visibility[i] = __int_as_float(visible ? 1 : 0);
+    if (in_range) visibility[i] = __int_as_float(visible ? 1 : 0);
 
+    // tile count with per-tile culling (gutProjector.cuh:279-293).  Footprints of up to kSmallBox tiles are counted by the
+    // owning lane; larger ones are counted by the whole warp, 32 tiles per step, so one big splat does not serialise its warp.
     uint32_t ntiles = 0;
+    TileBox bb = {0, 0, 0, 0};
+    int cells = 0;
     if (visible) {
-        const TileBox bb = tile_box(cam.grid_x, cam.grid_y, pcx, pcy, ex, ey);
-        if (cfg.tile_culling) {
+        bb = tile_box(cam.grid_x, cam.grid_y, pcx, pcy, ex, ey);
+        cells = (bb.x1 - bb.x0) * (bb.y1 - bb.y0);
+        if (!cfg.tile_culling) {
+            ntiles = static_cast<uint32_t>(cells);
+            cells = 0;
+        } else if (cells <= kSmallBox) {
             for (int y = bb.y0; y < bb.y1; ++y)
                 for (int x = bb.x0; x < bb.x1; ++x)
                     if (tile_min_power(static_cast<float>(x), static_cast<float>(y), ca, cb, cc, pcx, pcy) < maxpow) ntiles++;
-        } else {
-            ntiles = static_cast<uint32_t>((bb.x1 - bb.x0) * (bb.y1 - bb.y0));
+            cells = 0;
         }
     }
+    {
+        const unsigned lane = threadIdx.x & 31;
+        unsigned big = __ballot_sync(0xFFFFFFFFu, cells > kSmallBox);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const int bx0 = __shfl_sync(0xFFFFFFFFu, bb.x0, src), by0 = __shfl_sync(0xFFFFFFFFu, bb.y0, src);
+            const int bw = __shfl_sync(0xFFFFFFFFu, bb.x1, src) - bx0, nc = __shfl_sync(0xFFFFFFFFu, cells, src);
+            const float qa = __shfl_sync(0xFFFFFFFFu, ca, src), qb = __shfl_sync(0xFFFFFFFFu, cb, src), qc = __shfl_sync(0xFFFFFFFFu, cc, src);
+            const float qx = __shfl_sync(0xFFFFFFFFu, pcx, src), qy = __shfl_sync(0xFFFFFFFFu, pcy, src), qp = __shfl_sync(0xFFFFFFFFu, maxpow, src);
+            uint32_t total = 0;
+            for (int c0 = 0; c0 < nc; c0 += 32) {
+                const int c = c0 + static_cast<int>(lane);
+                bool pass = false;
+                if (c < nc) {
+                    const int y = by0 + c / bw, x = bx0 + c % bw;
+                    pass = tile_min_power(static_cast<float>(x), static_cast<float>(y), qa, qb, qc, qx, qy) < qp;
+                }
+                total += __popc(__ballot_sync(0xFFFFFFFFu, pass));
+            }
+            if (static_cast<int>(lane) == src) ntiles = total;
+        }
+    }
+    if (!in_range) return;
     tiles_count[i] = ntiles;
 
     ProjRecord pr;
@@ -326,39 +332,90 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
     rgb[i * 3 + 2] = col[2];
 }
 
-// G3: emit (tile << 32 | depth bits, particle) for every surviving tile (GUTProjector::expand, gutProjector.cuh:324-388)
+// G3: emit (tile << 32 | depth bits, particle) for every surviving tile (GUTProjector::expand, gutProjector.cuh:324-388).
+// Each particle owns the slice [offset[i-1], offset[i]) of the key stream, so the order between particles is the
+// reference's; inside a slice the tiles are written in the reference's row-major order too (ordered ballot compaction
+// when the warp walks a large footprint together).
 __global__ void __launch_bounds__(256) expand_kernel(FrameCamera cam, FrameConfig cfg, int64_t n,
                                                      const uint32_t* __restrict__ offsets, const ProjRecord* __restrict__ proj,
                                                      const float* __restrict__ depth, uint64_t* __restrict__ keys,
                                                      uint32_t* __restrict__ values) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const ProjRecord pr = proj[i];
-    if (pr.ex <= 1e-06f) return;
-    const uint32_t dkey = __float_as_uint(depth[i]);
-    uint32_t off = (i == 0) ? 0u : offsets[i - 1];
-    const uint32_t maxoff = offsets[i];
-    const TileBox bb = tile_box(cam.grid_x, cam.grid_y, pr.cx, pr.cy, pr.ex, pr.ey);
-    if (cfg.tile_culling) {
-        const float maxpow = logf(pr.op / cfg.min_alpha);
-        for (int y = bb.y0; (y < bb.y1) && (off < maxoff); ++y)
-            for (int x = bb.x0; (x < bb.x1) && (off < maxoff); ++x)
-                if (tile_min_power(static_cast<float>(x), static_cast<float>(y), pr.ca, pr.cb, pr.cc, pr.cx, pr.cy) < maxpow) {
+    const bool in_range = i < n;
+    ProjRecord pr;
+    pr.ex = 0.f;
+    if (in_range) pr = proj[i];
+    const bool active = in_range && !(pr.ex <= 1e-06f);
+    uint32_t dkey = 0, off = 0, maxoff = 0;
+    TileBox bb = {0, 0, 0, 0};
+    float maxpow = 0.f;
+    int cells = 0;
+    if (active) {
+        dkey = __float_as_uint(depth[i]);
+        off = (i == 0) ? 0u : offsets[i - 1];
+        maxoff = offsets[i];
+        bb = tile_box(cam.grid_x, cam.grid_y, pr.cx, pr.cy, pr.ex, pr.ey);
+        cells = (bb.x1 - bb.x0) * (bb.y1 - bb.y0);
+        if (!cfg.tile_culling) {
+            for (int y = bb.y0; y < bb.y1; ++y)
+                for (int x = bb.x0; x < bb.x1; ++x) {
                     keys[off] = (static_cast<uint64_t>(static_cast<uint32_t>(y * cam.grid_x + x)) << 32) | dkey;
                     values[off] = static_cast<uint32_t>(i);
                     off++;
                 }
-        for (; off < maxoff; ++off) {  // padding, never produced when project and expand agree (gutProjector.cuh:372-376)
-            keys[off] = (static_cast<uint64_t>(kInvalid) << 32) | __float_as_uint(3.4028235e+38f);
-            values[off] = kInvalid;
-        }
-    } else {
-        for (int y = bb.y0; y < bb.y1; ++y)
-            for (int x = bb.x0; x < bb.x1; ++x) {
-                keys[off] = (static_cast<uint64_t>(static_cast<uint32_t>(y * cam.grid_x + x)) << 32) | dkey;
-                values[off] = static_cast<uint32_t>(i);
-                off++;
+            cells = 0;
+        } else {
+            maxpow = logf(pr.op / cfg.min_alpha);
+            if (cells <= kSmallBox) {
+                for (int y = bb.y0; (y < bb.y1) && (off < maxoff); ++y)
+                    for (int x = bb.x0; (x < bb.x1) && (off < maxoff); ++x)
+                        if (tile_min_power(static_cast<float>(x), static_cast<float>(y), pr.ca, pr.cb, pr.cc, pr.cx, pr.cy) < maxpow) {
+                            keys[off] = (static_cast<uint64_t>(static_cast<uint32_t>(y * cam.grid_x + x)) << 32) | dkey;
+                            values[off] = static_cast<uint32_t>(i);
+                            off++;
+                        }
+                for (; off < maxoff; ++off) {  // padding, never produced when project and expand agree (gutProjector.cuh:372-376)
+                    keys[off] = (static_cast<uint64_t>(kInvalid) << 32) | __float_as_uint(3.4028235e+38f);
+                    values[off] = kInvalid;
+                }
+                cells = 0;
             }
+        }
+    }
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned big = __ballot_sync(0xFFFFFFFFu, cells > kSmallBox);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int bx0 = __shfl_sync(0xFFFFFFFFu, bb.x0, src), by0 = __shfl_sync(0xFFFFFFFFu, bb.y0, src);
+        const int bw = __shfl_sync(0xFFFFFFFFu, bb.x1, src) - bx0, nc = __shfl_sync(0xFFFFFFFFu, cells, src);
+        const float qa = __shfl_sync(0xFFFFFFFFu, pr.ca, src), qb = __shfl_sync(0xFFFFFFFFu, pr.cb, src), qc = __shfl_sync(0xFFFFFFFFu, pr.cc, src);
+        const float qx = __shfl_sync(0xFFFFFFFFu, pr.cx, src), qy = __shfl_sync(0xFFFFFFFFu, pr.cy, src), qp = __shfl_sync(0xFFFFFFFFu, maxpow, src);
+        const uint32_t qkey = __shfl_sync(0xFFFFFFFFu, dkey, src), qend = __shfl_sync(0xFFFFFFFFu, maxoff, src);
+        uint32_t cur = __shfl_sync(0xFFFFFFFFu, off, src);
+        const uint32_t pid = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, static_cast<int>(i & 0x7FFFFFFF), src));
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+            const int c = c0 + static_cast<int>(lane);
+            bool pass = false;
+            int tile = 0;
+            if (c < nc) {
+                const int y = by0 + c / bw, x = bx0 + c % bw;
+                tile = y * cam.grid_x + x;
+                pass = tile_min_power(static_cast<float>(x), static_cast<float>(y), qa, qb, qc, qx, qy) < qp;
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+            const uint32_t dst = cur + __popc(m & lt_mask);
+            if (pass && dst < qend) {
+                keys[dst] = (static_cast<uint64_t>(static_cast<uint32_t>(tile)) << 32) | qkey;
+                values[dst] = pid;
+            }
+            cur += __popc(m);
+        }
+        for (uint32_t k = cur + lane; k < qend; k += 32) {  // padding (see above)
+            keys[k] = (static_cast<uint64_t>(kInvalid) << 32) | __float_as_uint(3.4028235e+38f);
+            values[k] = kInvalid;
+        }
     }
 }
 

@@ -15,6 +15,8 @@
 // (16 SHFL instead of 70) and lands them with ONE coalesced 64-byte vector RED per (warp, particle) into a
 // [N,16] accumulator that G8 consumes and re-zeroes.
 #include "gut_common.cuh"
+#include "hit_math.cuh"
+#include "tma.cuh"
 
 namespace gutb200 {
 
@@ -508,100 +510,119 @@ __constant__ float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.315391
 __constant__ float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
                              -0.4570457994644658f, 1.445305721320277f,  -0.5900435899266435f};
 
-__global__ void __launch_bounds__(128) project_backward_kernel(FrameCamera cam, int64_t n, const float* __restrict__ particles,
-                                                               const float* __restrict__ sph, int deg, const float* __restrict__ rgb,
-                                                               const uint32_t* __restrict__ tiles_count, float* __restrict__ grad_acc,
-                                                               float* __restrict__ d_particles, float* __restrict__ d_sph) {
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4* acc4 = reinterpret_cast<float4*>(grad_acc + i * kGradRow);
-    const float4 a0 = acc4[0], a1 = acc4[1], a2 = acc4[2], a3 = acc4[3];
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    acc4[0] = zero; acc4[1] = zero; acc4[2] = zero; acc4[3] = zero;
+// Block of 128 particles, all global traffic through TMA bulk copies (cp.async.bulk + mbarrier): one copy brings the block's
+// accumulator rows, one 192-byte copy per VISIBLE particle brings its SH coefficients, and three bulk stores write the
+// d_sph rows, the d_particles rows and the re-zeroed accumulator rows (every output row is written, zeros for invisible
+// particles, so the caller needs no memset).  Threads only touch shared memory, with 128-bit accesses.
+constexpr int kPbThreads = 128;
 
-    float dpx = a0.x, dpy = a0.y, dpz = a0.z;
-    float4* ds4 = reinterpret_cast<float4*>(d_sph + i * 48);
-    if (tiles_count[i] == 0) {
-#pragma unroll
-        for (int k = 0; k < 12; ++k) ds4[k] = zero;
-    } else {
-        // incident direction = normalize(position - sensor position) (gutProjector.cuh:418)
-        const float4 p = __ldg(reinterpret_cast<const float4*>(particles + i * 12));
-        const float vx = p.x - cam.cam_pos[0], vy = p.y - cam.cam_pos[1], vz = p.z - cam.cam_pos[2];
-        const float len = sqrtf(vx * vx + vy * vy + vz * vz);
-        const float inv_len = len > 0.f ? 1.0f / len : 0.f;
-        const float x = len > 0.f ? vx * inv_len : 1.f, y = vy * inv_len, z = vz * inv_len;
-        // clamp mask of max(f + 0.5, 0) (sphericalHarmonics.slang:63); rgb holds the unclamped f + 0.5
-        const float mgr = rgb[i * 3 + 0] > 0.f ? a3.x : 0.f;
-        const float mgg = rgb[i * 3 + 1] > 0.f ? a3.y : 0.f;
-        const float mgb = rgb[i * 3 + 2] > 0.f ? a3.z : 0.f;
-        float b[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) b[k] = 0.f;
-        b[0] = kC0;
-        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-        if (deg > 0) {
-            b[1] = -kC1 * y; b[2] = kC1 * z; b[3] = -kC1 * x;
-            if (deg > 1) {
-                b[4] = kC2[0] * xy; b[5] = kC2[1] * yz; b[6] = kC2[2] * (2.0f * zz - xx - yy); b[7] = kC2[3] * xz; b[8] = kC2[4] * (xx - yy);
-                if (deg > 2) {
-                    b[9] = kC3[0] * y * (3.0f * xx - yy);
-                    b[10] = kC3[1] * xy * z;
-                    b[11] = kC3[2] * y * (4.0f * zz - xx - yy);
-                    b[12] = kC3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-                    b[13] = kC3[4] * x * (4.0f * zz - xx - yy);
-                    b[14] = kC3[5] * z * (xx - yy);
-                    b[15] = kC3[6] * x * (xx - 3.0f * yy);
-                }
-            }
-        }
-        float o[48];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            o[k * 3 + 0] = b[k] * mgr;
-            o[k * 3 + 1] = b[k] * mgg;
-            o[k * 3 + 2] = b[k] * mgb;
-        }
-#pragma unroll
-        for (int k = 0; k < 12; ++k) ds4[k] = make_float4(o[k * 4], o[k * 4 + 1], o[k * 4 + 2], o[k * 4 + 3]);
-
-        // d(rgb)/d(direction) . masked gradient, then through normalize (gaussianParticles.slang:545-558)
-        if (deg > 0 && len > 0.f) {
-            float cf[48];
-            const float4* c4 = reinterpret_cast<const float4*>(sph + i * 48);
-#pragma unroll
-            for (int k = 0; k < 12; ++k) {
-                const float4 v = __ldg(c4 + k);
-                cf[k * 4] = v.x; cf[k * 4 + 1] = v.y; cf[k * 4 + 2] = v.z; cf[k * 4 + 3] = v.w;
-            }
-            // s[j] = sum_c coeff[j][c] * masked_grad[c]
-            float s[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) s[k] = cf[k * 3] * mgr + cf[k * 3 + 1] * mgg + cf[k * 3 + 2] * mgb;
-            float gx = -kC1 * s[3], gy = -kC1 * s[1], gz = kC1 * s[2];
-            if (deg > 1) {
-                gx += kC2[0] * y * s[4] + kC2[2] * (-2.f * x) * s[6] + kC2[3] * z * s[7] + kC2[4] * (2.f * x) * s[8];
-                gy += kC2[0] * x * s[4] + kC2[1] * z * s[5] + kC2[2] * (-2.f * y) * s[6] + kC2[4] * (-2.f * y) * s[8];
-                gz += kC2[1] * y * s[5] + kC2[2] * (4.f * z) * s[6] + kC2[3] * x * s[7];
-                if (deg > 2) {
-                    gx += kC3[0] * (6.f * xy) * s[9] + kC3[1] * yz * s[10] + kC3[2] * (-2.f * xy) * s[11] + kC3[3] * (-6.f * xz) * s[12] +
-                          kC3[4] * (4.f * zz - 3.f * xx - yy) * s[13] + kC3[5] * (2.f * xz) * s[14] + kC3[6] * (3.f * xx - 3.f * yy) * s[15];
-                    gy += kC3[0] * (3.f * xx - 3.f * yy) * s[9] + kC3[1] * xz * s[10] + kC3[2] * (4.f * zz - xx - 3.f * yy) * s[11] +
-                          kC3[3] * (-6.f * yz) * s[12] + kC3[4] * (-2.f * xy) * s[13] + kC3[5] * (-2.f * yz) * s[14] + kC3[6] * (-6.f * xy) * s[15];
-                    gz += kC3[1] * xy * s[10] + kC3[2] * (8.f * yz) * s[11] + kC3[3] * (6.f * zz - 3.f * xx - 3.f * yy) * s[12] +
-                          kC3[4] * (8.f * xz) * s[13] + kC3[5] * (xx - yy) * s[14];
-                }
-            }
-            const float dd = x * gx + y * gy + z * gz;
-            dpx += (gx - x * dd) * inv_len;
-            dpy += (gy - y * dd) * inv_len;
-            dpz += (gz - z * dd) * inv_len;
-        }
+__global__ void __launch_bounds__(kPbThreads) project_backward_kernel(FrameCamera cam, int64_t n, const float* __restrict__ particles,
+                                                                      const float* __restrict__ sph, int deg, const float* __restrict__ rgb,
+                                                                      const uint32_t* __restrict__ tiles_count, float* __restrict__ grad_acc,
+                                                                      float* __restrict__ d_particles, float* __restrict__ d_sph) {
+    __shared__ __align__(128) float4 s_acc[kPbThreads * 4];   // in: accumulator rows, out: zeros
+    __shared__ __align__(128) float4 s_sh[kPbThreads * 12];   // in: SH coefficients, out: d_sph rows
+    __shared__ __align__(128) float4 s_dp[kPbThreads * 3];    // out: d_particles rows
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x;
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * kPbThreads;
+    const int cnt = static_cast<int>(min(static_cast<int64_t>(kPbThreads), n - base));
+    if (tid == 0) {
+        mbar_init(&s_bar, kPbThreads);
+        fence_proxy_async();
     }
-    float4* dp4 = reinterpret_cast<float4*>(d_particles + i * 12);
-    dp4[0] = make_float4(dpx, dpy, dpz, a0.w);
-    dp4[1] = a1;
-    dp4[2] = make_float4(a2.x, a2.y, a2.z, 0.f);
+    __syncthreads();
+    const int64_t i = base + tid;
+    const bool in_range = tid < cnt;
+    const bool vis = in_range && (tiles_count[i] != 0u);
+    const bool want_sh = vis && (deg > 0);
+    mbar_expect_tx(&s_bar, (tid == 0 ? static_cast<uint32_t>(cnt) * 64u : 0u) + (want_sh ? 192u : 0u));
+    if (tid == 0) tma_bulk_g2s(s_acc, grad_acc + base * kGradRow, static_cast<uint32_t>(cnt) * 64u, &s_bar);
+    if (want_sh) tma_bulk_g2s(s_sh + tid * 12, sph + i * 48, 192u, &s_bar);
+    // overlap the remaining scalar loads with the bulk copies
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    if (vis) {
+        p = __ldg(reinterpret_cast<const float4*>(particles + i * 12));
+        c0 = rgb[i * 3 + 0]; c1 = rgb[i * 3 + 1]; c2 = rgb[i * 3 + 2];
+    }
+    mbar_wait(&s_bar, 0);
+
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in_range) {
+        const float4 a0 = s_acc[tid * 4 + 0], a1 = s_acc[tid * 4 + 1], a2 = s_acc[tid * 4 + 2], a3 = s_acc[tid * 4 + 3];
+        s_acc[tid * 4 + 0] = zero; s_acc[tid * 4 + 1] = zero; s_acc[tid * 4 + 2] = zero; s_acc[tid * 4 + 3] = zero;
+        float dpx = a0.x, dpy = a0.y, dpz = a0.z;
+        float4* row = s_sh + tid * 12;
+        if (!vis) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) row[k] = zero;
+        } else {
+            // incident direction = normalize(position - sensor position) (gutProjector.cuh:418)
+            const float vx = p.x - cam.cam_pos[0], vy = p.y - cam.cam_pos[1], vz = p.z - cam.cam_pos[2];
+            const float len = sqrtf(vx * vx + vy * vy + vz * vz);
+            const float inv_len = len > 0.f ? 1.0f / len : 0.f;
+            const float x = len > 0.f ? vx * inv_len : 1.f, y = vy * inv_len, z = vz * inv_len;
+            // clamp mask of max(f + 0.5, 0) (sphericalHarmonics.slang:63); rgb holds the unclamped f + 0.5
+            const float mgr = c0 > 0.f ? a3.x : 0.f, mgg = c1 > 0.f ? a3.y : 0.f, mgb = c2 > 0.f ? a3.z : 0.f;
+            float bs[16];
+            sh_basis16(deg, x, y, z, bs);
+            if (deg > 0 && len > 0.f) {
+                // s[j] = sum_c coeff[j][c] * masked_grad[c]; then d(rgb)/d(direction) . grad, then through normalize
+                // (gaussianParticles.slang:545-558)
+                float cf[48];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                    const float4 v = row[k];
+                    cf[k * 4] = v.x; cf[k * 4 + 1] = v.y; cf[k * 4 + 2] = v.z; cf[k * 4 + 3] = v.w;
+                }
+                float sc[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) sc[k] = cf[k * 3] * mgr + cf[k * 3 + 1] * mgg + cf[k * 3 + 2] * mgb;
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                float gx = -kC1 * sc[3], gy = -kC1 * sc[1], gz = kC1 * sc[2];
+                if (deg > 1) {
+                    gx += kC2[0] * y * sc[4] + kC2[2] * (-2.f * x) * sc[6] + kC2[3] * z * sc[7] + kC2[4] * (2.f * x) * sc[8];
+                    gy += kC2[0] * x * sc[4] + kC2[1] * z * sc[5] + kC2[2] * (-2.f * y) * sc[6] + kC2[4] * (-2.f * y) * sc[8];
+                    gz += kC2[1] * y * sc[5] + kC2[2] * (4.f * z) * sc[6] + kC2[3] * x * sc[7];
+                    if (deg > 2) {
+                        gx += kC3[0] * (6.f * xy) * sc[9] + kC3[1] * yz * sc[10] + kC3[2] * (-2.f * xy) * sc[11] + kC3[3] * (-6.f * xz) * sc[12] +
+                              kC3[4] * (4.f * zz - 3.f * xx - yy) * sc[13] + kC3[5] * (2.f * xz) * sc[14] + kC3[6] * (3.f * xx - 3.f * yy) * sc[15];
+                        gy += kC3[0] * (3.f * xx - 3.f * yy) * sc[9] + kC3[1] * xz * sc[10] + kC3[2] * (4.f * zz - xx - 3.f * yy) * sc[11] +
+                              kC3[3] * (-6.f * yz) * sc[12] + kC3[4] * (-2.f * xy) * sc[13] + kC3[5] * (-2.f * yz) * sc[14] +
+                              kC3[6] * (-6.f * xy) * sc[15];
+                        gz += kC3[1] * xy * sc[10] + kC3[2] * (8.f * yz) * sc[11] + kC3[3] * (6.f * zz - 3.f * xx - 3.f * yy) * sc[12] +
+                              kC3[4] * (8.f * xz) * sc[13] + kC3[5] * (xx - yy) * sc[14];
+                    }
+                }
+                const float dd = x * gx + y * gy + z * gz;
+                dpx += (gx - x * dd) * inv_len;
+                dpy += (gy - y * dd) * inv_len;
+                dpz += (gz - z * dd) * inv_len;
+            }
+            float o[48];  // d SH = basis x masked gradient
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                o[k * 3 + 0] = bs[k] * mgr;
+                o[k * 3 + 1] = bs[k] * mgg;
+                o[k * 3 + 2] = bs[k] * mgb;
+            }
+#pragma unroll
+            for (int k = 0; k < 12; ++k) row[k] = make_float4(o[k * 4], o[k * 4 + 1], o[k * 4 + 2], o[k * 4 + 3]);
+        }
+        s_dp[tid * 3 + 0] = make_float4(dpx, dpy, dpz, a0.w);
+        s_dp[tid * 3 + 1] = a1;
+        s_dp[tid * 3 + 2] = make_float4(a2.x, a2.y, a2.z, 0.f);
+    }
+    fence_proxy_async();  // our shared-memory writes must be visible to the TMA engine
+    __syncthreads();
+    if (tid == 0) {
+        tma_bulk_s2g(d_sph + base * 48, s_sh, static_cast<uint32_t>(cnt) * 192u);
+        tma_bulk_s2g(d_particles + base * 12, s_dp, static_cast<uint32_t>(cnt) * 48u);
+        tma_bulk_s2g(grad_acc + base * kGradRow, s_acc, static_cast<uint32_t>(cnt) * 64u);
+        tma_commit_group();
+        tma_wait_group_read0();  // shared memory must stay valid until the engine has read it
+    }
 }
 
 }  // namespace
@@ -635,8 +656,8 @@ void launch_project_backward(cudaStream_t s, const FrameCamera& cam, int64_t n, 
                              int sph_degree, const float* rgb, const uint32_t* tiles_count, float* grad_acc, float* d_particles,
                              float* d_sph) {
     if (n <= 0) return;
-    const unsigned blocks = static_cast<unsigned>((n + 127) / 128);
-    project_backward_kernel<<<blocks, 128, 0, s>>>(cam, n, particles, sph, sph_degree, rgb, tiles_count, grad_acc, d_particles, d_sph);
+    const unsigned blocks = static_cast<unsigned>((n + kPbThreads - 1) / kPbThreads);
+    project_backward_kernel<<<blocks, kPbThreads, 0, s>>>(cam, n, particles, sph, sph_degree, rgb, tiles_count, grad_acc, d_particles, d_sph);
 }
 
 }  // namespace gutb200

@@ -167,8 +167,9 @@ class SplatRaster:
 
     def trace_bwd(self, frame_id, n_active_features, particle_density, particle_radiance, ray_ori, ray_dir, ray_time, sensor_params,
                   timestamp_start, timestamp_end, pose_start, pose_end, ray_radiance_density, ray_radiance_density_grd,
-                  ray_hit_distance, ray_hit_distance_grd):
-        """splatRaster.cpp:264-350 -> (dDensity [N,12], dRadiance [N,48])"""
+                  ray_hit_distance, ray_hit_distance_grd, out=None):
+        """splatRaster.cpp:264-350 -> (dDensity [N,12], dRadiance [N,48]).  `out` (extension): a pair of preallocated
+        tensors to write into, e.g. two views of one flat buffer so that a single all-reduce covers both."""
         dev = ray_ori.device
         h, w = int(ray_ori.shape[1]), int(ray_ori.shape[2])
         n = int(particle_density.shape[0])
@@ -177,8 +178,12 @@ class SplatRaster:
         ray_ori, ray_dir = ray_ori.contiguous(), ray_dir.contiguous()
         rgba, d_rgba = ray_radiance_density.contiguous(), ray_radiance_density_grd.contiguous().float()
         dist, d_dist = ray_hit_distance.contiguous(), ray_hit_distance_grd.contiguous().float()
-        d_density = torch.empty((n, 12), dtype=torch.float32, device=dev)
-        d_radiance = torch.empty((n, 48), dtype=torch.float32, device=dev)
+        if out is not None:
+            d_density, d_radiance = out
+            assert d_density.shape == (n, 12) and d_radiance.shape == (n, 48) and d_density.is_contiguous() and d_radiance.is_contiguous()
+        else:
+            d_density = torch.empty((n, 12), dtype=torch.float32, device=dev)
+            d_radiance = torch.empty((n, 48), dtype=torch.float32, device=dev)
         cam = self._camera(sensor_params, pose_start, pose_end, w, h)
         stream = torch.cuda.current_stream(dev).cuda_stream
         self._context(dev).backward(stream, cam, n, _ptr(particle_density), _ptr(particle_radiance), int(n_active_features),

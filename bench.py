@@ -422,13 +422,16 @@ def main():
     def view_of(step):  # disjoint cameras per rank
         return (step * world + rank) % n_views
 
+    grad_flat = torch.empty(n * 60, dtype=torch.float32, device=dev)  # [N,12] and [N,48] views of one bucket: one all-reduce
+    grad_views = (grad_flat[: n * 12].view(n, 12), grad_flat[n * 12:].view(n, 48))
+
     def step_device(step):
         pose = poses[view_of(step)]
         rgba, dst, hits, vis = raster.trace(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose)
-        dp, ds = raster.trace_bwd(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose, rgba, d_rgba, dst, d_dist)
+        dp, ds = raster.trace_bwd(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose, rgba, d_rgba, dst, d_dist,
+                                  out=grad_views)
         if world > 1:
-            dist.all_reduce(dp)
-            dist.all_reduce(ds)
+            dist.all_reduce(grad_flat)
         return dp, ds
 
     def barrier():
