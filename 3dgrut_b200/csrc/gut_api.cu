@@ -213,6 +213,10 @@ void fill_frame(gutb200_ctx* c, const gutb200_camera* cam) {
     memcpy(f.radial, cam->radial, sizeof(f.radial));
     memcpy(f.tangential, cam->tangential, sizeof(f.tangential));
     memcpy(f.thin_prism, cam->thin_prism, sizeof(f.thin_prism));
+    f.has_distortion = 0;
+    for (float v : cam->radial) f.has_distortion |= (v != 0.f);
+    for (float v : cam->tangential) f.has_distortion |= (v != 0.f);
+    for (float v : cam->thin_prism) f.has_distortion |= (v != 0.f);
     f.res_x = static_cast<float>(cam->width);
     f.res_y = static_cast<float>(cam->height);
     const Pose ps = pose_from7(cam->pose_start), pe = pose_from7(cam->pose_end);

@@ -22,6 +22,7 @@ struct FrameCamera {
     float s2w[12];        // sensor->world at mid exposure (gutRenderer.cu:267,406)
     float cam_pos[3];     // sensor position in world space (gutRenderer.cu:282)
     float res_x, res_y;   // float copies of width/height
+    int has_distortion;   // any radial / tangential / thin-prism coefficient non-zero
 };
 
 struct FrameConfig {

@@ -68,6 +68,14 @@ __device__ __forceinline__ bool project_pinhole(const FrameCamera& cam, float to
         return false;
     }
     const float u = x / z, v = y / z;
+    if (!cam.has_distortion) {
+        // all distortion coefficients are zero: icD == 1 and delta == 0 exactly, so the general expression below
+        // reduces to this one bit for bit
+        ox = u * cam.fx + cam.cx;
+        oy = v * cam.fy + cam.cy;
+        const float mx0 = cam.res_x * tol, my0 = cam.res_y * tol;
+        return (ox > -mx0) && (oy > -my0) && (ox < cam.res_x + mx0) && (oy < cam.res_y + my0);
+    }
     const float uu = u * u, vv = v * v;
     const float r2 = uu + vv;
     const float a1 = 2.f * u * v;

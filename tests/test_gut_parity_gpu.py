@@ -228,3 +228,38 @@ def test_per_pixel_ray_origins_take_the_general_path():
     ctx.backward_host(cam, n, p(sc.particles), p(sc.sph), 3, p(ro_c), p(rd_c), p(rgba), p(d_rgba), p(dist), p(d_dist), p(dp), p(ds))
     assert rel_l2(dp, dp_ref) <= 1e-3 and rel_l2(ds, ds_ref) <= 1e-3
     ctx.close()
+
+
+def test_distorted_pinhole_takes_the_general_projection_path():
+    """Non-zero OpenCV distortion coefficients: tile counts / keys stay bit-exact (cameraProjections.cuh:72-118)."""
+    import b200_native as nat
+    from oracle import gut_oracle as go
+
+    sc = scenes.scene_c1()
+    pose = scenes.pose7_from_c2w(sc.camera(5, 10))
+    ocam = go.make_camera(sc.width, sc.height, sc.fx, sc.fy, sc.cx, sc.cy, pose)
+    cam = nat.Camera()
+    cam.width, cam.height = sc.width, sc.height
+    cam.principal[:] = [sc.cx, sc.cy]
+    cam.focal[:] = [sc.fx, sc.fy]
+    cam.pose_start[:] = [float(v) for v in pose]
+    cam.pose_end[:] = [float(v) for v in pose]
+    for c in (ocam, cam):
+        c.radial[:] = [0.05, -0.01, 0.002, 0.01, 0.0, 0.0]
+        c.tangential[:] = [0.001, -0.0005]
+        c.thin_prism[:] = [0.0003, 0.0, -0.0002, 0.0]
+    ro, rd = sc.rays()
+    cfg = go.default_config()
+    pr, bn, rgba_ref, dist_ref, hits_ref = go.forward_all(cfg, ocam, ro, rd, sc.particles, sc.sph, 3)
+    ctx = nat.Context(nat.default_config(), 0)
+    n, hw = sc.n, sc.width * sc.height
+    rgba, dist, hits, vis = (np.zeros((hw, 4), np.float32), np.zeros(hw, np.float32), np.zeros(hw, np.float32), np.zeros(n, np.float32))
+    p = lambda a: a.ctypes.data  # noqa: E731
+    ro_c, rd_c = np.ascontiguousarray(ro), np.ascontiguousarray(rd)
+    ctx.forward_host(cam, n, p(sc.particles), p(sc.sph), 3, p(ro_c), p(rd_c), p(rgba), p(dist), p(hits), p(vis))
+    assert np.array_equal(ctx.debug_copy(nat.DBG_TILES_COUNT), pr.tiles_count)
+    assert np.array_equal(ctx.debug_copy(nat.DBG_SORTED_KEYS), bn.sorted_keys)
+    assert np.array_equal(ctx.debug_copy(nat.DBG_SORTED_VALUES), bn.sorted_values)
+    mean_e, max_e, bad = image_error_report("distorted pinhole rgba", rgba.reshape(rgba_ref.shape), rgba_ref)
+    assert mean_e <= 1e-5 and max_e <= 2e-2 and bad <= 3
+    ctx.close()
