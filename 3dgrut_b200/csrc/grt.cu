@@ -29,7 +29,7 @@
 namespace gutb200 {
 size_t sort32_temp_bytes(int64_t n);
 void run_sort32_pairs(cudaStream_t s, void* temp, size_t temp_bytes, const uint32_t* kin, uint32_t* kout, const uint32_t* vin,
-                      uint32_t* vout, int64_t n);
+                      uint32_t* vout, int64_t n, int end_bit);
 }  // namespace gutb200
 
 using namespace gutb200;
@@ -657,7 +657,7 @@ int grtb200_build_bvh(grtb200_ctx* c, void* stream, int64_t n, const float* pos,
         morton_kernel<<<blocks, 256, 0, s>>>(ni, static_cast<const Proxy*>(c->proxies), static_cast<const int*>(c->scene),
                                              static_cast<uint32_t*>(c->codes), static_cast<uint32_t*>(c->ids));
         run_sort32_pairs(s, c->sort_temp, c->sort_temp_bytes, static_cast<const uint32_t*>(c->codes), static_cast<uint32_t*>(c->codes_sorted),
-                         static_cast<const uint32_t*>(c->ids), static_cast<uint32_t*>(c->ids_sorted), n);
+                         static_cast<const uint32_t*>(c->ids), static_cast<uint32_t*>(c->ids_sorted), n, 30);
         GRT_CUDA(c, cudaMemsetAsync(c->flags, 0, static_cast<size_t>(n) * 4, s));
         hierarchy_kernel<<<blocks, 256, 0, s>>>(ni, static_cast<const uint32_t*>(c->codes_sorted), static_cast<const uint32_t*>(c->ids_sorted),
                                                 static_cast<int2*>(c->children), static_cast<int*>(c->parent), static_cast<int*>(c->leaf_parent));

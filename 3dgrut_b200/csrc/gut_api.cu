@@ -157,6 +157,7 @@ struct gutb200_ctx {
 
     // forward context (reused by backward): per particle
     DeviceBuffer tiles_count, offsets, proj, depth, rgb, grad_acc, scan_temp;
+    DeviceBuffer ids, perm, depth_sorted, cnt_perm, dsort_temp;   // depth sort of the particles
     // per intersection
     DeviceBuffer keys_in, keys_out, vals_in, vals_out, sort_temp;
     // per tile
@@ -353,7 +354,8 @@ void gutb200_destroy(gutb200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DeviceBuffer* bufs[] = {&c->tiles_count, &c->offsets, &c->proj, &c->depth, &c->rgb, &c->grad_acc, &c->scan_temp, &c->keys_in,
+    DeviceBuffer* bufs[] = {&c->tiles_count, &c->offsets, &c->proj, &c->depth, &c->rgb, &c->grad_acc, &c->scan_temp, &c->ids, &c->perm,
+                            &c->depth_sorted, &c->cnt_perm, &c->dsort_temp, &c->keys_in,
                             &c->keys_out, &c->vals_in, &c->vals_out, &c->sort_temp, &c->ranges, &c->tile_order, &c->h_particles, &c->h_sph,
                             &c->h_rays_o, &c->h_rays_d, &c->h_rgba, &c->h_dist, &c->h_hits, &c->h_vis, &c->h_drgba, &c->h_ddist,
                             &c->h_dpart, &c->h_dsph};
@@ -396,19 +398,29 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     GUT_CUDA(c, c->ranges.reserve(static_cast<size_t>(tiles) * 8, s));
     GUT_CUDA(c, c->tile_order.reserve(static_cast<size_t>(tiles) * 4, s));
     GUT_CUDA(c, c->scan_temp.reserve(scan_temp_bytes(n) + 16, s));
+    GUT_CUDA(c, c->ids.reserve(nn * 4, s));
+    GUT_CUDA(c, c->perm.reserve(nn * 4, s));
+    GUT_CUDA(c, c->depth_sorted.reserve(nn * 4, s));
+    GUT_CUDA(c, c->cnt_perm.reserve(nn * 4, s));
+    GUT_CUDA(c, c->dsort_temp.reserve(sort32_temp_bytes(static_cast<int64_t>(nn)) + 16, s));
 
     uint32_t total = 0;
     if (n > 0) {
         {
             StageTimer t(c, 0, s);
             launch_project(s, c->cam, c->fcfg, n, particles, sph, sph_degree, c->tiles_count.as<uint32_t>(), c->proj.as<ProjRecord>(),
-                           c->depth.as<float>(), c->rgb.as<float>(), visibility);
+                           c->depth.as<float>(), c->rgb.as<float>(), visibility, c->ids.as<uint32_t>());
         }
         c->launches++;
         {
             StageTimer t(c, 1, s);
-            run_inclusive_scan(s, c->scan_temp.ptr, c->scan_temp.bytes, c->tiles_count.as<uint32_t>(), c->offsets.as<uint32_t>(), n);
+            // depth order of the particles (positive floats sort like their bit patterns), then slice offsets in that order
+            run_sort32_pairs(s, c->dsort_temp.ptr, c->dsort_temp.bytes, reinterpret_cast<const uint32_t*>(c->depth.as<float>()),
+                             c->depth_sorted.as<uint32_t>(), c->ids.as<uint32_t>(), c->perm.as<uint32_t>(), n, 32);
+            launch_gather_counts(s, n, c->perm.as<uint32_t>(), c->tiles_count.as<uint32_t>(), c->cnt_perm.as<uint32_t>());
+            run_inclusive_scan(s, c->scan_temp.ptr, c->scan_temp.bytes, c->cnt_perm.as<uint32_t>(), c->offsets.as<uint32_t>(), n);
         }
+        c->launches++;
         // the one host round trip of the frame, as in the reference (gutRenderer.cu:313-321): sizes the sort
         GUT_CUDA(c, cudaMemcpyAsync(c->pinned_total, c->offsets.as<uint32_t>() + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         GUT_CUDA(c, cudaStreamSynchronize(s));
@@ -416,25 +428,25 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     }
     GUT_CUDA(c, cudaMemsetAsync(c->ranges.ptr, 0, static_cast<size_t>(tiles) * 8, s));
     if (total > 0) {
-        const int end_bit = 32 + static_cast<int>(higher_msb(static_cast<uint32_t>(tiles)));
-        GUT_CUDA(c, c->keys_in.reserve(static_cast<size_t>(total) * 8, s));
-        GUT_CUDA(c, c->keys_out.reserve(static_cast<size_t>(total) * 8, s));
+        const int end_bit = static_cast<int>(higher_msb(static_cast<uint32_t>(tiles)));  // tile bits only (gutRenderer.cu:365 sorts 32 + this)
+        GUT_CUDA(c, c->keys_in.reserve(static_cast<size_t>(total) * 4, s));
+        GUT_CUDA(c, c->keys_out.reserve(static_cast<size_t>(total) * 4, s));
         GUT_CUDA(c, c->vals_in.reserve(static_cast<size_t>(total) * 4, s));
         GUT_CUDA(c, c->vals_out.reserve(static_cast<size_t>(total) * 4, s));
-        GUT_CUDA(c, c->sort_temp.reserve(sort_temp_bytes(total, end_bit) + 16, s));
+        GUT_CUDA(c, c->sort_temp.reserve(sort32_temp_bytes(total) + 16, s));
         {
             StageTimer t(c, 2, s);
-            launch_expand(s, c->cam, c->fcfg, n, c->offsets.as<uint32_t>(), c->proj.as<ProjRecord>(), c->depth.as<float>(),
-                          c->keys_in.as<uint64_t>(), c->vals_in.as<uint32_t>());
+            launch_expand(s, c->cam, c->fcfg, n, c->perm.as<uint32_t>(), c->offsets.as<uint32_t>(), c->proj.as<ProjRecord>(),
+                          c->keys_in.as<uint32_t>(), c->vals_in.as<uint32_t>());
         }
         {
             StageTimer t(c, 3, s);
-            run_sort_pairs(s, c->sort_temp.ptr, c->sort_temp.bytes, c->keys_in.as<uint64_t>(), c->keys_out.as<uint64_t>(),
-                           c->vals_in.as<uint32_t>(), c->vals_out.as<uint32_t>(), total, end_bit);
+            run_sort32_pairs(s, c->sort_temp.ptr, c->sort_temp.bytes, c->keys_in.as<uint32_t>(), c->keys_out.as<uint32_t>(),
+                             c->vals_in.as<uint32_t>(), c->vals_out.as<uint32_t>(), total, end_bit);
         }
         {
             StageTimer t(c, 4, s);
-            launch_tile_ranges(s, total, c->keys_out.as<uint64_t>(), c->ranges.as<uint32_t>());
+            launch_tile_ranges(s, total, c->keys_out.as<uint32_t>(), c->ranges.as<uint32_t>());
         }
         c->launches += 2;
     } else {
@@ -585,7 +597,19 @@ int gutb200_debug_copy(gutb200_ctx* c, int what, void* dst, size_t bytes) {
     const size_t n = static_cast<size_t>(c->n), I = static_cast<size_t>(c->num_isect), T = static_cast<size_t>(c->num_tiles);
     switch (what) {
         case GUTB200_DBG_TILES_COUNT: src = c->tiles_count.ptr; have = n * 4; break;
-        case GUTB200_DBG_SORTED_KEYS: src = c->keys_out.ptr; have = I * 8; break;
+        case GUTB200_DBG_SORTED_KEYS: {  // the reference's 64-bit keys, rebuilt from (tile, particle -> depth bits)
+            if (bytes != I * 8) return fail(c, "debug buffer %d holds %zu bytes, caller asked for %zu", what, I * 8, bytes);
+            if (I == 0) return 0;
+            void* tmp = nullptr;
+            GUT_CUDA(c, cudaMalloc(&tmp, I * 8));
+            launch_synth_keys(c->fwd_stream, static_cast<int64_t>(I), c->keys_out.as<uint32_t>(), c->vals_out.as<uint32_t>(), c->depth.as<float>(),
+                              static_cast<uint64_t*>(tmp));
+            cudaError_t e = cudaStreamSynchronize(c->fwd_stream);
+            if (e == cudaSuccess) e = cudaMemcpy(dst, tmp, I * 8, cudaMemcpyDeviceToHost);
+            cudaFree(tmp);
+            GUT_CUDA(c, e);
+            return 0;
+        }
         case GUTB200_DBG_SORTED_VALUES: src = c->vals_out.ptr; have = I * 4; break;
         case GUTB200_DBG_TILE_RANGES: src = c->ranges.ptr; have = T * 8; break;
         case GUTB200_DBG_DEPTH: src = c->depth.ptr; have = n * 4; break;

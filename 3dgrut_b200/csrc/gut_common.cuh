@@ -45,10 +45,12 @@ constexpr int kGradRow = 16;
 
 void launch_project(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const float* particles,
                     const float* sph, int sph_degree, uint32_t* tiles_count, ProjRecord* proj, float* depth, float* rgb,
-                    float* visibility);
-void launch_expand(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const uint32_t* offsets,
-                   const ProjRecord* proj, const float* depth, uint64_t* keys, uint32_t* values);
-void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint64_t* sorted_keys, uint32_t* ranges);
+                    float* visibility, uint32_t* ids);
+void launch_gather_counts(cudaStream_t s, int64_t n, const uint32_t* perm, const uint32_t* counts, uint32_t* out);
+void launch_expand(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const uint32_t* perm, const uint32_t* offsets,
+                   const ProjRecord* proj, uint32_t* keys, uint32_t* values);
+void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint32_t* sorted_keys, uint32_t* ranges);
+void launch_synth_keys(cudaStream_t s, int64_t num, const uint32_t* tiles, const uint32_t* vals, const float* depth, uint64_t* out);
 
 void launch_tile_order(cudaStream_t s, const FrameCamera& cam, const uint32_t* ranges, uint32_t* tile_order);
 void launch_render_forward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
@@ -65,8 +67,8 @@ void launch_project_backward(cudaStream_t s, const FrameCamera& cam, int64_t n, 
 // CUB-backed helpers (scan + radix sort), gut_sort.cu
 size_t scan_temp_bytes(int64_t n);
 void run_inclusive_scan(cudaStream_t s, void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, int64_t n);
-size_t sort_temp_bytes(int64_t n, int end_bit);
-void run_sort_pairs(cudaStream_t s, void* temp, size_t temp_bytes, const uint64_t* kin, uint64_t* kout, const uint32_t* vin,
-                    uint32_t* vout, int64_t n, int end_bit);
+size_t sort32_temp_bytes(int64_t n);
+void run_sort32_pairs(cudaStream_t s, void* temp, size_t temp_bytes, const uint32_t* kin, uint32_t* kout, const uint32_t* vin,
+                      uint32_t* vout, int64_t n, int end_bit);
 
 }  // namespace gutb200

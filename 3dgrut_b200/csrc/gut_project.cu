@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
                                                                const float* __restrict__ sph, int sph_degree,
                                                                uint32_t* __restrict__ tiles_count, ProjRecord* __restrict__ proj,
                                                                float* __restrict__ depth, float* __restrict__ rgb,
-                                                               float* __restrict__ visibility) {
+                                                               float* __restrict__ visibility, uint32_t* __restrict__ ids) {
     __shared__ __align__(128) float4 s_rec[kProjThreads * 3];
     __shared__ __align__(8) uint64_t s_bar;
 
@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
     }
     if (!in_range) return;
     tiles_count[i] = ntiles;
+    ids[i] = static_cast<uint32_t>(i);  // payload of the depth sort
 
     ProjRecord pr;
     float zdepth = 0.f, col[3] = {0.f, 0.f, 0.f};
@@ -340,34 +341,37 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
     rgb[i * 3 + 2] = col[2];
 }
 
-// G3: emit (tile << 32 | depth bits, particle) for every surviving tile (GUTProjector::expand, gutProjector.cuh:324-388).
-// Each particle owns the slice [offset[i-1], offset[i]) of the key stream, so the order between particles is the
-// reference's; inside a slice the tiles are written in the reference's row-major order too (ordered ballot compaction
-// when the warp walks a large footprint together).
-__global__ void __launch_bounds__(256) expand_kernel(FrameCamera cam, FrameConfig cfg, int64_t n,
+// G3: emit (tile, particle) for every surviving tile (GUTProjector::expand, gutProjector.cuh:324-388).
+// The reference emits 64-bit (tile << 32 | depth) keys in particle order and radix-sorts 44 bits of them (6 passes over
+// 12 bytes per entry).  Here the particles are depth-sorted first (N 32-bit keys), each owns the slice
+// [offset[rank-1], offset[rank]) of the stream, and only the 12-13 tile bits of the entries remain to be sorted
+// (2 passes over 8 bytes per entry): same final order, a quarter of the traffic.  Inside a slice the tiles are written
+// in the reference's row-major order (ordered ballot compaction when the warp walks a large footprint together).
+__global__ void __launch_bounds__(256) expand_kernel(FrameCamera cam, FrameConfig cfg, int64_t n, const uint32_t* __restrict__ perm,
                                                      const uint32_t* __restrict__ offsets, const ProjRecord* __restrict__ proj,
-                                                     const float* __restrict__ depth, uint64_t* __restrict__ keys,
-                                                     uint32_t* __restrict__ values) {
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const bool in_range = i < n;
+                                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ values) {
+    // thread j handles the particle at depth rank j: slices of the key stream are laid out in depth order, so the stable
+    // tile sort that follows yields (tile, depth, particle) order == the reference's stable sort of (tile<<32 | depth) keys
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool in_range = j < n;
+    const int64_t i = in_range ? static_cast<int64_t>(perm[j]) : 0;
     ProjRecord pr;
     pr.ex = 0.f;
     if (in_range) pr = proj[i];
     const bool active = in_range && !(pr.ex <= 1e-06f);
-    uint32_t dkey = 0, off = 0, maxoff = 0;
+    uint32_t off = 0, maxoff = 0;
     TileBox bb = {0, 0, 0, 0};
     float maxpow = 0.f;
     int cells = 0;
     if (active) {
-        dkey = __float_as_uint(depth[i]);
-        off = (i == 0) ? 0u : offsets[i - 1];
-        maxoff = offsets[i];
+        off = (j == 0) ? 0u : offsets[j - 1];
+        maxoff = offsets[j];
         bb = tile_box(cam.grid_x, cam.grid_y, pr.cx, pr.cy, pr.ex, pr.ey);
         cells = (bb.x1 - bb.x0) * (bb.y1 - bb.y0);
         if (!cfg.tile_culling) {
             for (int y = bb.y0; y < bb.y1; ++y)
                 for (int x = bb.x0; x < bb.x1; ++x) {
-                    keys[off] = (static_cast<uint64_t>(static_cast<uint32_t>(y * cam.grid_x + x)) << 32) | dkey;
+                    keys[off] = static_cast<uint32_t>(y * cam.grid_x + x);
                     values[off] = static_cast<uint32_t>(i);
                     off++;
                 }
@@ -378,12 +382,12 @@ __global__ void __launch_bounds__(256) expand_kernel(FrameCamera cam, FrameConfi
                 for (int y = bb.y0; (y < bb.y1) && (off < maxoff); ++y)
                     for (int x = bb.x0; (x < bb.x1) && (off < maxoff); ++x)
                         if (tile_min_power(static_cast<float>(x), static_cast<float>(y), pr.ca, pr.cb, pr.cc, pr.cx, pr.cy) < maxpow) {
-                            keys[off] = (static_cast<uint64_t>(static_cast<uint32_t>(y * cam.grid_x + x)) << 32) | dkey;
+                            keys[off] = static_cast<uint32_t>(y * cam.grid_x + x);
                             values[off] = static_cast<uint32_t>(i);
                             off++;
                         }
                 for (; off < maxoff; ++off) {  // padding, never produced when project and expand agree (gutProjector.cuh:372-376)
-                    keys[off] = (static_cast<uint64_t>(kInvalid) << 32) | __float_as_uint(3.4028235e+38f);
+                    keys[off] = kInvalid;
                     values[off] = kInvalid;
                 }
                 cells = 0;
@@ -400,7 +404,7 @@ __global__ void __launch_bounds__(256) expand_kernel(FrameCamera cam, FrameConfi
         const int bw = __shfl_sync(0xFFFFFFFFu, bb.x1, src) - bx0, nc = __shfl_sync(0xFFFFFFFFu, cells, src);
         const float qa = __shfl_sync(0xFFFFFFFFu, pr.ca, src), qb = __shfl_sync(0xFFFFFFFFu, pr.cb, src), qc = __shfl_sync(0xFFFFFFFFu, pr.cc, src);
         const float qx = __shfl_sync(0xFFFFFFFFu, pr.cx, src), qy = __shfl_sync(0xFFFFFFFFu, pr.cy, src), qp = __shfl_sync(0xFFFFFFFFu, maxpow, src);
-        const uint32_t qkey = __shfl_sync(0xFFFFFFFFu, dkey, src), qend = __shfl_sync(0xFFFFFFFFu, maxoff, src);
+        const uint32_t qend = __shfl_sync(0xFFFFFFFFu, maxoff, src);
         uint32_t cur = __shfl_sync(0xFFFFFFFFu, off, src);
         const uint32_t pid = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, static_cast<int>(i & 0x7FFFFFFF), src));
         for (int c0 = 0; c0 < nc; c0 += 32) {
@@ -415,29 +419,29 @@ __global__ void __launch_bounds__(256) expand_kernel(FrameCamera cam, FrameConfi
             const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
             const uint32_t dst = cur + __popc(m & lt_mask);
             if (pass && dst < qend) {
-                keys[dst] = (static_cast<uint64_t>(static_cast<uint32_t>(tile)) << 32) | qkey;
+                keys[dst] = static_cast<uint32_t>(tile);
                 values[dst] = pid;
             }
             cur += __popc(m);
         }
         for (uint32_t k = cur + lane; k < qend; k += 32) {  // padding (see above)
-            keys[k] = (static_cast<uint64_t>(kInvalid) << 32) | __float_as_uint(3.4028235e+38f);
+            keys[k] = kInvalid;
             values[k] = kInvalid;
         }
     }
 }
 
 // G5: [begin,end) of every tile in the sorted key stream (computeSortedTileRangeIndices, gutRenderer.cu:46-76)
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t num_keys, const uint64_t* __restrict__ keys,
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t num_keys, const uint32_t* __restrict__ keys,
                                                           uint32_t* __restrict__ ranges) {
     const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (k >= num_keys) return;
-    const uint32_t tile = static_cast<uint32_t>(keys[k] >> 32);
+    const uint32_t tile = keys[k];
     const bool valid = tile != kInvalid;
     if (k == 0) {
         if (valid) ranges[tile * 2] = 0u;
     } else {
-        const uint32_t prev = static_cast<uint32_t>(keys[k - 1] >> 32);
+        const uint32_t prev = keys[k - 1];
         if (prev != tile) {
             if (prev != kInvalid) ranges[prev * 2 + 1] = static_cast<uint32_t>(k);
             if (valid) ranges[tile * 2] = static_cast<uint32_t>(k);
@@ -446,24 +450,51 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t num_keys, cons
     if (valid && (k == num_keys - 1)) ranges[tile * 2 + 1] = static_cast<uint32_t>(num_keys);
 }
 
+// counts in depth order (input of the offset scan)
+__global__ void __launch_bounds__(256) gather_counts_kernel(int64_t n, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ counts,
+                                                            uint32_t* __restrict__ out) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = counts[perm[j]];
+}
+
+// test-only: the reference's 64-bit keys (tile << 32 | depth bits) of the sorted stream
+__global__ void __launch_bounds__(256) synth_keys_kernel(int64_t num, const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ vals,
+                                                         const float* __restrict__ depth, uint64_t* __restrict__ out) {
+    const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= num) return;
+    const uint32_t v = vals[k];
+    const uint32_t d = v == kInvalid ? __float_as_uint(3.4028235e+38f) : __float_as_uint(depth[v]);
+    out[k] = (static_cast<uint64_t>(tiles[k]) << 32) | d;
+}
+
 }  // namespace
+
+void launch_gather_counts(cudaStream_t s, int64_t n, const uint32_t* perm, const uint32_t* counts, uint32_t* out) {
+    if (n <= 0) return;
+    gather_counts_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(n, perm, counts, out);
+}
+
+void launch_synth_keys(cudaStream_t s, int64_t num, const uint32_t* tiles, const uint32_t* vals, const float* depth, uint64_t* out) {
+    if (num <= 0) return;
+    synth_keys_kernel<<<static_cast<unsigned>((num + 255) / 256), 256, 0, s>>>(num, tiles, vals, depth, out);
+}
 
 void launch_project(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const float* particles,
                     const float* sph, int sph_degree, uint32_t* tiles_count, ProjRecord* proj, float* depth, float* rgb,
-                    float* visibility) {
+                    float* visibility, uint32_t* ids) {
     if (n <= 0) return;
     const unsigned blocks = static_cast<unsigned>((n + kProjThreads - 1) / kProjThreads);
-    project_kernel<<<blocks, kProjThreads, 0, s>>>(cam, cfg, n, particles, sph, sph_degree, tiles_count, proj, depth, rgb, visibility);
+    project_kernel<<<blocks, kProjThreads, 0, s>>>(cam, cfg, n, particles, sph, sph_degree, tiles_count, proj, depth, rgb, visibility, ids);
 }
 
-void launch_expand(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const uint32_t* offsets,
-                   const ProjRecord* proj, const float* depth, uint64_t* keys, uint32_t* values) {
+void launch_expand(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const uint32_t* perm, const uint32_t* offsets,
+                   const ProjRecord* proj, uint32_t* keys, uint32_t* values) {
     if (n <= 0) return;
     const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-    expand_kernel<<<blocks, 256, 0, s>>>(cam, cfg, n, offsets, proj, depth, keys, values);
+    expand_kernel<<<blocks, 256, 0, s>>>(cam, cfg, n, perm, offsets, proj, keys, values);
 }
 
-void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint64_t* sorted_keys, uint32_t* ranges) {
+void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint32_t* sorted_keys, uint32_t* ranges) {
     if (num_keys <= 0) return;
     const unsigned blocks = static_cast<unsigned>((num_keys + 255) / 256);
     tile_ranges_kernel<<<blocks, 256, 0, s>>>(num_keys, sorted_keys, ranges);
