@@ -543,6 +543,8 @@ int gutb200_backward_host(gutb200_ctx* c, const gutb200_camera* cam, int64_t n, 
                           const float* out_dist, const float* d_dist, float* d_particles, float* d_sph) {
     if (!c || !cam) return 1;
     (void)particles; (void)sph; (void)rays_o; (void)rays_d;  // still resident from forward_host (same contract as the reference ctx)
+    if (!c->have_forward || c->fwd_stream != c->own_stream)
+        return fail(c, "backward needs the forward context of the same stream / particle count / resolution");
     cudaStream_t s = c->own_stream;
     const size_t np = static_cast<size_t>(n), px = static_cast<size_t>(cam->width) * cam->height;
     GUT_CUDA(c, cudaSetDevice(c->device));

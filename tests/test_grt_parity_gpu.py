@@ -122,3 +122,31 @@ def test_grt_edge_cases_empty_single_and_missing_rays():
             assert np.abs(rgb.cpu().numpy().reshape(ref[0].shape) - ref[0]).max() <= 1e-4
             assert np.array_equal(hits.cpu().numpy().reshape(ref[3].shape), ref[3])
     ctx.close()
+
+
+def test_hybrid_primary_raster_plus_traced_secondary():
+    """BASELINE config 5: 3DGUT primary + 3DGRT secondary on the same Gaussians; each pass matches its oracle and the
+    gradients of the composite reach the parameters through both tracers."""
+    import hybrid
+    import threedgrt_tracer
+    import threedgut_tracer
+    from test_gut_parity_gpu import _Batch as GutBatch
+
+    sc = scenes.scene_c1(n=400, width=64, height=48)
+    c2w = np.asarray(sc.camera(2, 9), np.float32)
+    dev = torch.device("cuda", 0)
+    g = _Gaussians(sc, dev)
+    g.positions.grad = None
+    batch = GutBatch(sc, c2w, dev)
+    batch.T_to_world = batch.T_to_world.to(dev)
+    gut = threedgut_tracer.Tracer({})
+    grt = threedgrt_tracer.Tracer({"render": {"min_transmittance": 0.001}})
+    out = hybrid.render_hybrid(gut, grt, g, batch, train=True)
+    # secondary pass against the brute-force oracle on the same reflected rays
+    sec_o, sec_d, hit = hybrid.mirror_rays(batch.rays_ori, batch.rays_dir, batch.T_to_world, (0.0, 0.0, -1.2), (0.0, 0.0, 1.0))
+    ref = go.grt_trace(go.grt_config(), sc.particles, sc.sph, 3, sec_o[0].cpu().numpy(), sec_d[0].cpu().numpy(), np.eye(4, dtype=np.float32))
+    mean_e, max_e, bad = image_error_report("hybrid secondary rgb", out["pred_secondary"][0].detach().cpu().numpy(), ref[0])
+    assert mean_e <= 1e-5 and max_e <= 2e-2 and bad <= 3
+    assert float(hit.float().mean()) > 0.05
+    out["pred_features_hybrid"].sum().backward()
+    assert g.positions.grad is not None and float(g.positions.grad.abs().sum()) > 0 and torch.isfinite(g._sph.grad).all()

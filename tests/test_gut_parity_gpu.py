@@ -263,3 +263,28 @@ def test_distorted_pinhole_takes_the_general_projection_path():
     mean_e, max_e, bad = image_error_report("distorted pinhole rgba", rgba.reshape(rgba_ref.shape), rgba_ref)
     assert mean_e <= 1e-5 and max_e <= 2e-2 and bad <= 3
     ctx.close()
+
+
+def test_error_conventions():
+    """Failures surface as non-zero return codes / exceptions (the reference logs and drops its Status codes)."""
+    import b200_native as nat
+
+    ctx = nat.Context(nat.default_config(), 0)
+    cam = nat.Camera()
+    cam.width, cam.height = 32, 32
+    buf = np.zeros((4, 64), np.float32)
+    with pytest.raises(RuntimeError, match="forward context"):
+        ctx.backward_host(cam, 1, buf.ctypes.data, buf.ctypes.data, 3, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data,
+                          buf.ctypes.data, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data)
+    bad = nat.default_config()
+    bad.kernel_degree = 3
+    ctx2 = nat.Context(bad, 0)
+    with pytest.raises(RuntimeError, match="kernel_degree"):
+        ctx2.forward_host(cam, 1, buf.ctypes.data, buf.ctypes.data, 3, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data,
+                          buf.ctypes.data, buf.ctypes.data)
+    cam.width = 0
+    with pytest.raises(RuntimeError, match="resolution"):
+        ctx.forward_host(cam, 1, buf.ctypes.data, buf.ctypes.data, 3, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data,
+                         buf.ctypes.data, buf.ctypes.data)
+    ctx.close()
+    ctx2.close()
