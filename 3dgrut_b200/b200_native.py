@@ -30,7 +30,7 @@ class Config(C.Structure):
         ("ut_alpha", C.c_float), ("ut_beta", C.c_float), ("ut_kappa", C.c_float), ("ut_delta", C.c_float),
         ("ut_margin", C.c_float),
         ("rect_bounding", C.c_int32), ("tight_opacity_bounding", C.c_int32), ("tile_culling", C.c_int32),
-        ("global_z_order", C.c_int32), ("enable_timings", C.c_int32),
+        ("global_z_order", C.c_int32), ("enable_timings", C.c_int32), ("subtile_culling", C.c_int32),
     ]
 
 

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -252,6 +253,7 @@ void fill_frame(gutb200_ctx* c, const gutb200_camera* cam) {
     g.tight_opacity_bounding = s.tight_opacity_bounding;
     g.tile_culling = s.tile_culling;
     g.global_z_order = s.global_z_order;
+    g.subtile_culling = s.subtile_culling;
 }
 
 int check_args(gutb200_ctx* c, const gutb200_camera* cam, int64_t n, const void* particles) {
@@ -329,6 +331,8 @@ void gutb200_default_config(gutb200_config* c) {  // configs/render/3dgut.yaml, 
     c->tile_culling = 1;
     c->global_z_order = 1;
     c->enable_timings = 0;
+    c->subtile_culling = 3;  // bit 0: renderBackward, bit 1: render
+    if (const char* e = std::getenv("GUTB200_SUBTILE_CULLING")) c->subtile_culling = std::atoi(e);  // A/B switch for profiling
 }
 
 int gutb200_create(const gutb200_config* cfg, int device, gutb200_ctx** out) {

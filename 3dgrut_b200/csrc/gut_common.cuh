@@ -31,6 +31,7 @@ struct FrameConfig {
     float ut_delta, ut_margin;
     float w0_mean, wi, w0_cov;   // unscented-transform weights (gutProjector.cuh:150,163,201)
     int rect_bounding, tight_opacity_bounding, tile_culling, global_z_order;
+    int subtile_culling;   // ours: conservative per-warp / per-pixel conic pre-test in the render kernels (gut_render.cu)
 };
 
 // Projection result of one particle consumed by the expand kernel: centre, extent, conic, opacity (32 B).

@@ -76,6 +76,126 @@ __device__ __forceinline__ float kernel_response_grad(float gray, float gres, fl
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// Sub-tile culling (ours; the reference runs the full test on all 256 pixels of a tile for every entry of the tile's list).
+//
+// For rays with a common origin o the accept test of a (pixel, particle) pair,
+//     |normalize(M d) x g|^2 < r^2,   M = S^-1 R^T, g = M (o - mu),  r^2 = r^2(min response, min alpha / density),
+// is a quadratic inequality in the projective coordinates (u, v) of the ray in a local frame (e1, e2, e3), d ~ e3 + u e1 + v e2:
+//     f(u,v) = |c3 + u c1 + v c2|^2 - r^2 |a3 + u a1 + v a2|^2 < 0,   a_i = M e_i,  c_i = a_i x g
+// (same cross-product formulation as the exact test, hence the same conditioning).  Each warp owns an 8x4 pixel block; before it
+// walks a chunk of 32 list entries, LANE k decides for ENTRY k whether {f < 0} can meet the block's (u, v) rectangle at all --
+// the minimum of the convex quadratic over the rectangle, with r^2 inflated and a bound of the fp32 evaluation error subtracted,
+// so the decision is a NECESSARY condition of the exact test.  The warp then runs the exact test only on the entries whose
+// ballot bit is set (48 % of the warp iterations on C2).  Pairs dropped could never be accepted: outputs are bit-identical with
+// the switch on and off (tests/test_gut_parity_gpu.py::test_subtile_culling_is_bit_identical).
+
+struct WarpFrame {
+    float e1x, e1y, e1z, e2x, e2y, e2z, e3x, e3y, e3z;   // frame around the direction of the block's first live pixel
+    float ulo, uhi, vlo, vhi, umax;                      // the block's rectangle in that frame
+    bool on;
+};
+
+__device__ __forceinline__ WarpFrame make_warp_frame(const FrameCamera& cam, const Ray& ray, bool alive, bool enabled, int lane) {
+    WarpFrame wf;
+    wf.on = false;
+    const unsigned live = __ballot_sync(kFull, alive);
+    if (!enabled || live == 0u) return wf;
+    const int src = __ffs(live) - 1;
+    float dx = __shfl_sync(kFull, ray.dx, src), dy = __shfl_sync(kFull, ray.dy, src), dz = __shfl_sync(kFull, ray.dz, src);
+    const float n2 = dx * dx + dy * dy + dz * dz;
+    if (!(n2 > 1e-20f) || !(n2 < 1e20f)) return wf;
+    const float in = rsqrtf(n2);
+    dx *= in; dy *= in; dz *= in;
+    const float* m = cam.s2w;  // complement: the camera axis least aligned with the direction
+    const float cxa = fabsf(m[0] * dx + m[1] * dy + m[2] * dz), cya = fabsf(m[3] * dx + m[4] * dy + m[5] * dz);
+    const float ax = cxa <= cya ? m[0] : m[3], ay = cxa <= cya ? m[1] : m[4], az = cxa <= cya ? m[2] : m[5];
+    const float k = ax * dx + ay * dy + az * dz;
+    float e1x = ax - k * dx, e1y = ay - k * dy, e1z = az - k * dz;
+    const float l1 = e1x * e1x + e1y * e1y + e1z * e1z;
+    if (!(l1 > 1e-6f)) return wf;
+    const float i1 = rsqrtf(l1);
+    e1x *= i1; e1y *= i1; e1z *= i1;
+    wf.e1x = e1x; wf.e1y = e1y; wf.e1z = e1z;
+    wf.e2x = dy * e1z - dz * e1y; wf.e2y = dz * e1x - dx * e1z; wf.e2z = dx * e1y - dy * e1x;
+    wf.e3x = dx; wf.e3y = dy; wf.e3z = dz;
+    // this lane's ray in the frame; every live ray must point within 60 degrees of e3
+    const float w = ray.dx * dx + ray.dy * dy + ray.dz * dz;
+    const float r2 = ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz;
+    const bool fine = !alive || ((w > 0.f) && (w * w > 0.25f * r2));
+    const float iw = (alive && fine) ? 1.0f / w : 0.f;
+    const float u = (ray.dx * e1x + ray.dy * e1y + ray.dz * e1z) * iw;
+    const float v = (ray.dx * wf.e2x + ray.dy * wf.e2y + ray.dz * wf.e2z) * iw;
+    float ulo = alive ? u : 3.0e38f, uhi = alive ? u : -3.0e38f, vlo = alive ? v : 3.0e38f, vhi = alive ? v : -3.0e38f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ulo = fminf(ulo, __shfl_xor_sync(kFull, ulo, o));
+        uhi = fmaxf(uhi, __shfl_xor_sync(kFull, uhi, o));
+        vlo = fminf(vlo, __shfl_xor_sync(kFull, vlo, o));
+        vhi = fmaxf(vhi, __shfl_xor_sync(kFull, vhi, o));
+    }
+    // half a pixel of slack is not needed: the rectangle is the hull of the rays themselves
+    wf.ulo = ulo; wf.uhi = uhi; wf.vlo = vlo; wf.vhi = vhi;
+    wf.umax = fmaxf(fmaxf(fabsf(ulo), fabsf(uhi)), fmaxf(fabsf(vlo), fabsf(vhi)));
+    wf.on = __all_sync(kFull, fine);
+    return wf;
+}
+
+// Can any ray of the warp's block be accepted by the particle with canonical transform rows (m0, m1, m2), canonical ray origin g
+// and density dns?  Conservative (see the section comment).
+template <int DEG>
+__device__ __forceinline__ bool block_candidate(const FrameConfig& cfg, const WarpFrame& wf, float m0x, float m0y, float m0z, float m1x,
+                                                float m1y, float m1z, float m2x, float m2y, float m2z, float gx, float gy, float gz,
+                                                float dns) {
+    const float tau = fmaxf(cfg.min_kernel_density, dns > 0.f ? cfg.min_alpha / dns : 2.f);
+    if (!(tau < 1.f)) return false;  // response <= 1: never accepted
+    const float ln = -logf(tau);
+    float r2 = DEG == 4 ? sqrtf(18.f * ln) : 2.f * ln;   // exp(-gray^2/18) > tau  |  exp(-gray/2) > tau
+    r2 = r2 * 1.002f + 1e-6f;
+    const float a1x = m0x * wf.e1x + m0y * wf.e1y + m0z * wf.e1z, a1y = m1x * wf.e1x + m1y * wf.e1y + m1z * wf.e1z,
+                a1z = m2x * wf.e1x + m2y * wf.e1y + m2z * wf.e1z;
+    const float a2x = m0x * wf.e2x + m0y * wf.e2y + m0z * wf.e2z, a2y = m1x * wf.e2x + m1y * wf.e2y + m1z * wf.e2z,
+                a2z = m2x * wf.e2x + m2y * wf.e2y + m2z * wf.e2z;
+    const float a3x = m0x * wf.e3x + m0y * wf.e3y + m0z * wf.e3z, a3y = m1x * wf.e3x + m1y * wf.e3y + m1z * wf.e3z,
+                a3z = m2x * wf.e3x + m2y * wf.e3y + m2z * wf.e3z;
+    const float c1x = a1y * gz - a1z * gy, c1y = a1z * gx - a1x * gz, c1z = a1x * gy - a1y * gx;
+    const float c2x = a2y * gz - a2z * gy, c2y = a2z * gx - a2x * gz, c2z = a2x * gy - a2y * gx;
+    const float c3x = a3y * gz - a3z * gy, c3y = a3z * gx - a3x * gz, c3z = a3x * gy - a3y * gx;
+    const float a33 = a3x * a3x + a3y * a3y + a3z * a3z, c33 = c3x * c3x + c3y * c3y + c3z * c3z;
+    const float A00 = (c1x * c1x + c1y * c1y + c1z * c1z) - r2 * (a1x * a1x + a1y * a1y + a1z * a1z);
+    const float A01 = (c1x * c2x + c1y * c2y + c1z * c2z) - r2 * (a1x * a2x + a1y * a2y + a1z * a2z);
+    const float A11 = (c2x * c2x + c2y * c2y + c2z * c2z) - r2 * (a2x * a2x + a2y * a2y + a2z * a2z);
+    const float B0 = (c1x * c3x + c1y * c3y + c1z * c3z) - r2 * (a1x * a3x + a1y * a3y + a1z * a3z);
+    const float B1 = (c2x * c3x + c2y * c3y + c2z * c3z) - r2 * (a2x * a3x + a2y * a3y + a2z * a3z);
+    const float K = c33 - r2 * a33;
+    // f is convex iff A > 0; otherwise {f < 0} is unbounded (particle around / behind the origin): keep the entry
+    if (!(A00 > 0.f) || !(A11 > 0.f) || !(A00 * A11 > A01 * A01)) return true;
+    // bound of the fp32 error of f over the block and of the exact test's own rounding near the boundary
+    const float U = wf.umax;
+    const float g2 = gx * gx + gy * gy + gz * gz;
+    const float err = 1e-5f * ((A00 + 2.f * fabsf(A01) + A11) * U * U + 2.f * (fabsf(B0) + fabsf(B1)) * U + c33 + r2 * a33) +
+                      4e-6f * sqrtf(fmaxf(c33, r2 * a33) * a33 * g2);
+    const float Kp = K - err;
+    // minimum of f(u,v) = A00 u^2 + 2 A01 u v + A11 v^2 + 2 B0 u + 2 B1 v + Kp over the rectangle: the unconstrained minimiser
+    // if it lies inside, else the smallest of the four edge minima (1-D convex quadratics, clamped)
+    const float u0 = wf.ulo, u1 = wf.uhi, v0 = wf.vlo, v1 = wf.vhi;
+    const float iA00 = 1.0f / A00, iA11 = 1.0f / A11;
+    const float qa = fmaf(A01, u0, B1), qb = fmaf(A01, u1, B1), pa = fmaf(A01, v0, B0), pb = fmaf(A01, v1, B0);
+    const float va = fminf(fmaxf(-qa * iA11, v0), v1), vb = fminf(fmaxf(-qb * iA11, v0), v1);
+    const float ua = fminf(fmaxf(-pa * iA00, u0), u1), ub = fminf(fmaxf(-pb * iA00, u0), u1);
+    const float fa = fmaf(va, fmaf(A11, va, 2.f * qa), fmaf(u0, fmaf(A00, u0, 2.f * B0), Kp));
+    const float fb = fmaf(vb, fmaf(A11, vb, 2.f * qb), fmaf(u1, fmaf(A00, u1, 2.f * B0), Kp));
+    const float fc = fmaf(ua, fmaf(A00, ua, 2.f * pa), fmaf(v0, fmaf(A11, v0, 2.f * B1), Kp));
+    const float fd = fmaf(ub, fmaf(A00, ub, 2.f * pb), fmaf(v1, fmaf(A11, v1, 2.f * B1), Kp));
+    const float edge_min = fminf(fminf(fa, fb), fminf(fc, fd));
+    // centre inside the rectangle: the interior minimum is below every edge value; keep the entry unless even f(centre) > 0,
+    // which the edge values cannot tell -- so test the centre explicitly
+    const float det = A00 * A11 - A01 * A01;
+    const float cu = (A01 * B1 - A11 * B0), cv = (A01 * B0 - A00 * B1);  // times det
+    const bool inside = (cu >= u0 * det) && (cu <= u1 * det) && (cv >= v0 * det) && (cv <= v1 * det);
+    return inside || (edge_min < 0.f);
+}
+
+// ----------------------------------------------------------------------------------------------------------
 // G6 forward
 // staged record, 5 x float4: rows of M = diag(1/s) R^T with the particle position in .w, then (s, density), (rgb)
 
@@ -108,11 +228,57 @@ __device__ __forceinline__ bool tile_common_origin(const FrameCamera& cam, const
     return __syncthreads_and(same);
 }
 
+// exact test + compositing of one (pixel, staged entry j) pair
 template <int DEG, bool UNIFORM>
-__device__ __forceinline__ void forward_tile(const FrameConfig& cfg, FwdSmem& sm, const Ray& ray, float o0x, float o0y, float o0z, int tid,
-                                             uint32_t begin, uint32_t end, const float* __restrict__ particles,
+__device__ __forceinline__ void forward_pair(const FrameConfig& cfg, const FwdSmem& sm, int j, const Ray& ray, bool& alive, float& T, float& cr,
+                                             float& cg, float& cb, float& dist, uint32_t& hits) {
+    const float4 m0 = sm.m0[j], m1 = sm.m1[j], m2 = sm.m2[j];
+    float gox, goy, goz;
+    if (UNIFORM) {
+        gox = m0.w; goy = m1.w; goz = m2.w;
+    } else {
+        const float vx = ray.ox - m0.w, vy = ray.oy - m1.w, vz = ray.oz - m2.w;
+        gox = m0.x * vx + m0.y * vy + m0.z * vz;
+        goy = m1.x * vx + m1.y * vy + m1.z * vz;
+        goz = m2.x * vx + m2.y * vy + m2.z * vz;
+    }
+    const float ax = m0.x * ray.dx + m0.y * ray.dy + m0.z * ray.dz;
+    const float ay = m1.x * ray.dx + m1.y * ray.dy + m1.z * ray.dz;
+    const float az = m2.x * ray.dx + m2.y * ray.dy + m2.z * ray.dz;
+    const float l = ax * ax + ay * ay + az * az;
+    const float il = l > 0.f ? rsqrtf(l) : 1.f;
+    const float gdx = ax * il, gdy = ay * il, gdz = az * il;
+    const float ccx = gdy * goz - gdz * goy, ccy = gdz * gox - gdx * goz, ccz = gdx * goy - gdy * gox;
+    const float gray = ccx * ccx + ccy * ccy + ccz * ccz;
+    const float gres = kernel_response<DEG>(gray);
+    const float4 sd = sm.sd[j];
+    const float alpha = fminf(cfg.max_alpha, gres * sd.w);
+    if ((gres > cfg.min_kernel_density) && (alpha > cfg.min_alpha)) {
+        const float pd = -(gdx * gox + gdy * goy + gdz * goz);
+        const float hx = sd.x * gdx * pd, hy = sd.y * gdy * pd, hz = sd.z * gdz * pd;
+        const float t = sqrtf(hx * hx + hy * hy + hz * hz);
+        if ((t > ray.tmin) && (t < ray.tmax)) {
+            const float w = alpha * T;
+            dist += t * w;
+            T *= (1.f - alpha);
+            if (w > 0.f) {
+                const float4 c = sm.col[j];
+                cr += c.x * w;
+                cg += c.y * w;
+                cb += c.z * w;
+                hits++;
+            }
+            if (T < cfg.min_transmittance) alive = false;
+        }
+    }
+}
+
+template <int DEG, bool UNIFORM>
+__device__ __forceinline__ void forward_tile(const FrameConfig& cfg, FwdSmem& sm, const WarpFrame& wf, const Ray& ray, float o0x, float o0y,
+                                             float o0z, int tid, uint32_t begin, uint32_t end, const float* __restrict__ particles,
                                              const float* __restrict__ rgb, const uint32_t* __restrict__ sorted_values, bool& alive,
                                              float& T, float& cr, float& cg, float& cb, float& dist, uint32_t& hits) {
+    const int lane = tid & 31;
     for (uint32_t base = begin; base < end; base += kBatch) {
         if (__syncthreads_and(!alive)) break;
         const uint32_t k = base + tid;
@@ -141,46 +307,25 @@ __device__ __forceinline__ void forward_tile(const FrameConfig& cfg, FwdSmem& sm
         }
         __syncthreads();
         const int count = min(kBatch, static_cast<int>(end - base));
-        for (int j = 0; alive && j < count; ++j) {
-            const float4 m0 = sm.m0[j], m1 = sm.m1[j], m2 = sm.m2[j];
-            float gox, goy, goz;
-            if (UNIFORM) {
-                gox = m0.w; goy = m1.w; goz = m2.w;
-            } else {
-                const float vx = ray.ox - m0.w, vy = ray.oy - m1.w, vz = ray.oz - m2.w;
-                gox = m0.x * vx + m0.y * vy + m0.z * vz;
-                goy = m1.x * vx + m1.y * vy + m1.z * vz;
-                goz = m2.x * vx + m2.y * vy + m2.z * vz;
-            }
-            const float ax = m0.x * ray.dx + m0.y * ray.dy + m0.z * ray.dz;
-            const float ay = m1.x * ray.dx + m1.y * ray.dy + m1.z * ray.dz;
-            const float az = m2.x * ray.dx + m2.y * ray.dy + m2.z * ray.dz;
-            const float l = ax * ax + ay * ay + az * az;
-            const float il = l > 0.f ? rsqrtf(l) : 1.f;
-            const float gdx = ax * il, gdy = ay * il, gdz = az * il;
-            const float ccx = gdy * goz - gdz * goy, ccy = gdz * gox - gdx * goz, ccz = gdx * goy - gdy * gox;
-            const float gray = ccx * ccx + ccy * ccy + ccz * ccz;
-            const float gres = kernel_response<DEG>(gray);
-            const float4 sd = sm.sd[j];
-            const float alpha = fminf(cfg.max_alpha, gres * sd.w);
-            if ((gres > cfg.min_kernel_density) && (alpha > cfg.min_alpha)) {
-                const float pd = -(gdx * gox + gdy * goy + gdz * goz);
-                const float hx = sd.x * gdx * pd, hy = sd.y * gdy * pd, hz = sd.z * gdz * pd;
-                const float t = sqrtf(hx * hx + hy * hy + hz * hz);
-                if ((t > ray.tmin) && (t < ray.tmax)) {
-                    const float w = alpha * T;
-                    dist += t * w;
-                    T *= (1.f - alpha);
-                    if (w > 0.f) {
-                        const float4 c = sm.col[j];
-                        cr += c.x * w;
-                        cg += c.y * w;
-                        cb += c.z * w;
-                        hits++;
-                    }
-                    if (T < cfg.min_transmittance) alive = false;
+        if (UNIFORM) {
+            // chunks of 32 entries: lane k screens entry k against the warp's pixel block, the warp walks the survivors
+            for (int c = 0; c < count; c += 32) {
+                if (!__any_sync(kFull, alive)) break;
+                const int e = c + lane;
+                bool cand = e < count;
+                if (wf.on && cand) {
+                    const float4 m0 = sm.m0[e], m1 = sm.m1[e], m2 = sm.m2[e];
+                    cand = block_candidate<DEG>(cfg, wf, m0.x, m0.y, m0.z, m1.x, m1.y, m1.z, m2.x, m2.y, m2.z, m0.w, m1.w, m2.w, sm.sd[e].w);
+                }
+                unsigned todo = __ballot_sync(kFull, cand);
+                while (todo) {
+                    const int j = c + __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    if (alive) forward_pair<DEG, true>(cfg, sm, j, ray, alive, T, cr, cg, cb, dist, hits);
                 }
             }
+        } else {
+            for (int j = 0; alive && j < count; ++j) forward_pair<DEG, false>(cfg, sm, j, ray, alive, T, cr, cg, cb, dist, hits);
         }
     }
 }
@@ -209,15 +354,16 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
     const bool valid = inside && ray.alive;
     float o0x, o0y, o0z;
     const bool uniform = tile_common_origin(cam, rays_o, tile, inside, pix, o0x, o0y, o0z);
+    const WarpFrame wf = make_warp_frame(cam, ray, valid, uniform && (cfg.subtile_culling & 2), tid & 31);
 
     float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, dist = 0.f;
     uint32_t hits = 0;
     bool alive = valid;
     const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
     if (uniform)
-        forward_tile<DEG, true>(cfg, sm, ray, o0x, o0y, o0z, tid, begin, end, particles, rgb, sorted_values, alive, T, cr, cg, cb, dist, hits);
+        forward_tile<DEG, true>(cfg, sm, wf, ray, o0x, o0y, o0z, tid, begin, end, particles, rgb, sorted_values, alive, T, cr, cg, cb, dist, hits);
     else
-        forward_tile<DEG, false>(cfg, sm, ray, o0x, o0y, o0z, tid, begin, end, particles, rgb, sorted_values, alive, T, cr, cg, cb, dist, hits);
+        forward_tile<DEG, false>(cfg, sm, wf, ray, o0x, o0y, o0z, tid, begin, end, particles, rgb, sorted_values, alive, T, cr, cg, cb, dist, hits);
 
     if (valid) {  // finalizeRay (rayPayload.cuh:160-193); invalid rays keep the initial buffer values
         reinterpret_cast<float4*>(out_rgba)[pix] = make_float4(cr, cg, cb, 1.0f - T);
@@ -300,8 +446,8 @@ __device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lan
 }
 
 template <int DEG, bool UNIFORM>
-__device__ __forceinline__ void backward_tile(const FrameConfig& cfg, BwdSmem& sm, const Ray& ray, float o0x, float o0y, float o0z, int tid,
-                                              int lane, uint32_t begin, uint32_t end, const float* __restrict__ particles,
+__device__ __forceinline__ void backward_tile(const FrameConfig& cfg, BwdSmem& sm, const WarpFrame& wf, const Ray& ray, float o0x, float o0y,
+                                              float o0z, int tid, int lane, uint32_t begin, uint32_t end, const float* __restrict__ particles,
                                               const float* __restrict__ rgb, const uint32_t* __restrict__ sorted_values, bool alive,
                                               float Cix, float Ciy, float Ciz, float Cgx, float Cgy, float Cgz, float Tint, float Tgrad,
                                               float Dint, float Dgrad, float* __restrict__ grad_acc) {
@@ -333,8 +479,20 @@ __device__ __forceinline__ void backward_tile(const FrameConfig& cfg, BwdSmem& s
         }
         __syncthreads();
         const int count = min(kBatch, static_cast<int>(end - base));
-        for (int j = 0; j < count; ++j) {
+        // chunks of 32 entries: lane k screens entry k against the warp's pixel block (UNIFORM tiles), the warp walks the survivors
+        for (int c = 0; c < count; c += 32) {
             if (__all_sync(kFull, !alive)) break;
+            const int e = c + lane;
+            bool cand = e < count;
+            if (UNIFORM && wf.on && cand) {
+                const float4 r0 = sm.r0[e], r1 = sm.r1[e], r2 = sm.r2[e], is = sm.is[e], g0 = sm.go[e];
+                cand = block_candidate<DEG>(cfg, wf, is.x * r0.x, is.x * r0.y, is.x * r0.z, is.y * r1.x, is.y * r1.y, is.y * r1.z, is.z * r2.x,
+                                            is.z * r2.y, is.z * r2.z, g0.x, g0.y, g0.z, sm.sc[e].w);
+            }
+            unsigned todo = __ballot_sync(kFull, cand);
+            while (todo) {
+            const int j = c + __ffs(todo) - 1;
+            todo &= todo - 1;
             float g[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) g[i] = 0.f;
@@ -445,6 +603,8 @@ __device__ __forceinline__ void backward_tile(const FrameConfig& cfg, BwdSmem& s
                     const uint32_t idx = __float_as_uint(sm.cl[j].w);
                     atomicAdd(grad_acc + static_cast<size_t>(idx) * kGradRow + (lane >> 1), total);
                 }
+                if (__all_sync(kFull, !alive)) break;
+            }
             }
         }
     }
@@ -491,13 +651,21 @@ __global__ void __launch_bounds__(kTilePixels, 3) render_backward_kernel(FrameCa
 
     float o0x, o0y, o0z;
     const bool uniform = tile_common_origin(cam, rays_o, tile, inside, pix, o0x, o0y, o0z);
+    // the warp-uniform frame lives in shared memory: 15 fewer live registers in the adjoint loop
+    __shared__ WarpFrame wfs[kTilePixels / 32];
+    WarpFrame& wf = wfs[tid >> 5];
+    {
+        const WarpFrame tmp = make_warp_frame(cam, ray, alive, uniform && (cfg.subtile_culling & 1), lane);
+        if (lane == 0) wf = tmp;
+        __syncwarp();
+    }
     const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
     if (uniform)
-        backward_tile<DEG, true>(cfg, sm, ray, o0x, o0y, o0z, tid, lane, begin, end, particles, rgb, sorted_values, alive, Cix, Ciy, Ciz, Cgx,
-                                 Cgy, Cgz, Tint, Tgrad, Dint, Dgrad, grad_acc);
+        backward_tile<DEG, true>(cfg, sm, wf, ray, o0x, o0y, o0z, tid, lane, begin, end, particles, rgb, sorted_values, alive, Cix, Ciy, Ciz,
+                                 Cgx, Cgy, Cgz, Tint, Tgrad, Dint, Dgrad, grad_acc);
     else
-        backward_tile<DEG, false>(cfg, sm, ray, o0x, o0y, o0z, tid, lane, begin, end, particles, rgb, sorted_values, alive, Cix, Ciy, Ciz, Cgx,
-                                  Cgy, Cgz, Tint, Tgrad, Dint, Dgrad, grad_acc);
+        backward_tile<DEG, false>(cfg, sm, wf, ray, o0x, o0y, o0z, tid, lane, begin, end, particles, rgb, sorted_values, alive, Cix, Ciy, Ciz,
+                                  Cgx, Cgy, Cgz, Tint, Tgrad, Dint, Dgrad, grad_acc);
 }
 
 // ----------------------------------------------------------------------------------------------------------

@@ -196,6 +196,65 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+
+class HostFeed:
+    """End-to-end input feed: every step's rays and target image are copied from pinned host memory on a copy stream
+    while the previous step computes (what a DataLoader with pinned memory does), and every step's loss is read back
+    to the host through a pinned slot one step later.  All copies stay inside the timed region: K steps issue K
+    host->device input copies and K device->host loss reads."""
+
+    def __init__(self, torch, dev, pinned):
+        self.torch, self.dev, self.pinned = torch, dev, pinned
+        self.stream = torch.cuda.Stream(device=dev)
+        self.next = None
+        self.loss_slots = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.loss_events = [None, None]
+        self.count = 0
+        self.last_loss = float("nan")
+
+    def _issue(self):
+        torch = self.torch
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))  # buffers freed by older steps are safe to reuse
+        with torch.cuda.stream(self.stream):
+            tensors = [t.to(self.dev, non_blocking=True) for t in self.pinned]
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return tensors, ev
+
+    def take(self):
+        """This step's device tensors (copy already in flight) + issue the next step's copy."""
+        torch = self.torch
+        if self.next is None:
+            self.next = self._issue()
+        tensors, ev = self.next
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(ev)
+        for t in tensors:
+            t.record_stream(cur)
+        self.next = self._issue()
+        return tensors
+
+    def give_loss(self, loss):
+        """Queue the device->host read of this step's loss; return the previous step's value."""
+        torch = self.torch
+        k = self.count & 1
+        if self.loss_events[k ^ 1] is not None:
+            self.loss_events[k ^ 1].synchronize()
+            self.last_loss = float(self.loss_slots[k ^ 1][0])
+        self.loss_slots[k].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.loss_events[k] = ev
+        self.count += 1
+        return self.last_loss
+
+    def drain(self):
+        for ev in self.loss_events:
+            if ev is not None:
+                ev.synchronize()
+        self.torch.cuda.synchronize(self.dev)
+
+
 def run_grt(args, rank, local_rank, world, dev, dist):
     """C4: the C2 scene through the 3DGRT path.  A step = build_bvh (the reference's default config rebuilds every
     step, configs/render/3dgrt.yaml:6 + base_gs.yaml:88) + trace + trace_bwd."""
@@ -301,11 +360,11 @@ def run_grt(args, rank, local_rank, world, dev, dist):
     class _B:
         pass
 
+    feed = HostFeed(torch, dev, [pin_o, pin_d, pin_gt])
+
     def step_e2e(step):
         b = _B()
-        b.rays_ori = pin_o.to(dev, non_blocking=True)
-        b.rays_dir = pin_d.to(dev, non_blocking=True)
-        gt = pin_gt.to(dev, non_blocking=True)
+        b.rays_ori, b.rays_dir, gt = feed.take()
         b.T_to_world = c2ws[view_of(step)].to(dev)
         for g in grads:
             g.grad = None
@@ -316,7 +375,7 @@ def run_grt(args, rank, local_rank, world, dev, dist):
         if world > 1:
             for g in grads:
                 dist.all_reduce(g.grad)
-        return float(loss.item())
+        return feed.give_loss(loss)
 
     e2e_steps = max(5, args.steps // 2)
     for s in range(min(args.warmup, 3)):
@@ -325,6 +384,7 @@ def run_grt(args, rank, local_rank, world, dev, dist):
     t0 = time.perf_counter()
     for s in range(e2e_steps):
         step_e2e(args.warmup + s)
+    feed.drain()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -343,7 +403,8 @@ def run_grt(args, rank, local_rank, world, dev, dist):
                        "step": "build_bvh + trace + trace_bwd", "l2": "flushed between timed steps (256 MiB fill)", "N": n, "P": P_},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                    "api": "threedgrt_tracer.Tracer.build_acc + render + loss.backward"},
+                    "api": "threedgrt_tracer.Tracer.build_acc + render + loss.backward",
+                    "feed": "pinned host -> device on a copy stream, one step ahead; loss read back one step later"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
                          "peak_source": peak_src, "kernel_ms": stage_ms[dom],
@@ -504,11 +565,11 @@ def main():
     c2ws = [torch.from_numpy(np.asarray(sc.camera(i, n_views), np.float32))[None] for i in range(n_views)]
     grads = [_G.positions, _G._d, _G._r, _G._s, _G._f]
 
+    feed = HostFeed(torch, dev, [pin_o, pin_d, pin_gt])
+
     def step_e2e(step):
         b = _B()
-        b.rays_ori = pin_o.to(dev, non_blocking=True)
-        b.rays_dir = pin_d.to(dev, non_blocking=True)
-        gt = pin_gt.to(dev, non_blocking=True)
+        b.rays_ori, b.rays_dir, gt = feed.take()
         b.T_to_world = c2ws[view_of(step)]
         for g in grads:
             g.grad = None
@@ -518,7 +579,7 @@ def main():
         if world > 1:
             for g in grads:
                 dist.all_reduce(g.grad)
-        return float(loss.item())  # D2H read of the step's result
+        return feed.give_loss(loss)  # D2H read of the step's result (pinned slot, consumed one step later)
 
     e2e_steps = max(10, args.steps // 2)
     for s in range(min(args.warmup, 5)):
@@ -527,6 +588,7 @@ def main():
     t0 = time.perf_counter()
     for s in range(e2e_steps):
         step_e2e(args.warmup + s)
+    feed.drain()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
@@ -567,7 +629,8 @@ def main():
                        "N": N_, "V": V_, "I": I_, "T": T_, "P": P_},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                    "api": "threedgut_tracer.Tracer.render + loss.backward"},
+                    "api": "threedgut_tracer.Tracer.render + loss.backward",
+                    "feed": "pinned host -> device on a copy stream, one step ahead; loss read back one step later"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(stage_bytes[dom]),

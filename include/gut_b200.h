@@ -56,6 +56,8 @@ typedef struct gutb200_config {
     int32_t rect_bounding, tight_opacity_bounding, tile_culling;
     int32_t global_z_order;
     int32_t enable_timings;   /* render.enable_kernel_timings (src/splatRaster.cpp:168-169); 2 = also per-stage events */
+    int32_t subtile_culling;  /* ours (no reference twin): exact-conservative sub-tile culling in render/renderBackward; 0 = off.
+                               * Results are bit-identical either way (forward) -- the switch exists for the A/B test. */
 } gutb200_config;
 
 typedef struct gutb200_ctx gutb200_ctx;

@@ -158,6 +158,62 @@ def test_c_abi_host_entry_points_match_device_path():
     ctx.close()
 
 
+def _host_frame(ctx, sc, pose, d_rgba, d_dist):
+    import b200_native as nat
+
+    cam = nat.Camera()
+    cam.width, cam.height = sc.width, sc.height
+    cam.principal[:] = [sc.cx, sc.cy]
+    cam.focal[:] = [sc.fx, sc.fy]
+    cam.pose_start[:] = [float(v) for v in pose]
+    cam.pose_end[:] = [float(v) for v in pose]
+    n, hw = sc.n, sc.width * sc.height
+    rgba, dist, hits, vis = (np.zeros((hw, 4), np.float32), np.zeros(hw, np.float32), np.zeros(hw, np.float32), np.zeros(n, np.float32))
+    p = lambda a: a.ctypes.data  # noqa: E731
+    ro, rd = sc.rays()
+    ro, rd = np.ascontiguousarray(ro), np.ascontiguousarray(rd)
+    ctx.forward_host(cam, n, p(sc.particles), p(sc.sph), sc.sph_degree, p(ro), p(rd), p(rgba), p(dist), p(hits), p(vis))
+    dp, ds = np.zeros((n, 12), np.float32), np.zeros((n, 48), np.float32)
+    ctx.backward_host(cam, n, p(sc.particles), p(sc.sph), sc.sph_degree, p(ro), p(rd), p(rgba), p(d_rgba), p(dist), p(d_dist), p(dp), p(ds))
+    return rgba, dist, hits, dp, ds
+
+
+@pytest.mark.parametrize("scene_name,degree", [("c1", 2), ("c1", 4), ("c2", 2), ("c2", 4), ("c3_small", 2)])
+def test_subtile_culling_is_bit_identical(scene_name, degree):
+    """The conic pre-test of the render kernels (gut_render.cu, ours) only drops (pixel, particle) pairs the exact test
+    would reject: forward outputs must be BIT-identical with the switch on and off, gradients equal up to the order of
+    the atomics.  Covers tiny particles (c1), a dense object (c2, both kernel degrees) and an unbounded scene with
+    large / partly-behind-the-camera particles (c3)."""
+    import b200_native as nat
+
+    if scene_name == "c1":
+        sc = scenes.scene_c1()
+    elif scene_name == "c2":
+        sc = scenes.scene_c2()
+    else:
+        sc = scenes.scene_c3(n=400_000, width=640, height=400)
+    rng = np.random.default_rng(5)
+    hw = sc.width * sc.height
+    d_rgba = rng.normal(size=(hw, 4)).astype(np.float32)
+    d_dist = (0.1 * rng.normal(size=hw)).astype(np.float32)
+    for cam_index in (1, 6):
+        pose = tracer_pose(sc.camera(cam_index, 10))
+        out = []
+        for on in (1, 0):
+            cfg = nat.default_config()
+            cfg.kernel_degree = degree
+            cfg.subtile_culling = 3 * on
+            ctx = nat.Context(cfg, 0)
+            out.append(_host_frame(ctx, sc, pose, d_rgba, d_dist))
+            ctx.close()
+        (rgba1, dist1, hits1, dp1, ds1), (rgba0, dist0, hits0, dp0, ds0) = out
+        assert hits0.sum() > 0
+        assert np.array_equal(hits1, hits0), f"hit counts differ on {(hits1 != hits0).sum()} pixels"
+        assert np.array_equal(rgba1.view(np.uint32), rgba0.view(np.uint32))
+        assert np.array_equal(dist1.view(np.uint32), dist0.view(np.uint32))
+        assert rel_l2(dp1, dp0) <= 1e-5 and rel_l2(ds1, ds0) <= 1e-5
+
+
 def test_empty_and_offscreen_inputs():
     """Edge cases: zero particles, and particles all behind the camera (I = 0)."""
     import b200_native as nat
