@@ -19,6 +19,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -217,6 +218,7 @@ __global__ void single_leaf_kernel(const Box* __restrict__ leaf_boxes, BvhNode* 
 struct TraceParams {
     int n, width, height, batch;   // rays are [batch, height, width, 3]
     int sph_degree;
+    int packet;                    // 1: coherent warps traverse as a packet (GRTB200_PACKET=0 turns it off for A/B runs)
     float min_transmittance, min_response, min_alpha, max_alpha;
     float r2w[12];                 // row-major 3x4
     float scene[6];
@@ -233,12 +235,24 @@ struct TraceParams {
 };
 
 // one k-nearest query == one optixTrace of the reference: the 16 smallest t* in (tmin, tmax) in ascending order
-__device__ __forceinline__ void knn_query(const TraceParams& P, float ox, float oy, float oz, float dx, float dy, float dz, float idx_,
-                                          float idy_, float idz_, float tmin, float tmax, float (&kt)[kK], uint32_t (&kid)[kK]) {
+//
+// PACKET = true: the 32 rays of a warp (an 8x4 pixel block of coherent rays) walk the tree TOGETHER -- one traversal stack with
+// warp-uniform control flow, a subtree is entered when ANY lane's ray needs it, node records are fetched once per warp (uniform
+// address) and every lane keeps its own 16-slot payload and its own cull bound.  Per-ray results are the same as with
+// PACKET = false (each lane still tests exactly the leaves its own ray reaches); what changes is that no lane idles while others
+// traverse (the per-thread walk ran at 8.9 of 32 lanes, profiles/r01_d_grt_c4.md).  Lanes with want == false take part in the votes
+// with an empty ray interval.
+template <bool PACKET>
+__device__ __forceinline__ void knn_query(const TraceParams& P, bool want, float ox, float oy, float oz, float dx, float dy, float dz,
+                                          float idx_, float idy_, float idz_, float tmin, float tmax, float (&kt)[kK], uint32_t (&kid)[kK]) {
 #pragma unroll
     for (int i = 0; i < kK; ++i) {
         kt[i] = kInf;
         kid[i] = kNone;
+    }
+    if (PACKET && !want) {  // empty interval: every slab test of this lane fails
+        tmin = 1.f;
+        tmax = 0.f;
     }
     int stack[kStack];
     int sp = 0;
@@ -267,18 +281,27 @@ __device__ __forceinline__ void knn_query(const TraceParams& P, float ox, float 
         const bool lhit = (lt0 <= lt1) && (lt0 < bound);
         const bool rhit = (rt0 <= rt1) && (rt0 < bound);
         const int lc = __float_as_int(mt.x), rc = __float_as_int(mt.y);
+        bool lany = lhit, rany = rhit, first_is_left = lt0 > rt0;  // push the farther child first
+        if (PACKET) {
+            const unsigned lm = __ballot_sync(0xFFFFFFFFu, lhit), rm = __ballot_sync(0xFFFFFFFFu, rhit);
+            if ((lm | rm) == 0u) continue;
+            lany = lm != 0u;
+            rany = rm != 0u;
+            // order by the majority of the lanes that need both children
+            first_is_left = 2 * __popc(__ballot_sync(0xFFFFFFFFu, lhit && rhit && (lt0 > rt0))) > __popc(lm & rm);
+        }
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
             // visit the nearer child last-pushed (so it is popped first); leaves are tested immediately
-            const bool first_is_left = lt0 > rt0;  // push the farther one first
             const bool is_left = (side == 0) ? first_is_left : !first_is_left;
             const bool hit = is_left ? lhit : rhit;
             const int child = is_left ? lc : rc;
-            if (!hit) continue;
+            if (!(is_left ? lany : rany)) continue;
             if (child >= 0) {
                 if (sp < kStack) stack[sp++] = child;
                 continue;
             }
+            if (!hit) continue;
             const uint32_t pid = static_cast<uint32_t>(~child);
             const float4* pp = reinterpret_cast<const float4*>(P.proxies + pid);
             const float4 a0 = __ldg(pp), a1 = __ldg(pp + 1), a2 = __ldg(pp + 2);
@@ -333,27 +356,11 @@ __device__ __forceinline__ void scene_clip(const float* bb, float ox, float oy, 
     t1 = fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz)));
 }
 
-template <int DEG, bool BWD>
-__global__ void __launch_bounds__(128) trace_kernel(TraceParams P) {
-    // a warp covers an 8x4 pixel block of one image for traversal coherence
-    const int bw = (P.width + 7) / 8, bh = (P.height + 3) / 4;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int per_image = bw * bh;
-    if (warp >= per_image * P.batch) return;
-    const int img = warp / per_image, blk = warp % per_image;
-    const int px = (blk % bw) * 8 + (lane & 7), py = (blk / bw) * 4 + (lane >> 3);
-    if (px >= P.width || py >= P.height) return;
-    const int64_t ray = (static_cast<int64_t>(img) * P.height + py) * P.width + px;
-
-    const float rox = P.rays_o[ray * 3], roy = P.rays_o[ray * 3 + 1], roz = P.rays_o[ray * 3 + 2];
-    const float rdx = P.rays_d[ray * 3], rdy = P.rays_d[ray * 3 + 1], rdz = P.rays_d[ray * 3 + 2];
-    const float* m = P.r2w;  // rayWorldOrigin / rayWorldDirection (pipelineParameters.h:96-114)
-    const float ox = m[0] * rox + m[1] * roy + m[2] * roz + m[3];
-    const float oy = m[4] * rox + m[5] * roy + m[6] * roz + m[7];
-    const float oz = m[8] * rox + m[9] * roy + m[10] * roz + m[11];
-    const float dx = m[0] * rdx + m[1] * rdy + m[2] * rdz;
-    const float dy = m[4] * rdx + m[5] * rdy + m[6] * rdz;
-    const float dz = m[8] * rdx + m[9] * rdy + m[10] * rdz;
+// Per-ray work after the rays are set up.  PACKET: the warp's 32 rays traverse together (warp-uniform loops, every lane of the warp
+// must call this, `valid` marks the lanes that own a ray).
+template <int DEG, bool BWD, bool PACKET>
+__device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int64_t ray, float ox, float oy, float oz, float dx, float dy,
+                                           float dz) {
     const float idx_ = 1.0f / dx, idy_ = 1.0f / dy, idz_ = 1.0f / dz;
 
     float t0, t1;
@@ -367,9 +374,13 @@ __global__ void __launch_bounds__(128) trace_kernel(TraceParams P) {
 
     if (!BWD) {
         float last = fmaxf(0.f, t0 - kEpsT), hits = 0.f;
-        while ((P.n > 0) && (last <= t1) && (T > P.min_transmittance)) {
-            knn_query(P, ox, oy, oz, dx, dy, dz, idx_, idy_, idz_, last + kEpsT, t1 + kEpsT, kt, kid);
-            if (kid[0] == kNone) break;
+        bool want = valid && (P.n > 0);
+        while (true) {
+            want = want && (last <= t1) && (T > P.min_transmittance);
+            if (PACKET ? !__any_sync(0xFFFFFFFFu, want) : !want) break;
+            knn_query<PACKET>(P, want, ox, oy, oz, dx, dy, dz, idx_, idy_, idz_, last + kEpsT, t1 + kEpsT, kt, kid);
+            if (kid[0] == kNone) want = false;
+            if (!want) continue;
             float lt[kK];
             uint32_t li[kK];
 #pragma unroll
@@ -404,13 +415,15 @@ __global__ void __launch_bounds__(128) trace_kernel(TraceParams P) {
                 }
                 last = fmaxf(last, lt[i]);
             }
-            if (li[kK - 1] == kNone) break;  // fewer than 16 hits: the ray is exhausted, the reference's next trace would return nothing
+            if (li[kK - 1] == kNone) want = false;  // fewer than 16 hits: the ray is exhausted, the reference's next trace would return nothing
         }
-        P.out_rgb[ray * 3] = Cx; P.out_rgb[ray * 3 + 1] = Cy; P.out_rgb[ray * 3 + 2] = Cz;
-        P.out_alpha[ray] = 1.f - T;
-        P.out_dist[ray * 2] = D;
-        P.out_dist[ray * 2 + 1] = last;
-        P.out_hits[ray] = hits;
+        if (valid) {
+            P.out_rgb[ray * 3] = Cx; P.out_rgb[ray * 3 + 1] = Cy; P.out_rgb[ray * 3 + 2] = Cz;
+            P.out_alpha[ray] = 1.f - T;
+            P.out_dist[ray * 2] = D;
+            P.out_dist[ray * 2 + 1] = last;
+            P.out_hits[ray] = hits;
+        }
     } else {
         const float Cix = P.out_rgb[ray * 3], Ciy = P.out_rgb[ray * 3 + 1], Ciz = P.out_rgb[ray * 3 + 2];
         const float Tint = 1.0f - P.out_alpha[ray], Dint = P.out_dist[ray * 2], max_hit = P.out_dist[ray * 2 + 1];
@@ -418,9 +431,13 @@ __global__ void __launch_bounds__(128) trace_kernel(TraceParams P) {
         const float Tgrad = -1.0f * P.d_alpha[ray], Dgrad = P.d_dist[ray];
         float start = fmaxf(0.f, t0 - kEpsT);
         const float end = fminf(max_hit, t1) + kEpsT;
-        while ((P.n > 0) && (start < end)) {
-            knn_query(P, ox, oy, oz, dx, dy, dz, idx_, idy_, idz_, start + kEpsT, end, kt, kid);
-            if (kid[0] == kNone) break;
+        bool want = valid && (P.n > 0);
+        while (true) {
+            want = want && (start < end);
+            if (PACKET ? !__any_sync(0xFFFFFFFFu, want) : !want) break;
+            knn_query<PACKET>(P, want, ox, oy, oz, dx, dy, dz, idx_, idy_, idz_, start + kEpsT, end, kt, kid);
+            if (kid[0] == kNone) want = false;
+            if (!want) continue;
             float lt[kK];
             uint32_t li[kK];
 #pragma unroll
@@ -465,10 +482,49 @@ __global__ void __launch_bounds__(128) trace_kernel(TraceParams P) {
                 }
                 start = fmaxf(start, lt[i]);
             }
-            if (li[kK - 1] == kNone) break;
+            if (li[kK - 1] == kNone) want = false;
         }
     }
 }
+
+template <int DEG, bool BWD>
+__global__ void __launch_bounds__(128) trace_kernel(TraceParams P) {
+    // a warp covers an 8x4 pixel block of one image for traversal coherence
+    const int bw = (P.width + 7) / 8, bh = (P.height + 3) / 4;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int per_image = bw * bh;
+    if (warp >= per_image * P.batch) return;  // whole warps only
+    const int img = warp / per_image, blk = warp % per_image;
+    const int px = (blk % bw) * 8 + (lane & 7), py = (blk / bw) * 4 + (lane >> 3);
+    const bool valid = (px < P.width) && (py < P.height);
+    const int64_t ray = (static_cast<int64_t>(img) * P.height + min(py, P.height - 1)) * P.width + min(px, P.width - 1);
+
+    const float rox = P.rays_o[ray * 3], roy = P.rays_o[ray * 3 + 1], roz = P.rays_o[ray * 3 + 2];
+    const float rdx = P.rays_d[ray * 3], rdy = P.rays_d[ray * 3 + 1], rdz = P.rays_d[ray * 3 + 2];
+    const float* m = P.r2w;  // rayWorldOrigin / rayWorldDirection (pipelineParameters.h:96-114)
+    const float ox = m[0] * rox + m[1] * roy + m[2] * roz + m[3];
+    const float oy = m[4] * rox + m[5] * roy + m[6] * roz + m[7];
+    const float oz = m[8] * rox + m[9] * roy + m[10] * roz + m[11];
+    const float dx = m[0] * rdx + m[1] * rdy + m[2] * rdz;
+    const float dy = m[4] * rdx + m[5] * rdy + m[6] * rdz;
+    const float dz = m[8] * rdx + m[9] * rdy + m[10] * rdz;
+
+    // packet traversal pays when the block's rays are coherent: directions within ~6 degrees of lane 0's and origins within 2 % of
+    // the scene diagonal; otherwise every thread walks the tree on its own
+    const float fx = __shfl_sync(0xFFFFFFFFu, dx, 0), fy = __shfl_sync(0xFFFFFFFFu, dy, 0), fz = __shfl_sync(0xFFFFFFFFu, dz, 0);
+    const float gx = __shfl_sync(0xFFFFFFFFu, ox, 0), gy = __shfl_sync(0xFFFFFFFFu, oy, 0), gz = __shfl_sync(0xFFFFFFFFu, oz, 0);
+    const float dot = dx * fx + dy * fy + dz * fz, n1 = dx * dx + dy * dy + dz * dz, n0 = fx * fx + fy * fy + fz * fz;
+    const float ex = P.scene[3] - P.scene[0], ey = P.scene[4] - P.scene[1], ez = P.scene[5] - P.scene[2];
+    const float sx = ox - gx, sy = oy - gy, sz = oz - gz;
+    const bool near_first = (dot > 0.f) && (dot * dot > 0.99f * n1 * n0) && (sx * sx + sy * sy + sz * sz <= 4e-4f * (ex * ex + ey * ey + ez * ez));
+    const bool coherent = P.packet && __all_sync(0xFFFFFFFFu, near_first);
+    if (coherent) {
+        trace_rays<DEG, BWD, true>(P, valid, ray, ox, oy, oz, dx, dy, dz);
+    } else if (valid) {
+        trace_rays<DEG, BWD, false>(P, true, ray, ox, oy, oz, dx, dy, dz);
+    }
+}
+
 
 int fail(grtb200_ctx* c, const char* fmt, ...);
 
@@ -541,6 +597,10 @@ int fill_params(grtb200_ctx* c, TraceParams& P, int64_t n, const float* particle
     P.height = height;
     P.batch = batch;
     P.sph_degree = sph_degree;
+    {
+        const char* e = std::getenv("GRTB200_PACKET");
+        P.packet = (e && e[0] == '0') ? 0 : 1;
+    }
     P.min_transmittance = min_t;
     P.min_response = c->cfg.min_response;
     P.min_alpha = c->cfg.min_alpha;
