@@ -42,6 +42,7 @@ constexpr float kInf = 1e20f;     // RayHit::InfiniteDistance
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr float kEpsT = 1e-9f;
 constexpr int kStack = 64;
+constexpr int kTraceBlocksPerSm = 5;  // caps the trace kernels at 102 registers: 20 warps per SM
 
 struct __align__(16) Proxy {  // rows of A^-1 = diag(1/kscl) R^T with the centre in .w
     float4 a0, a1, a2;
@@ -111,7 +112,11 @@ __device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) morton_kernel(int n, const Proxy* __restrict__ proxies, const int* __restrict__ scene,
+// size_levels > 0: the two top bits of the key are a size class of the proxy (radius relative to the scene diagonal), so the LBVH
+// splits the particles by size first and each class gets its own spatial subtree -- large proxies no longer inflate the boxes of
+// the subtrees that hold the many small ones (the crudest form of the "extended Morton code").
+__global__ void __launch_bounds__(256) morton_kernel(int n, const Proxy* __restrict__ proxies, const Box* __restrict__ boxes,
+                                                     const int* __restrict__ scene, int size_levels, float t0, float t1, float t2,
                                                      uint32_t* __restrict__ codes, uint32_t* __restrict__ ids) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -122,7 +127,13 @@ __global__ void __launch_bounds__(256) morton_kernel(int n, const Proxy* __restr
     const float ux = fminf(fmaxf((p.a0.w - lx) / ex * 1024.f, 0.f), 1023.f);
     const float uy = fminf(fmaxf((p.a1.w - ly) / ey * 1024.f, 0.f), 1023.f);
     const float uz = fminf(fmaxf((p.a2.w - lz) / ez * 1024.f, 0.f), 1023.f);
-    codes[i] = expand_bits(static_cast<uint32_t>(ux)) * 4 + expand_bits(static_cast<uint32_t>(uy)) * 2 + expand_bits(static_cast<uint32_t>(uz));
+    uint32_t cls = 0;
+    if (size_levels > 0) {
+        const float diag = sqrtf(ex * ex + ey * ey + ez * ez);
+        const float rel = boxes[i].lo.w / diag;   // proxy radius / scene diagonal
+        cls = rel < t0 ? 0u : (rel < t1 ? 1u : (rel < t2 ? 2u : 3u));
+    }
+    codes[i] = (cls << 30) | (expand_bits(static_cast<uint32_t>(ux)) * 4 + expand_bits(static_cast<uint32_t>(uy)) * 2 + expand_bits(static_cast<uint32_t>(uz)));
     ids[i] = static_cast<uint32_t>(i);
 }
 
@@ -242,6 +253,51 @@ struct TraceParams {
 // PACKET = false (each lane still tests exactly the leaves its own ray reaches); what changes is that no lane idles while others
 // traverse (the per-thread walk ran at 8.9 of 32 lanes, profiles/r01_d_grt_c4.md).  Lanes with want == false take part in the votes
 // with an empty ray interval.
+// proxy test of one leaf for this lane's ray + insertion into the sorted payload
+__device__ __forceinline__ void leaf_visit(const TraceParams& P, uint32_t pid, float ox, float oy, float oz, float dx, float dy, float dz,
+                                           float tmin, float tmax, float (&kt)[kK], uint32_t (&kid)[kK]) {
+    const float4* pp = reinterpret_cast<const float4*>(P.proxies + pid);
+    const float4 a0 = __ldg(pp), a1 = __ldg(pp + 1), a2 = __ldg(pp + 2);
+    const float vx = ox - a0.w, vy = oy - a1.w, vz = oz - a2.w;
+    const float oix = a0.x * vx + a0.y * vy + a0.z * vz, oiy = a1.x * vx + a1.y * vy + a1.z * vz,
+                oiz = a2.x * vx + a2.y * vy + a2.z * vz;
+    const float dix = a0.x * dx + a0.y * dy + a0.z * dz, diy = a1.x * dx + a1.y * dy + a1.z * dz,
+                diz = a2.x * dx + a2.y * dy + a2.z * dz;
+    // ray segment vs the unit cube of instance space (the custom primitive's AABB)
+    float tin = tmin, tout = tmax, q0, q1;
+    q0 = (-1.f - oix) / dix; q1 = (1.f - oix) / dix;
+    tin = fmaxf(tin, fminf(q0, q1)); tout = fminf(tout, fmaxf(q0, q1));
+    q0 = (-1.f - oiy) / diy; q1 = (1.f - oiy) / diy;
+    tin = fmaxf(tin, fminf(q0, q1)); tout = fminf(tout, fmaxf(q0, q1));
+    q0 = (-1.f - oiz) / diz; q1 = (1.f - oiz) / diz;
+    tin = fmaxf(tin, fminf(q0, q1)); tout = fminf(tout, fmaxf(q0, q1));
+    if (!(tin <= tout)) return;
+    // intersectInstanceParticle (gaussianParticles.cuh:449-465)
+    const float dd = dix * dix + diy * diy + diz * diz;
+    const float den = 1.f / dd;
+    float ht = -(oix * dix + oiy * diy + oiz * diz) * den;
+    if (!((ht > tmin) && (ht < tmax))) return;
+    const float il = dd > 0.f ? rsqrtf(dd) : 1.f;
+    const float n0 = dix * il, n1 = diy * il, n2 = diz * il;
+    const float c0 = n1 * oiz - n2 * oiy, c1 = n2 * oix - n0 * oiz, c2 = n0 * oiy - n1 * oix;
+    if (!((c0 * c0 + c1 * c1 + c2 * c2) * den < 9.f)) return;
+    // __anyhit__ah (referenceOptix.cu:222-248): bubble the hit into the sorted 16-slot payload
+    if (ht < kt[kK - 1]) {
+        uint32_t hid = pid;
+#pragma unroll
+        for (int i = 0; i < kK; ++i) {
+            if (ht < kt[i]) {
+                const float tt = kt[i];
+                const uint32_t ti = kid[i];
+                kt[i] = ht;
+                kid[i] = hid;
+                ht = tt;
+                hid = ti;
+            }
+        }
+    }
+}
+
 template <bool PACKET>
 __device__ __forceinline__ void knn_query(const TraceParams& P, bool want, float ox, float oy, float oz, float dx, float dy, float dz,
                                           float idx_, float idy_, float idz_, float tmin, float tmax, float (&kt)[kK], uint32_t (&kid)[kK]) {
@@ -254,6 +310,10 @@ __device__ __forceinline__ void knn_query(const TraceParams& P, bool want, float
         tmin = 1.f;
         tmax = 0.f;
     }
+    // slab planes as one FMA each: t = plane * (1/d) + (-o/d); `slack` covers the rounding difference to (plane - o) / d, so the
+    // box test stays a superset of the exact proxy test of the leaves
+    const float nox = -ox * idx_, noy = -oy * idy_, noz = -oz * idz_;
+    const float slack = 4e-7f * (fabsf(nox) + fabsf(noy) + fabsf(noz)) + 1e-30f;
     int stack[kStack];
     int sp = 0;
     stack[sp++] = 0;
@@ -263,87 +323,44 @@ __device__ __forceinline__ void knn_query(const TraceParams& P, bool want, float
         const float4 b0 = __ldg(np), b1 = __ldg(np + 1), b2 = __ldg(np + 2), mt = __ldg(np + 3);
         const float bound = kt[kK - 1];  // kInf until 16 hits are held
         // slab tests of both children against [tmin, tmax]
-        float l0 = (b0.x - ox) * idx_, l1 = (b0.w - ox) * idx_;
+        float l0 = fmaf(b0.x, idx_, nox), l1 = fmaf(b0.w, idx_, nox);
         float lt0 = fminf(l0, l1), lt1 = fmaxf(l0, l1);
-        l0 = (b0.y - oy) * idy_; l1 = (b1.x - oy) * idy_;
+        l0 = fmaf(b0.y, idy_, noy); l1 = fmaf(b1.x, idy_, noy);
         lt0 = fmaxf(lt0, fminf(l0, l1)); lt1 = fminf(lt1, fmaxf(l0, l1));
-        l0 = (b0.z - oz) * idz_; l1 = (b1.y - oz) * idz_;
+        l0 = fmaf(b0.z, idz_, noz); l1 = fmaf(b1.y, idz_, noz);
         lt0 = fmaxf(lt0, fminf(l0, l1)); lt1 = fminf(lt1, fmaxf(l0, l1));
         lt0 = fmaxf(lt0, tmin); lt1 = fminf(lt1, tmax);
-        float r0 = (b1.z - ox) * idx_, r1 = (b2.y - ox) * idx_;
+        float r0 = fmaf(b1.z, idx_, nox), r1 = fmaf(b2.y, idx_, nox);
         float rt0 = fminf(r0, r1), rt1 = fmaxf(r0, r1);
-        r0 = (b1.w - oy) * idy_; r1 = (b2.z - oy) * idy_;
+        r0 = fmaf(b1.w, idy_, noy); r1 = fmaf(b2.z, idy_, noy);
         rt0 = fmaxf(rt0, fminf(r0, r1)); rt1 = fminf(rt1, fmaxf(r0, r1));
-        r0 = (b2.x - oz) * idz_; r1 = (b2.w - oz) * idz_;
+        r0 = fmaf(b2.x, idz_, noz); r1 = fmaf(b2.w, idz_, noz);
         rt0 = fmaxf(rt0, fminf(r0, r1)); rt1 = fminf(rt1, fmaxf(r0, r1));
         rt0 = fmaxf(rt0, tmin); rt1 = fminf(rt1, tmax);
         // like OptiX, cull a subtree whose box is entered beyond the current 16th hit (ray tmax shrinks to it)
-        const bool lhit = (lt0 <= lt1) && (lt0 < bound);
-        const bool rhit = (rt0 <= rt1) && (rt0 < bound);
+        const bool lhit = (lt0 <= lt1 + slack) && (lt0 < bound);
+        const bool rhit = (rt0 <= rt1 + slack) && (rt0 < bound);
         const int lc = __float_as_int(mt.x), rc = __float_as_int(mt.y);
-        bool lany = lhit, rany = rhit, first_is_left = lt0 > rt0;  // push the farther child first
-        if (PACKET) {
-            const unsigned lm = __ballot_sync(0xFFFFFFFFu, lhit), rm = __ballot_sync(0xFFFFFFFFu, rhit);
-            if ((lm | rm) == 0u) continue;
-            lany = lm != 0u;
-            rany = rm != 0u;
-            // order by the majority of the lanes that need both children
-            first_is_left = 2 * __popc(__ballot_sync(0xFFFFFFFFu, lhit && rhit && (lt0 > rt0))) > __popc(lm & rm);
+        bool lpush = lhit && (lc >= 0), rpush = rhit && (rc >= 0);
+        if (PACKET) {  // a subtree is entered when ANY lane needs it
+            lpush = (lc >= 0) && __any_sync(0xFFFFFFFFu, lhit);
+            rpush = (rc >= 0) && __any_sync(0xFFFFFFFFu, rhit);
         }
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            // visit the nearer child last-pushed (so it is popped first); leaves are tested immediately
-            const bool is_left = (side == 0) ? first_is_left : !first_is_left;
-            const bool hit = is_left ? lhit : rhit;
-            const int child = is_left ? lc : rc;
-            if (!(is_left ? lany : rany)) continue;
-            if (child >= 0) {
-                if (sp < kStack) stack[sp++] = child;
-                continue;
+        if (lpush && rpush) {
+            // nearer child on top of the stack; a packet follows the majority of the lanes that need both
+            bool left_far = lt0 > rt0;
+            if (PACKET) left_far = 2 * __popc(__ballot_sync(0xFFFFFFFFu, lhit && rhit && (lt0 > rt0))) > __popc(__ballot_sync(0xFFFFFFFFu, lhit && rhit));
+            if (sp + 1 < kStack) {
+                stack[sp] = left_far ? lc : rc;
+                stack[sp + 1] = left_far ? rc : lc;
+                sp += 2;
             }
-            if (!hit) continue;
-            const uint32_t pid = static_cast<uint32_t>(~child);
-            const float4* pp = reinterpret_cast<const float4*>(P.proxies + pid);
-            const float4 a0 = __ldg(pp), a1 = __ldg(pp + 1), a2 = __ldg(pp + 2);
-            const float vx = ox - a0.w, vy = oy - a1.w, vz = oz - a2.w;
-            const float oix = a0.x * vx + a0.y * vy + a0.z * vz, oiy = a1.x * vx + a1.y * vy + a1.z * vz,
-                        oiz = a2.x * vx + a2.y * vy + a2.z * vz;
-            const float dix = a0.x * dx + a0.y * dy + a0.z * dz, diy = a1.x * dx + a1.y * dy + a1.z * dz,
-                        diz = a2.x * dx + a2.y * dy + a2.z * dz;
-            // ray segment vs the unit cube of instance space (the custom primitive's AABB)
-            float tin = tmin, tout = tmax, q0, q1;
-            q0 = (-1.f - oix) / dix; q1 = (1.f - oix) / dix;
-            tin = fmaxf(tin, fminf(q0, q1)); tout = fminf(tout, fmaxf(q0, q1));
-            q0 = (-1.f - oiy) / diy; q1 = (1.f - oiy) / diy;
-            tin = fmaxf(tin, fminf(q0, q1)); tout = fminf(tout, fmaxf(q0, q1));
-            q0 = (-1.f - oiz) / diz; q1 = (1.f - oiz) / diz;
-            tin = fmaxf(tin, fminf(q0, q1)); tout = fminf(tout, fmaxf(q0, q1));
-            if (!(tin <= tout)) continue;
-            // intersectInstanceParticle (gaussianParticles.cuh:449-465)
-            const float dd = dix * dix + diy * diy + diz * diz;
-            const float den = 1.f / dd;
-            float ht = -(oix * dix + oiy * diy + oiz * diz) * den;
-            if (!((ht > tmin) && (ht < tmax))) continue;
-            const float il = dd > 0.f ? rsqrtf(dd) : 1.f;
-            const float n0 = dix * il, n1 = diy * il, n2 = diz * il;
-            const float c0 = n1 * oiz - n2 * oiy, c1 = n2 * oix - n0 * oiz, c2 = n0 * oiy - n1 * oix;
-            if (!((c0 * c0 + c1 * c1 + c2 * c2) * den < 9.f)) continue;
-            // __anyhit__ah (referenceOptix.cu:222-248): bubble the hit into the sorted 16-slot payload
-            if (ht < kt[kK - 1]) {
-                uint32_t hid = pid;
-#pragma unroll
-                for (int i = 0; i < kK; ++i) {
-                    if (ht < kt[i]) {
-                        const float tt = kt[i];
-                        const uint32_t ti = kid[i];
-                        kt[i] = ht;
-                        kid[i] = hid;
-                        ht = tt;
-                        hid = ti;
-                    }
-                }
-            }
+        } else if (lpush || rpush) {
+            if (sp < kStack) stack[sp++] = lpush ? lc : rc;
         }
+        // leaves are tested immediately, by the lanes whose ray reaches them
+        if ((lc < 0) && lhit) leaf_visit(P, static_cast<uint32_t>(~lc), ox, oy, oz, dx, dy, dz, tmin, tmax, kt, kid);
+        if ((rc < 0) && rhit) leaf_visit(P, static_cast<uint32_t>(~rc), ox, oy, oz, dx, dy, dz, tmin, tmax, kt, kid);
     }
 }
 
@@ -365,8 +382,6 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
 
     float t0, t1;
     scene_clip(P.scene, ox, oy, oz, idx_, idy_, idz_, t0, t1);
-    float basis[16];
-    sh_basis16(P.sph_degree, dx, dy, dz, basis);
 
     float kt[kK];
     uint32_t kid[kK];
@@ -385,6 +400,8 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
             uint32_t li[kK];
 #pragma unroll
             for (int i = 0; i < kK; ++i) { lt[i] = kt[i]; li[i] = kid[i]; }
+            float basis[16];  // recomputed per chunk: 16 registers less across the traversal
+            sh_basis16(P.sph_degree, dx, dy, dz, basis);
 #pragma unroll 1
             for (int i = 0; i < kK; ++i) {
                 const uint32_t pid = li[i];
@@ -442,6 +459,8 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
             uint32_t li[kK];
 #pragma unroll
             for (int i = 0; i < kK; ++i) { lt[i] = kt[i]; li[i] = kid[i]; }
+            float basis[16];  // recomputed per chunk: 16 registers less across the traversal
+            sh_basis16(P.sph_degree, dx, dy, dz, basis);
 #pragma unroll 1
             for (int i = 0; i < kK; ++i) {
                 const uint32_t pid = li[i];
@@ -466,18 +485,26 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
                     float gr[11], rg[3];
                     hit_adjoint<DEG>(f, h, dx, dy, dz, fmaxf(r, 0.f), fmaxf(g, 0.f), fmaxf(b, 0.f), P.min_transmittance, Tint, Tgrad, Cix,
                                      Ciy, Ciz, Cgx, Cgy, Cgz, Dint, Dgrad, T, Cx, Cy, Cz, D, gr, rg);
-                    float* dp = P.d_particles + static_cast<size_t>(pid) * 12;
-#pragma unroll
-                    for (int q = 0; q < 11; ++q) atomicAdd(dp + q, gr[q]);
+                    // 16-byte vector reductions (red.global.add.v4.f32): 3 + 12 instead of 11 + 48 scalar atomics per hit
+                    float4* dp = reinterpret_cast<float4*>(P.d_particles + static_cast<size_t>(pid) * 12);
+                    atomicAdd(dp, make_float4(gr[0], gr[1], gr[2], gr[3]));
+                    atomicAdd(dp + 1, make_float4(gr[4], gr[5], gr[6], gr[7]));
+                    atomicAdd(dp + 2, make_float4(gr[8], gr[9], gr[10], 0.f));
                     // radianceFromSpHBwd<true> (gaussianParticles.cuh:101-177): clamp mask on the unclamped radiance
                     const float mr = r > 0.f ? rg[0] : 0.f, mg = g > 0.f ? rg[1] : 0.f, mb = b > 0.f ? rg[2] : 0.f;
-                    float* ds = P.d_sph + static_cast<size_t>(pid) * 48;
+                    float4* ds = reinterpret_cast<float4*>(P.d_sph + static_cast<size_t>(pid) * 48);
                     const int ncoef = (P.sph_degree + 1) * (P.sph_degree + 1);
-#pragma unroll 1
-                    for (int j = 0; j < ncoef; ++j) {
-                        atomicAdd(ds + j * 3, basis[j] * mr);
-                        atomicAdd(ds + j * 3 + 1, basis[j] * mg);
-                        atomicAdd(ds + j * 3 + 2, basis[j] * mb);
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) {
+                        if (k * 4 < ncoef * 3) {  // the basis is zero beyond the active degree
+                            float e[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int flat = k * 4 + q, j = flat / 3, c = flat % 3;
+                                e[q] = basis[j] * (c == 0 ? mr : (c == 1 ? mg : mb));
+                            }
+                            atomicAdd(ds + k, make_float4(e[0], e[1], e[2], e[3]));
+                        }
                     }
                 }
                 start = fmaxf(start, lt[i]);
@@ -488,7 +515,7 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
 }
 
 template <int DEG, bool BWD>
-__global__ void __launch_bounds__(128) trace_kernel(TraceParams P) {
+__global__ void __launch_bounds__(128, kTraceBlocksPerSm) trace_kernel(TraceParams P) {
     // a warp covers an 8x4 pixel block of one image for traversal coherence
     const int bw = (P.width + 7) / 8, bh = (P.height + 3) / 4;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -714,10 +741,21 @@ int grtb200_build_bvh(grtb200_ctx* c, void* stream, int64_t n, const float* pos,
         single_leaf_kernel<<<1, 1, 0, s>>>(static_cast<const Box*>(c->leaf_boxes), static_cast<BvhNode*>(c->nodes));
         c->launches++;
     } else {
-        morton_kernel<<<blocks, 256, 0, s>>>(ni, static_cast<const Proxy*>(c->proxies), static_cast<const int*>(c->scene),
+        int size_levels = 1;
+        float th[3] = {1.f / 48.f, 3e38f, 3e38f};  // proxy radius / scene diagonal; classes above the last finite threshold stay empty
+        if (const char* e = std::getenv("GRTB200_SIZE_LEVELS")) size_levels = std::atoi(e);  // A/B switches for profiling
+        if (const char* e = std::getenv("GRTB200_SIZE_T")) {
+            float a = 0.f, b = 0.f, d = 0.f;
+            const int got = std::sscanf(e, "%f,%f,%f", &a, &b, &d);
+            th[0] = got >= 1 && a > 0.f ? 1.f / a : 3e38f;
+            th[1] = got >= 2 && b > 0.f ? 1.f / b : 3e38f;
+            th[2] = got >= 3 && d > 0.f ? 1.f / d : 3e38f;
+        }
+        morton_kernel<<<blocks, 256, 0, s>>>(ni, static_cast<const Proxy*>(c->proxies), static_cast<const Box*>(c->leaf_boxes),
+                                             static_cast<const int*>(c->scene), size_levels, th[0], th[1], th[2],
                                              static_cast<uint32_t*>(c->codes), static_cast<uint32_t*>(c->ids));
         run_sort32_pairs(s, c->sort_temp, c->sort_temp_bytes, static_cast<const uint32_t*>(c->codes), static_cast<uint32_t*>(c->codes_sorted),
-                         static_cast<const uint32_t*>(c->ids), static_cast<uint32_t*>(c->ids_sorted), n, 30);
+                         static_cast<const uint32_t*>(c->ids), static_cast<uint32_t*>(c->ids_sorted), n, 32);
         GRT_CUDA(c, cudaMemsetAsync(c->flags, 0, static_cast<size_t>(n) * 4, s));
         hierarchy_kernel<<<blocks, 256, 0, s>>>(ni, static_cast<const uint32_t*>(c->codes_sorted), static_cast<const uint32_t*>(c->ids_sorted),
                                                 static_cast<int2*>(c->children), static_cast<int*>(c->parent), static_cast<int*>(c->leaf_parent));
