@@ -17,6 +17,7 @@
 // culled, which is what OptiX does when the any-hit program shrinks the ray's tmax.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -47,11 +48,15 @@ constexpr int kTraceBlocksPerSm = 5;  // caps the trace kernels at 102 registers
 struct __align__(16) Proxy {  // rows of A^-1 = diag(1/kscl) R^T with the centre in .w
     float4 a0, a1, a2;
 };
+struct __align__(16) LeafProxy {  // proxy in leaf (sorted) order: 64 B, the particles of one leaf are contiguous
+    float4 a0, a1, a2;
+    uint32_t pid, pad0, pad1, pad2;
+};
 struct __align__(16) BvhNode {
     float4 b0;    // lmin.xyz, lmax.x
     float4 b1;    // lmax.yz, rmin.xy
     float4 b2;    // rmin.z, rmax.xyz
-    float4 meta;  // left, right (int bits: >=0 internal, <0 leaf ~particle), left slack, right slack
+    float4 meta;  // left, right (int bits: >=0 internal, <0 leaf ~leaf index), left slack, right slack
 };
 struct __align__(16) Box {
     float4 lo;  // min.xyz, slack (largest proxy half-diagonal below)
@@ -135,6 +140,37 @@ __global__ void __launch_bounds__(256) morton_kernel(int n, const Proxy* __restr
     }
     codes[i] = (cls << 30) | (expand_bits(static_cast<uint32_t>(ux)) * 4 + expand_bits(static_cast<uint32_t>(uy)) * 2 + expand_bits(static_cast<uint32_t>(uz)));
     ids[i] = static_cast<uint32_t>(i);
+}
+
+// Leaves hold up to `leaf` consecutive particles of the sorted order: one thread per leaf writes the leaf's key (its first particle's),
+// its box (union) and the particles' proxies in leaf order.  Fewer, fatter leaves remove the bottom levels of the tree, where most
+// node visits happen; the particles of a leaf are tested back to back from one 64*leaf-byte record.
+__global__ void __launch_bounds__(256) leaf_kernel(int n, int leaf, const uint32_t* __restrict__ codes_sorted,
+                                                   const uint32_t* __restrict__ ids_sorted, const Proxy* __restrict__ proxies,
+                                                   const Box* __restrict__ boxes, uint32_t* __restrict__ leaf_codes,
+                                                   uint32_t* __restrict__ leaf_ids, Box* __restrict__ leaf_boxes,
+                                                   LeafProxy* __restrict__ leaf_proxies) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int first = g * leaf;
+    if (first >= n) return;
+    const int last = min(first + leaf, n);
+    Box u;
+    u.lo = make_float4(3e38f, 3e38f, 3e38f, 0.f);
+    u.hi = make_float4(-3e38f, -3e38f, -3e38f, 0.f);
+    for (int k = first; k < last; ++k) {
+        const uint32_t pid = ids_sorted[k];
+        const Box b = boxes[pid];
+        u.lo = make_float4(fminf(u.lo.x, b.lo.x), fminf(u.lo.y, b.lo.y), fminf(u.lo.z, b.lo.z), fmaxf(u.lo.w, b.lo.w));
+        u.hi = make_float4(fmaxf(u.hi.x, b.hi.x), fmaxf(u.hi.y, b.hi.y), fmaxf(u.hi.z, b.hi.z), 0.f);
+        const Proxy p = proxies[pid];
+        LeafProxy q;
+        q.a0 = p.a0; q.a1 = p.a1; q.a2 = p.a2;
+        q.pid = pid; q.pad0 = q.pad1 = q.pad2 = 0u;
+        leaf_proxies[k] = q;
+    }
+    leaf_codes[g] = codes_sorted[first];
+    leaf_ids[g] = static_cast<uint32_t>(g);
+    leaf_boxes[g] = u;
 }
 
 // common-prefix length of sorted keys i and j (index as tie breaker); -1 outside the range
@@ -237,8 +273,9 @@ struct TraceParams {
     const float* sph;
     const float* rays_o;
     const float* rays_d;
-    const Proxy* proxies;
+    const LeafProxy* proxies;      // leaf order
     const BvhNode* nodes;
+    int leaf;                      // particles per leaf
     // forward outputs / backward inputs
     float* out_rgb; float* out_alpha; float* out_dist; float* out_hits; float* visibility;
     const float* d_rgb; const float* d_alpha; const float* d_dist;
@@ -254,9 +291,9 @@ struct TraceParams {
 // traverse (the per-thread walk ran at 8.9 of 32 lanes, profiles/r01_d_grt_c4.md).  Lanes with want == false take part in the votes
 // with an empty ray interval.
 // proxy test of one leaf for this lane's ray + insertion into the sorted payload
-__device__ __forceinline__ void leaf_visit(const TraceParams& P, uint32_t pid, float ox, float oy, float oz, float dx, float dy, float dz,
-                                           float tmin, float tmax, float (&kt)[kK], uint32_t (&kid)[kK]) {
-    const float4* pp = reinterpret_cast<const float4*>(P.proxies + pid);
+__device__ __forceinline__ void proxy_visit(const LeafProxy* __restrict__ lp, float ox, float oy, float oz, float dx, float dy, float dz,
+                                            float tmin, float tmax, float (&kt)[kK], uint32_t (&kid)[kK]) {
+    const float4* pp = reinterpret_cast<const float4*>(lp);
     const float4 a0 = __ldg(pp), a1 = __ldg(pp + 1), a2 = __ldg(pp + 2);
     const float vx = ox - a0.w, vy = oy - a1.w, vz = oz - a2.w;
     const float oix = a0.x * vx + a0.y * vy + a0.z * vz, oiy = a1.x * vx + a1.y * vy + a1.z * vz,
@@ -283,7 +320,7 @@ __device__ __forceinline__ void leaf_visit(const TraceParams& P, uint32_t pid, f
     if (!((c0 * c0 + c1 * c1 + c2 * c2) * den < 9.f)) return;
     // __anyhit__ah (referenceOptix.cu:222-248): bubble the hit into the sorted 16-slot payload
     if (ht < kt[kK - 1]) {
-        uint32_t hid = pid;
+        uint32_t hid = __ldg(&lp->pid);
 #pragma unroll
         for (int i = 0; i < kK; ++i) {
             if (ht < kt[i]) {
@@ -296,6 +333,14 @@ __device__ __forceinline__ void leaf_visit(const TraceParams& P, uint32_t pid, f
             }
         }
     }
+}
+
+// all particles of leaf g for this lane's ray
+__device__ __forceinline__ void leaf_visit(const TraceParams& P, uint32_t g, float ox, float oy, float oz, float dx, float dy, float dz,
+                                           float tmin, float tmax, float (&kt)[kK], uint32_t (&kid)[kK]) {
+    const int first = static_cast<int>(g) * P.leaf, last = min(first + P.leaf, P.n);
+#pragma unroll 1
+    for (int k = first; k < last; ++k) proxy_visit(P.proxies + k, ox, oy, oz, dx, dy, dz, tmin, tmax, kt, kid);
 }
 
 template <bool PACKET>
@@ -566,8 +611,9 @@ struct grtb200_ctx {
     cudaStream_t build_stream = nullptr;
     void *proxies = nullptr, *leaf_boxes = nullptr, *node_boxes = nullptr, *nodes = nullptr, *codes = nullptr, *ids = nullptr,
          *codes_sorted = nullptr, *ids_sorted = nullptr, *children = nullptr, *parent = nullptr, *leaf_parent = nullptr, *flags = nullptr,
-         *scene = nullptr, *sort_temp = nullptr;
+         *scene = nullptr, *sort_temp = nullptr, *grp_codes = nullptr, *grp_ids = nullptr, *grp_boxes = nullptr, *grp_proxies = nullptr;
     size_t cap = 0, sort_temp_bytes = 0;
+    int leaf = 2;   // particles per leaf of the last build
     float scene_host[6] = {0, 0, 0, 0, 0, 0};
     bool scene_valid = false;
 };
@@ -592,7 +638,8 @@ int fail(grtb200_ctx* c, const char* fmt, ...) {
 
 void release(grtb200_ctx* c) {
     void** ptrs[] = {&c->proxies, &c->leaf_boxes, &c->node_boxes, &c->nodes, &c->codes, &c->ids, &c->codes_sorted, &c->ids_sorted,
-                     &c->children, &c->parent, &c->leaf_parent, &c->flags, &c->sort_temp};
+                     &c->children, &c->parent, &c->leaf_parent, &c->flags, &c->sort_temp, &c->grp_codes, &c->grp_ids, &c->grp_boxes,
+                     &c->grp_proxies};
     for (void** p : ptrs) {
         if (*p) cudaFree(*p);
         *p = nullptr;
@@ -638,7 +685,8 @@ int fill_params(grtb200_ctx* c, TraceParams& P, int64_t n, const float* particle
     P.sph = sph;
     P.rays_o = rays_o;
     P.rays_d = rays_d;
-    P.proxies = static_cast<const Proxy*>(c->proxies);
+    P.proxies = static_cast<const LeafProxy*>(c->grp_proxies);
+    P.leaf = c->leaf;
     P.nodes = static_cast<const BvhNode*>(c->nodes);
     return 0;
 }
@@ -725,6 +773,10 @@ int grtb200_build_bvh(grtb200_ctx* c, void* stream, int64_t n, const float* pos,
         GRT_CUDA(c, cudaMalloc(&c->parent, cap * 4));
         GRT_CUDA(c, cudaMalloc(&c->leaf_parent, cap * 4));
         GRT_CUDA(c, cudaMalloc(&c->flags, cap * 4));
+        GRT_CUDA(c, cudaMalloc(&c->grp_codes, cap * 4));
+        GRT_CUDA(c, cudaMalloc(&c->grp_ids, cap * 4));
+        GRT_CUDA(c, cudaMalloc(&c->grp_boxes, cap * sizeof(Box)));
+        GRT_CUDA(c, cudaMalloc(&c->grp_proxies, cap * sizeof(LeafProxy)));
         c->sort_temp_bytes = sort32_temp_bytes(static_cast<int64_t>(cap)) + 16;
         GRT_CUDA(c, cudaMalloc(&c->sort_temp, c->sort_temp_bytes));
         c->cap = cap;
@@ -737,12 +789,10 @@ int grtb200_build_bvh(grtb200_ctx* c, void* stream, int64_t n, const float* pos,
     proxy_kernel<<<blocks, 256, 0, s>>>(ni, pos, rot, scl, dns, c->cfg.min_response, c->cfg.density_clamping, static_cast<float>(c->cfg.kernel_degree),
                                         static_cast<Proxy*>(c->proxies), static_cast<Box*>(c->leaf_boxes), static_cast<int*>(c->scene));
     c->launches++;
-    if (n == 1) {
-        single_leaf_kernel<<<1, 1, 0, s>>>(static_cast<const Box*>(c->leaf_boxes), static_cast<BvhNode*>(c->nodes));
-        c->launches++;
-    } else {
+    {
         int size_levels = 1;
         float th[3] = {1.f / 48.f, 3e38f, 3e38f};  // proxy radius / scene diagonal; classes above the last finite threshold stay empty
+        int leaf = 2;  // measured at C4: 1 -> 83, 2 -> 87, 4 -> 84, 8 -> 75 frames/s (scripts/grt_leaf_sweep.sh)
         if (const char* e = std::getenv("GRTB200_SIZE_LEVELS")) size_levels = std::atoi(e);  // A/B switches for profiling
         if (const char* e = std::getenv("GRTB200_SIZE_T")) {
             float a = 0.f, b = 0.f, d = 0.f;
@@ -751,18 +801,33 @@ int grtb200_build_bvh(grtb200_ctx* c, void* stream, int64_t n, const float* pos,
             th[1] = got >= 2 && b > 0.f ? 1.f / b : 3e38f;
             th[2] = got >= 3 && d > 0.f ? 1.f / d : 3e38f;
         }
+        if (const char* e = std::getenv("GRTB200_LEAF")) leaf = std::max(1, std::min(16, std::atoi(e)));
+        c->leaf = leaf;
+        const int ng = (ni + leaf - 1) / leaf;
+        const unsigned gblocks = (ng + 255) / 256;
         morton_kernel<<<blocks, 256, 0, s>>>(ni, static_cast<const Proxy*>(c->proxies), static_cast<const Box*>(c->leaf_boxes),
                                              static_cast<const int*>(c->scene), size_levels, th[0], th[1], th[2],
                                              static_cast<uint32_t*>(c->codes), static_cast<uint32_t*>(c->ids));
         run_sort32_pairs(s, c->sort_temp, c->sort_temp_bytes, static_cast<const uint32_t*>(c->codes), static_cast<uint32_t*>(c->codes_sorted),
                          static_cast<const uint32_t*>(c->ids), static_cast<uint32_t*>(c->ids_sorted), n, 32);
-        GRT_CUDA(c, cudaMemsetAsync(c->flags, 0, static_cast<size_t>(n) * 4, s));
-        hierarchy_kernel<<<blocks, 256, 0, s>>>(ni, static_cast<const uint32_t*>(c->codes_sorted), static_cast<const uint32_t*>(c->ids_sorted),
-                                                static_cast<int2*>(c->children), static_cast<int*>(c->parent), static_cast<int*>(c->leaf_parent));
-        refit_kernel<<<blocks, 256, 0, s>>>(ni, static_cast<const int2*>(c->children), static_cast<const int*>(c->parent),
-                                            static_cast<const int*>(c->leaf_parent), static_cast<const Box*>(c->leaf_boxes),
-                                            static_cast<Box*>(c->node_boxes), static_cast<int*>(c->flags), static_cast<BvhNode*>(c->nodes));
-        c->launches += 3;
+        leaf_kernel<<<gblocks, 256, 0, s>>>(ni, leaf, static_cast<const uint32_t*>(c->codes_sorted), static_cast<const uint32_t*>(c->ids_sorted),
+                                            static_cast<const Proxy*>(c->proxies), static_cast<const Box*>(c->leaf_boxes),
+                                            static_cast<uint32_t*>(c->grp_codes), static_cast<uint32_t*>(c->grp_ids),
+                                            static_cast<Box*>(c->grp_boxes), static_cast<LeafProxy*>(c->grp_proxies));
+        c->launches += 2;
+        if (ng == 1) {
+            single_leaf_kernel<<<1, 1, 0, s>>>(static_cast<const Box*>(c->grp_boxes), static_cast<BvhNode*>(c->nodes));
+            c->launches++;
+        } else {
+            GRT_CUDA(c, cudaMemsetAsync(c->flags, 0, static_cast<size_t>(ng) * 4, s));
+            hierarchy_kernel<<<gblocks, 256, 0, s>>>(ng, static_cast<const uint32_t*>(c->grp_codes), static_cast<const uint32_t*>(c->grp_ids),
+                                                     static_cast<int2*>(c->children), static_cast<int*>(c->parent),
+                                                     static_cast<int*>(c->leaf_parent));
+            refit_kernel<<<gblocks, 256, 0, s>>>(ng, static_cast<const int2*>(c->children), static_cast<const int*>(c->parent),
+                                                 static_cast<const int*>(c->leaf_parent), static_cast<const Box*>(c->grp_boxes),
+                                                 static_cast<Box*>(c->node_boxes), static_cast<int*>(c->flags), static_cast<BvhNode*>(c->nodes));
+            c->launches += 2;
+        }
     }
     GRT_CUDA(c, cudaGetLastError());
     return 0;
