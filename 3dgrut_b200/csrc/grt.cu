@@ -276,6 +276,12 @@ struct TraceParams {
     const LeafProxy* proxies;      // leaf order
     const BvhNode* nodes;
     int leaf;                      // particles per leaf
+    // hit-list cache (ours): the forward records each ray's accepted hits, the backward replays them instead of re-tracing
+    uint32_t* hit_list;            // [hit_cap][rays] particle ids (coalesced across the rays of a warp); nullptr = off
+    uint32_t* hit_count;           // [rays] number of hits the backward must visit; kNone = more than hit_cap, re-trace this ray
+    int hit_cap;
+    int64_t rays;
+    int only_overflow;             // backward re-trace launch: handle only the rays whose list overflowed
     // forward outputs / backward inputs
     float* out_rgb; float* out_alpha; float* out_dist; float* out_hits; float* visibility;
     const float* d_rgb; const float* d_alpha; const float* d_dist;
@@ -418,6 +424,55 @@ __device__ __forceinline__ void scene_clip(const float* bb, float ox, float oy, 
     t1 = fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz)));
 }
 
+// adjoint of one candidate hit of a ray: re-evaluates the accept test, the radiance, processHitBwd, and scatters the gradients
+template <int DEG>
+__device__ __forceinline__ void backward_hit(const TraceParams& P, uint32_t pid, float ox, float oy, float oz, float dx, float dy, float dz,
+                                             const float (&basis)[16], float Tint, float Tgrad, float Cix, float Ciy, float Ciz, float Cgx,
+                                             float Cgy, float Cgz, float Dint, float Dgrad, float& T, float& Cx, float& Cy, float& Cz, float& D) {
+    const ParticleFrame f = load_frame(P.particles, pid);
+    const CanonicalHit h = canonical_hit<DEG>(f, ox, oy, oz, dx, dy, dz, P.min_response, P.min_alpha, P.max_alpha);
+    if (h.accept) {
+        const float4* c4 = reinterpret_cast<const float4*>(P.sph + static_cast<size_t>(pid) * 48);
+        float r = 0.5f, g = 0.5f, b = 0.5f;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const float4 v = __ldg(c4 + k);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int flat = k * 4 + q, j = flat / 3, c = flat % 3;
+                if (c == 0) r += basis[j] * e[q];
+                if (c == 1) g += basis[j] * e[q];
+                if (c == 2) b += basis[j] * e[q];
+            }
+        }
+        float gr[11], rg[3];
+        hit_adjoint<DEG>(f, h, dx, dy, dz, fmaxf(r, 0.f), fmaxf(g, 0.f), fmaxf(b, 0.f), P.min_transmittance, Tint, Tgrad, Cix,
+                         Ciy, Ciz, Cgx, Cgy, Cgz, Dint, Dgrad, T, Cx, Cy, Cz, D, gr, rg);
+        // 16-byte vector reductions (red.global.add.v4.f32): 3 + 12 instead of 11 + 48 scalar atomics per hit
+        float4* dp = reinterpret_cast<float4*>(P.d_particles + static_cast<size_t>(pid) * 12);
+        atomicAdd(dp, make_float4(gr[0], gr[1], gr[2], gr[3]));
+        atomicAdd(dp + 1, make_float4(gr[4], gr[5], gr[6], gr[7]));
+        atomicAdd(dp + 2, make_float4(gr[8], gr[9], gr[10], 0.f));
+        // radianceFromSpHBwd<true> (gaussianParticles.cuh:101-177): clamp mask on the unclamped radiance
+        const float mr = r > 0.f ? rg[0] : 0.f, mg = g > 0.f ? rg[1] : 0.f, mb = b > 0.f ? rg[2] : 0.f;
+        float4* ds = reinterpret_cast<float4*>(P.d_sph + static_cast<size_t>(pid) * 48);
+        const int ncoef = (P.sph_degree + 1) * (P.sph_degree + 1);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            if (k * 4 < ncoef * 3) {  // the basis is zero beyond the active degree
+                float e[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int flat = k * 4 + q, j = flat / 3, c = flat % 3;
+                    e[q] = basis[j] * (c == 0 ? mr : (c == 1 ? mg : mb));
+                }
+                atomicAdd(ds + k, make_float4(e[0], e[1], e[2], e[3]));
+            }
+        }
+    }
+}
+
 // Per-ray work after the rays are set up.  PACKET: the warp's 32 rays traverse together (warp-uniform loops, every lane of the warp
 // must call this, `valid` marks the lanes that own a ray).
 template <int DEG, bool BWD, bool PACKET>
@@ -435,6 +490,8 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
     if (!BWD) {
         float last = fmaxf(0.f, t0 - kEpsT), hits = 0.f;
         bool want = valid && (P.n > 0);
+        uint32_t nrec = 0;        // accepted hits so far
+        bool last_accepted = false;  // was the last processed hit accepted?
         while (true) {
             want = want && (last <= t1) && (T > P.min_transmittance);
             if (PACKET ? !__any_sync(0xFFFFFFFFu, want) : !want) break;
@@ -474,7 +531,10 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
                     D += hit_distance(f, h) * w;
                     hits += 1.f;
                     P.visibility[pid] = __int_as_float(1);  // benign race, same value (referenceOptix.cu:158-161)
+                    if (P.hit_list && nrec < static_cast<uint32_t>(P.hit_cap)) P.hit_list[static_cast<int64_t>(nrec) * P.rays + ray] = pid;
+                    nrec++;
                 }
+                last_accepted = h.accept;
                 last = fmaxf(last, lt[i]);
             }
             if (li[kK - 1] == kNone) want = false;  // fewer than 16 hits: the ray is exhausted, the reference's next trace would return nothing
@@ -485,6 +545,9 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
             P.out_dist[ray * 2] = D;
             P.out_dist[ray * 2 + 1] = last;
             P.out_hits[ray] = hits;
+            // the backward's re-trace ends strictly before the last processed hit (referenceBwdOptix.cu:115,125): if that hit was
+            // accepted it is not replayed either
+            if (P.hit_count) P.hit_count[ray] = nrec > static_cast<uint32_t>(P.hit_cap) ? kNone : nrec - ((last_accepted && nrec > 0) ? 1u : 0u);
         }
     } else {
         const float Cix = P.out_rgb[ray * 3], Ciy = P.out_rgb[ray * 3 + 1], Ciz = P.out_rgb[ray * 3 + 2];
@@ -494,6 +557,7 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
         float start = fmaxf(0.f, t0 - kEpsT);
         const float end = fminf(max_hit, t1) + kEpsT;
         bool want = valid && (P.n > 0);
+        if (P.only_overflow && want) want = P.hit_count[ray] == kNone;
         while (true) {
             want = want && (start < end);
             if (PACKET ? !__any_sync(0xFFFFFFFFu, want) : !want) break;
@@ -510,48 +574,7 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
             for (int i = 0; i < kK; ++i) {
                 const uint32_t pid = li[i];
                 if (pid == kNone) continue;
-                const ParticleFrame f = load_frame(P.particles, pid);
-                const CanonicalHit h = canonical_hit<DEG>(f, ox, oy, oz, dx, dy, dz, P.min_response, P.min_alpha, P.max_alpha);
-                if (h.accept) {
-                    const float4* c4 = reinterpret_cast<const float4*>(P.sph + static_cast<size_t>(pid) * 48);
-                    float r = 0.5f, g = 0.5f, b = 0.5f;
-#pragma unroll
-                    for (int k = 0; k < 12; ++k) {
-                        const float4 v = __ldg(c4 + k);
-                        const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int flat = k * 4 + q, j = flat / 3, c = flat % 3;
-                            if (c == 0) r += basis[j] * e[q];
-                            if (c == 1) g += basis[j] * e[q];
-                            if (c == 2) b += basis[j] * e[q];
-                        }
-                    }
-                    float gr[11], rg[3];
-                    hit_adjoint<DEG>(f, h, dx, dy, dz, fmaxf(r, 0.f), fmaxf(g, 0.f), fmaxf(b, 0.f), P.min_transmittance, Tint, Tgrad, Cix,
-                                     Ciy, Ciz, Cgx, Cgy, Cgz, Dint, Dgrad, T, Cx, Cy, Cz, D, gr, rg);
-                    // 16-byte vector reductions (red.global.add.v4.f32): 3 + 12 instead of 11 + 48 scalar atomics per hit
-                    float4* dp = reinterpret_cast<float4*>(P.d_particles + static_cast<size_t>(pid) * 12);
-                    atomicAdd(dp, make_float4(gr[0], gr[1], gr[2], gr[3]));
-                    atomicAdd(dp + 1, make_float4(gr[4], gr[5], gr[6], gr[7]));
-                    atomicAdd(dp + 2, make_float4(gr[8], gr[9], gr[10], 0.f));
-                    // radianceFromSpHBwd<true> (gaussianParticles.cuh:101-177): clamp mask on the unclamped radiance
-                    const float mr = r > 0.f ? rg[0] : 0.f, mg = g > 0.f ? rg[1] : 0.f, mb = b > 0.f ? rg[2] : 0.f;
-                    float4* ds = reinterpret_cast<float4*>(P.d_sph + static_cast<size_t>(pid) * 48);
-                    const int ncoef = (P.sph_degree + 1) * (P.sph_degree + 1);
-#pragma unroll
-                    for (int k = 0; k < 12; ++k) {
-                        if (k * 4 < ncoef * 3) {  // the basis is zero beyond the active degree
-                            float e[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int flat = k * 4 + q, j = flat / 3, c = flat % 3;
-                                e[q] = basis[j] * (c == 0 ? mr : (c == 1 ? mg : mb));
-                            }
-                            atomicAdd(ds + k, make_float4(e[0], e[1], e[2], e[3]));
-                        }
-                    }
-                }
+                backward_hit<DEG>(P, pid, ox, oy, oz, dx, dy, dz, basis, Tint, Tgrad, Cix, Ciy, Ciz, Cgx, Cgy, Cgz, Dint, Dgrad, T, Cx, Cy, Cz, D);
                 start = fmaxf(start, lt[i]);
             }
             if (li[kK - 1] == kNone) want = false;
@@ -598,6 +621,43 @@ __global__ void __launch_bounds__(128, kTraceBlocksPerSm) trace_kernel(TracePara
 }
 
 
+// Backward from the hit lists the forward recorded: no traversal, one thread per ray, list reads coalesced across the warp.
+// Rays whose list overflowed (hit_count == kNone) are left to the re-trace launch that follows.
+template <int DEG>
+__global__ void __launch_bounds__(128) replay_bwd_kernel(TraceParams P) {
+    const int bw = (P.width + 7) / 8, bh = (P.height + 3) / 4;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int per_image = bw * bh;
+    if (warp >= per_image * P.batch) return;
+    const int img = warp / per_image, blk = warp % per_image;
+    const int px = (blk % bw) * 8 + (lane & 7), py = (blk / bw) * 4 + (lane >> 3);
+    if (px >= P.width || py >= P.height) return;
+    const int64_t ray = (static_cast<int64_t>(img) * P.height + py) * P.width + px;
+    const uint32_t count = P.hit_count[ray];
+    if (count == kNone || count == 0u) return;
+    const float rox = P.rays_o[ray * 3], roy = P.rays_o[ray * 3 + 1], roz = P.rays_o[ray * 3 + 2];
+    const float rdx = P.rays_d[ray * 3], rdy = P.rays_d[ray * 3 + 1], rdz = P.rays_d[ray * 3 + 2];
+    const float* m = P.r2w;
+    const float ox = m[0] * rox + m[1] * roy + m[2] * roz + m[3];
+    const float oy = m[4] * rox + m[5] * roy + m[6] * roz + m[7];
+    const float oz = m[8] * rox + m[9] * roy + m[10] * roz + m[11];
+    const float dx = m[0] * rdx + m[1] * rdy + m[2] * rdz;
+    const float dy = m[4] * rdx + m[5] * rdy + m[6] * rdz;
+    const float dz = m[8] * rdx + m[9] * rdy + m[10] * rdz;
+    float basis[16];
+    sh_basis16(P.sph_degree, dx, dy, dz, basis);
+    const float Cix = P.out_rgb[ray * 3], Ciy = P.out_rgb[ray * 3 + 1], Ciz = P.out_rgb[ray * 3 + 2];
+    const float Tint = 1.0f - P.out_alpha[ray], Dint = P.out_dist[ray * 2];
+    const float Cgx = P.d_rgb[ray * 3], Cgy = P.d_rgb[ray * 3 + 1], Cgz = P.d_rgb[ray * 3 + 2];
+    const float Tgrad = -1.0f * P.d_alpha[ray], Dgrad = P.d_dist[ray];
+    float T = 1.f, Cx = 0.f, Cy = 0.f, Cz = 0.f, D = 0.f;
+#pragma unroll 1
+    for (uint32_t i = 0; i < count; ++i) {
+        const uint32_t pid = P.hit_list[static_cast<int64_t>(i) * P.rays + ray];
+        backward_hit<DEG>(P, pid, ox, oy, oz, dx, dy, dz, basis, Tint, Tgrad, Cix, Ciy, Ciz, Cgx, Cgy, Cgz, Dint, Dgrad, T, Cx, Cy, Cz, D);
+    }
+}
+
 int fail(grtb200_ctx* c, const char* fmt, ...);
 
 }  // namespace
@@ -614,6 +674,12 @@ struct grtb200_ctx {
          *scene = nullptr, *sort_temp = nullptr, *grp_codes = nullptr, *grp_ids = nullptr, *grp_boxes = nullptr, *grp_proxies = nullptr;
     size_t cap = 0, sort_temp_bytes = 0;
     int leaf = 2;   // particles per leaf of the last build
+    // hit-list cache of the last forward (see TraceParams)
+    void *hit_list = nullptr, *hit_count = nullptr;
+    size_t hit_list_bytes = 0, hit_count_bytes = 0;
+    int hit_cap = 96, hit_cap_used = 0;
+    uint64_t build_generation = 0;
+    struct { const float* rays_o; const float* rays_d; const float* particles; const float* out_rgb; const float* out_dist; int64_t rays; int64_t n; uint64_t generation; float r2w[12]; bool valid; } fwd_key = {};
     float scene_host[6] = {0, 0, 0, 0, 0, 0};
     bool scene_valid = false;
 };
@@ -738,6 +804,8 @@ void grtb200_destroy(grtb200_ctx* c) {
     cudaDeviceSynchronize();
     release(c);
     if (c->scene) cudaFree(c->scene);
+    if (c->hit_list) cudaFree(c->hit_list);
+    if (c->hit_count) cudaFree(c->hit_count);
     delete c;
 }
 
@@ -752,6 +820,8 @@ int grtb200_build_bvh(grtb200_ctx* c, void* stream, int64_t n, const float* pos,
     GRT_CUDA(c, cudaSetDevice(c->device));
     c->n = n;
     c->scene_valid = false;
+    c->build_generation++;
+    c->fwd_key.valid = false;
     if (n == 0) {
         for (float& v : c->scene_host) v = 0.f;
         c->scene_valid = true;
@@ -860,6 +930,37 @@ int grtb200_trace(grtb200_ctx* c, void* stream, int64_t n, const float* particle
     if (int rc = fill_params(c, P, n, particles, sph, sph_degree, min_transmittance, batch, height, width, rays_o, rays_d, ray_to_world_host, s)) return rc;
     P.out_rgb = out_rgb; P.out_alpha = out_alpha; P.out_dist = out_dist; P.out_hits = out_hits; P.visibility = visibility;
     if (n > 0) GRT_CUDA(c, cudaMemsetAsync(visibility, 0, static_cast<size_t>(n) * 4, s));
+    // hit-list cache for the backward of this forward (grow-only; GRTB200_HITCAP=0 turns it off, the backward then re-traces)
+    c->fwd_key.valid = false;
+    int cap = c->hit_cap;
+    if (const char* e = std::getenv("GRTB200_HITCAP")) cap = std::max(0, std::min(1024, std::atoi(e)));
+    const int64_t rays = static_cast<int64_t>(batch) * height * width;
+    if (cap > 0 && rays > 0 && n > 0) {
+        const size_t need = static_cast<size_t>(rays) * cap * 4, need_c = static_cast<size_t>(rays) * 4;
+        if (need > c->hit_list_bytes) {
+            GRT_CUDA(c, cudaStreamSynchronize(s));
+            if (c->hit_list) cudaFree(c->hit_list);
+            c->hit_list = nullptr;
+            c->hit_list_bytes = 0;
+            GRT_CUDA(c, cudaMalloc(&c->hit_list, need));
+            c->hit_list_bytes = need;
+        }
+        if (need_c > c->hit_count_bytes) {
+            GRT_CUDA(c, cudaStreamSynchronize(s));
+            if (c->hit_count) cudaFree(c->hit_count);
+            c->hit_count = nullptr;
+            c->hit_count_bytes = 0;
+            GRT_CUDA(c, cudaMalloc(&c->hit_count, need_c));
+            c->hit_count_bytes = need_c;
+        }
+        P.hit_list = static_cast<uint32_t*>(c->hit_list);
+        P.hit_count = static_cast<uint32_t*>(c->hit_count);
+        P.hit_cap = cap;
+        P.rays = rays;
+        c->fwd_key = {rays_o, rays_d, particles, out_rgb, out_dist, rays, n, c->build_generation, {}, true};
+        memcpy(c->fwd_key.r2w, P.r2w, sizeof(P.r2w));
+        c->hit_cap_used = cap;
+    }
     launch_trace<false>(c->cfg, P, s);
     c->launches++;
     GRT_CUDA(c, cudaGetLastError());
@@ -881,6 +982,27 @@ int grtb200_trace_bwd(grtb200_ctx* c, void* stream, int64_t n, const float* part
     if (n > 0) {
         GRT_CUDA(c, cudaMemsetAsync(d_particles, 0, static_cast<size_t>(n) * 48, s));
         GRT_CUDA(c, cudaMemsetAsync(d_sph, 0, static_cast<size_t>(n) * 192, s));
+    }
+    const int64_t rays = static_cast<int64_t>(batch) * height * width;
+    const bool replay = c->fwd_key.valid && c->fwd_key.rays_o == rays_o && c->fwd_key.rays_d == rays_d && c->fwd_key.particles == particles &&
+                        c->fwd_key.out_rgb == out_rgb && c->fwd_key.out_dist == out_dist && memcmp(c->fwd_key.r2w, P.r2w, sizeof(P.r2w)) == 0 &&
+                        c->fwd_key.rays == rays && c->fwd_key.n == n && c->fwd_key.generation == c->build_generation && n > 0;
+    if (replay) {  // the lists of the forward these outputs came from: replay them, re-trace only the rays that overflowed
+        P.hit_list = static_cast<uint32_t*>(c->hit_list);
+        P.hit_count = static_cast<uint32_t*>(c->hit_count);
+        P.hit_cap = c->hit_cap_used;
+        P.rays = rays;
+        const int bw = (P.width + 7) / 8, bh = (P.height + 3) / 4;
+        const int64_t warps = static_cast<int64_t>(bw) * bh * P.batch;
+        const unsigned blocks = static_cast<unsigned>((warps * 32 + 127) / 128);
+        if (blocks) {
+            if (c->cfg.kernel_degree == 4)
+                replay_bwd_kernel<4><<<blocks, 128, 0, s>>>(P);
+            else
+                replay_bwd_kernel<2><<<blocks, 128, 0, s>>>(P);
+            c->launches++;
+        }
+        P.only_overflow = 1;
     }
     launch_trace<true>(c->cfg, P, s);
     c->launches++;

@@ -168,11 +168,13 @@ def _grt_frame(sc, c2w, d_out):
     return img[0].detach().cpu().numpy(), out["hits_count"][0].detach().cpu().numpy(), grads
 
 
-@pytest.mark.parametrize("switch,off", [("GRTB200_PACKET", "0"), ("GRTB200_SIZE_LEVELS", "0")])
+@pytest.mark.parametrize("switch,off", [("GRTB200_PACKET", "0"), ("GRTB200_SIZE_LEVELS", "0"), ("GRTB200_LEAF", "1"),
+                                        ("GRTB200_HITCAP", "0"), ("GRTB200_HITCAP", "8")])
 def test_traversal_variants_give_the_same_image(switch, off, monkeypatch):
-    """Packet traversal and the size-class bit of the LBVH key change HOW the tree is built / walked, not which hits a ray
-    finds: the same rays through either variant must give the same image, hit counts and gradients (only ties between
-    equal t* may resolve differently, and the atomics reorder fp32 sums)."""
+    """Packet traversal, the size-class bit of the LBVH key and the leaf size change HOW the tree is built / walked, not which
+    hits a ray finds; the hit-list cache changes how the backward finds the forward's hits (HITCAP=0: re-trace like the
+    reference, HITCAP=8: nearly every ray overflows its list and takes the re-trace fallback).  The same rays through either
+    variant must give the same image, hit counts and gradients."""
     sc = scenes.scene_c2(n=60_000, width=256, height=256)
     c2w = np.asarray(sc.camera(2, 10), np.float32)
     rng = np.random.default_rng(0)
