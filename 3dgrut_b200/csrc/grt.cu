@@ -43,7 +43,10 @@ constexpr float kInf = 1e20f;     // RayHit::InfiniteDistance
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr float kEpsT = 1e-9f;
 constexpr int kStack = 64;
-constexpr int kTraceBlocksPerSm = 5;  // caps the trace kernels at 102 registers: 20 warps per SM
+#ifndef GRT_BLOCKS_PER_SM
+#define GRT_BLOCKS_PER_SM 6
+#endif
+constexpr int kTraceBlocksPerSm = GRT_BLOCKS_PER_SM;  // 6 -> 80 registers, 24 warps per SM (measured at C4: 4 -> 131, 5 -> 139, 6 -> 143 frames/s)
 
 struct __align__(16) Proxy {  // rows of A^-1 = diag(1/kscl) R^T with the centre in .w
     float4 a0, a1, a2;
