@@ -38,7 +38,18 @@ EXPORTS = [
     "gutb200_version", "gutb200_default_config", "gutb200_create", "gutb200_destroy", "gutb200_last_error",
     "gutb200_forward", "gutb200_backward", "gutb200_forward_host", "gutb200_backward_host", "gutb200_last_stats",
     "gutb200_debug_copy", "gutb200_collect_times", "gutb200_collect_stage_times", "gutb200_set_timings", "gutb200_launch_count",
+    "gutb200_backward_compact", "gutb200_sph_grad_from_views", "gutb200_camera_position",
 ]
+
+def camera_position(cam):
+    """Sensor position in world space as the kernels compute it (gutb200_camera_position): numpy float32 [3]."""
+    import numpy as np
+
+    out = np.zeros(3, np.float32)
+    if load().gutb200_camera_position(C.byref(cam), out.ctypes.data) != 0:
+        raise RuntimeError("gutb200_camera_position failed")
+    return out
+
 
 DBG_TILES_COUNT, DBG_SORTED_KEYS, DBG_SORTED_VALUES, DBG_TILE_RANGES, DBG_DEPTH, DBG_RGB, DBG_PROJ = range(7)
 
@@ -70,6 +81,9 @@ def load():
     cam = C.POINTER(Camera)
     lib.gutb200_forward.argtypes = [vp, vp, cam, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.gutb200_backward.argtypes = [vp, vp, cam, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.gutb200_backward_compact.argtypes = [vp, vp, cam, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.gutb200_sph_grad_from_views.argtypes = [vp, vp, i64, vp, i32, i32, vp, vp, vp]
+    lib.gutb200_camera_position.argtypes = [cam, vp]
     lib.gutb200_forward_host.argtypes = [vp, cam, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.gutb200_backward_host.argtypes = [vp, cam, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.gutb200_last_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
@@ -121,6 +135,20 @@ class Context:
                  d_particles, d_sph):
         self._check(self._lib.gutb200_backward(self._h, stream, C.byref(cam), n, particles, sph, sph_degree, rays_o, rays_d,
                                                out_rgba, d_rgba, out_dist, d_dist, d_particles, d_sph), "gutb200_backward")
+
+    def backward_compact(self, stream, cam, n, particles, sph, sph_degree, rays_o, rays_d, out_rgba, d_rgba, out_dist, d_dist,
+                         d_particles, d_radiance):
+        """Like backward, but emits the [N,4] masked radiance gradient instead of the [N,48] SH gradient (view-parallel exchange)."""
+        self._check(self._lib.gutb200_backward_compact(self._h, stream, C.byref(cam), n, particles, sph, sph_degree, rays_o, rays_d,
+                                                       out_rgba, d_rgba, out_dist, d_dist, d_particles, d_radiance), "gutb200_backward_compact")
+
+    def sph_grad_from_views(self, stream, n, particles, sph_degree, view_positions, d_radiance_all, d_sph):
+        """view_positions: float32 numpy [views,3] (host); d_radiance_all: device [views,N,4]; d_sph: device [N,48]."""
+        import numpy as np
+
+        vp_ = np.ascontiguousarray(view_positions, dtype=np.float32)
+        self._check(self._lib.gutb200_sph_grad_from_views(self._h, stream, n, particles, sph_degree, int(vp_.shape[0]), vp_.ctypes.data,
+                                                          d_radiance_all, d_sph), "gutb200_sph_grad_from_views")
 
     def forward_host(self, cam, n, particles, sph, sph_degree, rays_o, rays_d, out_rgba, out_dist, out_hits, visibility):
         self._check(self._lib.gutb200_forward_host(self._h, C.byref(cam), n, particles, sph, sph_degree, rays_o, rays_d,

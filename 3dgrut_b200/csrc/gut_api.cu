@@ -476,9 +476,9 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     return 0;
 }
 
-int gutb200_backward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int64_t n, const float* particles, const float* sph,
-                     int32_t sph_degree, const float* rays_o, const float* rays_d, const float* out_rgba, const float* d_rgba,
-                     const float* out_dist, const float* d_dist, float* d_particles, float* d_sph) {
+static int backward_impl(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int64_t n, const float* particles, const float* sph,
+                         int32_t sph_degree, const float* rays_o, const float* rays_d, const float* out_rgba, const float* d_rgba,
+                         const float* out_dist, const float* d_dist, float* d_particles, float* d_sph, bool compact) {
     if (int rc = check_args(c, cam, n, particles)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // the backward replays the sorted lists of the immediately preceding forward (gutRenderer.cu:436-440)
@@ -500,7 +500,7 @@ int gutb200_backward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, in
     if (n > 0) {
         StageTimer t(c, 7, s);
         launch_project_backward(s, c->cam, n, particles, sph, sph_degree, c->rgb.as<float>(), c->tiles_count.as<uint32_t>(),
-                                c->grad_acc.as<float>(), d_particles, d_sph);
+                                c->grad_acc.as<float>(), d_particles, d_sph, compact);
         c->launches++;
     }
     GUT_CUDA(c, cudaGetLastError());
@@ -508,6 +508,44 @@ int gutb200_backward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, in
         GUT_CUDA(c, cudaEventRecord(c->ev[3], s));
         c->bwd_pending = true;
     }
+    return 0;
+}
+
+int gutb200_backward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int64_t n, const float* particles, const float* sph,
+                     int32_t sph_degree, const float* rays_o, const float* rays_d, const float* out_rgba, const float* d_rgba,
+                     const float* out_dist, const float* d_dist, float* d_particles, float* d_sph) {
+    return backward_impl(c, stream, cam, n, particles, sph, sph_degree, rays_o, rays_d, out_rgba, d_rgba, out_dist, d_dist, d_particles, d_sph, false);
+}
+
+int gutb200_backward_compact(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int64_t n, const float* particles, const float* sph,
+                             int32_t sph_degree, const float* rays_o, const float* rays_d, const float* out_rgba, const float* d_rgba,
+                             const float* out_dist, const float* d_dist, float* d_particles, float* d_radiance) {
+    return backward_impl(c, stream, cam, n, particles, sph, sph_degree, rays_o, rays_d, out_rgba, d_rgba, out_dist, d_dist, d_particles, d_radiance,
+                         true);
+}
+
+int gutb200_sph_grad_from_views(gutb200_ctx* c, void* stream, int64_t n, const float* particles, int32_t sph_degree, int32_t views,
+                                const float* view_positions_host, const float* d_radiance_all, float* d_sph) {
+    if (!c) return 1;
+    if (views < 1 || views > 64) return fail(c, "views %d out of range (1..64)", views);
+    if (n < 0 || !view_positions_host) return fail(c, "invalid arguments");
+    if (sph_degree < 0 || sph_degree > 3) return fail(c, "sph_degree %d out of range", sph_degree);
+    GUT_CUDA(c, cudaSetDevice(c->device));
+    launch_sph_from_views(static_cast<cudaStream_t>(stream), n, particles, sph_degree, views, view_positions_host, d_radiance_all, d_sph);
+    c->launches++;
+    GUT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int gutb200_camera_position(const gutb200_camera* cam, float* pos3) {
+    if (!cam || !pos3) return 1;
+    // the sensor position the kernels use: translation of the inverse mid-exposure pose (fill_frame)
+    const Pose ps = pose_from7(cam->pose_start), pe = pose_from7(cam->pose_end);
+    Pose mid;
+    mid.q = slerp(ps.q, pe.q, 0.5f);
+    for (int k = 0; k < 3; ++k) mid.t[k] = ps.t[k] * (1.f - 0.5f) + pe.t[k] * 0.5f;
+    const Pose inv = pose_inverse(mid);
+    for (int k = 0; k < 3; ++k) pos3[k] = inv.t[k];
     return 0;
 }
 

@@ -63,7 +63,9 @@ void launch_render_backward(cudaStream_t s, const FrameCamera& cam, const FrameC
                             const float* out_dist, const float* d_dist, float* grad_acc);
 void launch_project_backward(cudaStream_t s, const FrameCamera& cam, int64_t n, const float* particles, const float* sph,
                              int sph_degree, const float* rgb, const uint32_t* tiles_count, float* grad_acc,
-                             float* d_particles, float* d_sph);
+                             float* d_particles, float* d_sph, bool compact = false);
+void launch_sph_from_views(cudaStream_t s, int64_t n, const float* particles, int sph_degree, int views, const float* view_positions,
+                           const float* d_radiance_all, float* d_sph);
 
 // CUB-backed helpers (scan + radix sort), gut_sort.cu
 size_t scan_temp_bytes(int64_t n);

@@ -684,6 +684,10 @@ __constant__ float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.457045
 // particles, so the caller needs no memset).  Threads only touch shared memory, with 128-bit accesses.
 constexpr int kPbThreads = 128;
 
+// COMPACT (view-parallel training): instead of the [N,48] SH gradient row the kernel emits the masked radiance gradient (3 floats) the
+// row is the outer product of -- d_sph[j][c] = basis_j(direction) * g[c] -- so ranks exchange 16 instead of 192 bytes per particle and
+// rebuild the summed rows with sph_from_views_kernel.
+template <bool COMPACT>
 __global__ void __launch_bounds__(kPbThreads) project_backward_kernel(FrameCamera cam, int64_t n, const float* __restrict__ particles,
                                                                       const float* __restrict__ sph, int deg, const float* __restrict__ rgb,
                                                                       const uint32_t* __restrict__ tiles_count, float* __restrict__ grad_acc,
@@ -768,29 +772,76 @@ __global__ void __launch_bounds__(kPbThreads) project_backward_kernel(FrameCamer
                 dpy += (gy - y * dd) * inv_len;
                 dpz += (gz - z * dd) * inv_len;
             }
-            float o[48];  // d SH = basis x masked gradient
+            if (COMPACT) {
+                row[0] = make_float4(mgr, mgg, mgb, 0.f);
+            } else {
+                float o[48];  // d SH = basis x masked gradient
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                o[k * 3 + 0] = bs[k] * mgr;
-                o[k * 3 + 1] = bs[k] * mgg;
-                o[k * 3 + 2] = bs[k] * mgb;
+                for (int k = 0; k < 16; ++k) {
+                    o[k * 3 + 0] = bs[k] * mgr;
+                    o[k * 3 + 1] = bs[k] * mgg;
+                    o[k * 3 + 2] = bs[k] * mgb;
+                }
+#pragma unroll
+                for (int k = 0; k < 12; ++k) row[k] = make_float4(o[k * 4], o[k * 4 + 1], o[k * 4 + 2], o[k * 4 + 3]);
             }
-#pragma unroll
-            for (int k = 0; k < 12; ++k) row[k] = make_float4(o[k * 4], o[k * 4 + 1], o[k * 4 + 2], o[k * 4 + 3]);
         }
         s_dp[tid * 3 + 0] = make_float4(dpx, dpy, dpz, a0.w);
         s_dp[tid * 3 + 1] = a1;
         s_dp[tid * 3 + 2] = make_float4(a2.x, a2.y, a2.z, 0.f);
     }
+    if (COMPACT) {  // pack the 16-byte radiance gradients of the block contiguously (front of s_sh) for one bulk store
+        const float4 mine = in_range ? s_sh[tid * 12] : zero;
+        __syncthreads();
+        s_sh[tid] = mine;
+    }
     fence_proxy_async();  // our shared-memory writes must be visible to the TMA engine
     __syncthreads();
     if (tid == 0) {
-        tma_bulk_s2g(d_sph + base * 48, s_sh, static_cast<uint32_t>(cnt) * 192u);
+        if (COMPACT)
+            tma_bulk_s2g(d_sph + base * 4, s_sh, static_cast<uint32_t>(cnt) * 16u);
+        else
+            tma_bulk_s2g(d_sph + base * 48, s_sh, static_cast<uint32_t>(cnt) * 192u);
         tma_bulk_s2g(d_particles + base * 12, s_dp, static_cast<uint32_t>(cnt) * 48u);
         tma_bulk_s2g(grad_acc + base * kGradRow, s_acc, static_cast<uint32_t>(cnt) * 64u);
         tma_commit_group();
         tma_wait_group_read0();  // shared memory must stay valid until the engine has read it
     }
+}
+
+// d_sph[p] = sum over views v of basis(direction of particle p seen from view v) x radiance gradient of view v (the rows the
+// non-compact G8 of each view would have written, summed in view order -- the same order on every rank).
+struct ViewPositions {
+    float pos[64][3];
+};
+
+__global__ void __launch_bounds__(128) sph_from_views_kernel(int64_t n, const float* __restrict__ particles, int deg, int views, ViewPositions vp,
+                                                              const float4* __restrict__ d_radiance_all, float4* __restrict__ d_sph) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = __ldg(reinterpret_cast<const float4*>(particles + i * 12));
+    float o[48];
+#pragma unroll
+    for (int k = 0; k < 48; ++k) o[k] = 0.f;
+    for (int v = 0; v < views; ++v) {
+        const float4 g = __ldg(d_radiance_all + static_cast<int64_t>(v) * n + i);
+        if (g.x == 0.f && g.y == 0.f && g.z == 0.f) continue;  // invisible in that view (or clamped): a zero row
+        const float vx = p.x - vp.pos[v][0], vy = p.y - vp.pos[v][1], vz = p.z - vp.pos[v][2];
+        const float len = sqrtf(vx * vx + vy * vy + vz * vz);
+        const float inv_len = len > 0.f ? 1.0f / len : 0.f;
+        const float x = len > 0.f ? vx * inv_len : 1.f, y = vy * inv_len, z = vz * inv_len;
+        float bs[16];
+        sh_basis16(deg, x, y, z, bs);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            o[k * 3 + 0] += bs[k] * g.x;
+            o[k * 3 + 1] += bs[k] * g.y;
+            o[k * 3 + 2] += bs[k] * g.z;
+        }
+    }
+    float4* row = d_sph + i * 12;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) row[k] = make_float4(o[k * 4], o[k * 4 + 1], o[k * 4 + 2], o[k * 4 + 3]);
 }
 
 }  // namespace
@@ -822,10 +873,24 @@ void launch_render_backward(cudaStream_t s, const FrameCamera& cam, const FrameC
 
 void launch_project_backward(cudaStream_t s, const FrameCamera& cam, int64_t n, const float* particles, const float* sph,
                              int sph_degree, const float* rgb, const uint32_t* tiles_count, float* grad_acc, float* d_particles,
-                             float* d_sph) {
+                             float* d_sph, bool compact) {
     if (n <= 0) return;
     const unsigned blocks = static_cast<unsigned>((n + kPbThreads - 1) / kPbThreads);
-    project_backward_kernel<<<blocks, kPbThreads, 0, s>>>(cam, n, particles, sph, sph_degree, rgb, tiles_count, grad_acc, d_particles, d_sph);
+    if (compact)
+        project_backward_kernel<true><<<blocks, kPbThreads, 0, s>>>(cam, n, particles, sph, sph_degree, rgb, tiles_count, grad_acc, d_particles, d_sph);
+    else
+        project_backward_kernel<false><<<blocks, kPbThreads, 0, s>>>(cam, n, particles, sph, sph_degree, rgb, tiles_count, grad_acc, d_particles, d_sph);
+}
+
+void launch_sph_from_views(cudaStream_t s, int64_t n, const float* particles, int sph_degree, int views, const float* view_positions /*host [views,3]*/,
+                           const float* d_radiance_all, float* d_sph) {
+    if (n <= 0) return;
+    ViewPositions vp;
+    for (int v = 0; v < views; ++v)
+        for (int k = 0; k < 3; ++k) vp.pos[v][k] = view_positions[v * 3 + k];
+    const unsigned blocks = static_cast<unsigned>((n + 127) / 128);
+    sph_from_views_kernel<<<blocks, 128, 0, s>>>(n, particles, sph_degree, views, vp, reinterpret_cast<const float4*>(d_radiance_all),
+                                                 reinterpret_cast<float4*>(d_sph));
 }
 
 }  // namespace gutb200

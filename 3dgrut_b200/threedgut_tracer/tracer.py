@@ -191,6 +191,53 @@ class SplatRaster:
                                     _ptr(d_density), _ptr(d_radiance))
         return d_density, d_radiance
 
+    # ---- view-parallel extensions (no reference twin: the reference trains on one GPU) -----------------------------------------
+
+    def trace_bwd_compact(self, frame_id, n_active_features, particle_density, particle_radiance, ray_ori, ray_dir, ray_time, sensor_params,
+                          timestamp_start, timestamp_end, pose_start, pose_end, ray_radiance_density, ray_radiance_density_grd,
+                          ray_hit_distance, ray_hit_distance_grd, out=None):
+        """trace_bwd that returns (dDensity [N,12], g [N,4]): g is the masked dL/d(radiance) of each particle in this view, from
+        which sph_grad_from_views rebuilds the [N,48] SH gradient of any set of views (16 instead of 192 bytes per particle to exchange)."""
+        dev = ray_ori.device
+        h, w = int(ray_ori.shape[1]), int(ray_ori.shape[2])
+        n = int(particle_density.shape[0])
+        particle_density = particle_density.contiguous()
+        particle_radiance = particle_radiance.contiguous()
+        ray_ori, ray_dir = ray_ori.contiguous(), ray_dir.contiguous()
+        rgba, d_rgba = ray_radiance_density.contiguous(), ray_radiance_density_grd.contiguous().float()
+        dist, d_dist = ray_hit_distance.contiguous(), ray_hit_distance_grd.contiguous().float()
+        if out is not None:
+            d_density, g = out
+            assert d_density.shape == (n, 12) and g.shape == (n, 4) and d_density.is_contiguous() and g.is_contiguous()
+        else:
+            d_density = torch.empty((n, 12), dtype=torch.float32, device=dev)
+            g = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        cam = self._camera(sensor_params, pose_start, pose_end, w, h)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._context(dev).backward_compact(stream, cam, n, _ptr(particle_density), _ptr(particle_radiance), int(n_active_features),
+                                            _ptr(ray_ori), _ptr(ray_dir), _ptr(rgba), _ptr(d_rgba), _ptr(dist), _ptr(d_dist),
+                                            _ptr(d_density), _ptr(g))
+        return d_density, g
+
+    def sensor_position(self, sensor_params, pose_start, pose_end, width, height):
+        """World-space sensor position of a view exactly as the kernels compute it: float32 numpy [3]."""
+        return native.camera_position(self._camera(sensor_params, pose_start, pose_end, int(width), int(height)))
+
+    def sph_grad_from_views(self, n_active_features, particle_density, view_positions, g_all, out=None):
+        """Sum over views of basis16(direction particle <- sensor_v) x g_v: the all-reduced [N,48] SH gradient.
+        view_positions: [views,3] (numpy / sequence, host); g_all: [views,N,4] device tensor (e.g. the result of an all-gather)."""
+        dev = particle_density.device
+        n = int(particle_density.shape[0])
+        particle_density = particle_density.contiguous()
+        g_all = g_all.contiguous()
+        assert g_all.dim() == 3 and g_all.shape[1] == n and g_all.shape[2] == 4
+        d_radiance = out if out is not None else torch.empty((n, 48), dtype=torch.float32, device=dev)
+        assert d_radiance.shape == (n, 48) and d_radiance.is_contiguous()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._context(dev).sph_grad_from_views(stream, n, _ptr(particle_density), int(n_active_features),
+                                               np.asarray(view_positions, np.float32).reshape(-1, 3), _ptr(g_all), _ptr(d_radiance))
+        return d_radiance
+
     def collect_times(self):
         """splatRaster.cpp:352-382: mean ms of the timers recorded since the last call"""
         out = {}

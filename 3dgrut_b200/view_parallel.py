@@ -61,3 +61,37 @@ def broadcast_parameters(params: Sequence[torch.Tensor], src: int = 0, group=Non
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         for p in params:
             dist.broadcast(p.data, src=src, group=group)
+
+
+class CompactGradientExchange:
+    """The gradient exchange of the 3DGUT path with 64 instead of 240 bytes per Gaussian on the wire.
+
+    A view's [N,48] SH gradient row is basis16(direction Gaussian <- sensor) x g, g = the masked dL/d(radiance) of the Gaussian in
+    that view (gut_render.cu: project_backward_kernel).  So the ranks
+      1. run `SplatRaster.trace_bwd_compact`, which writes d_particles [N,12] and g [N,4] into this object's buffers,
+      2. all-reduce d_particles (48 B x N) and all-gather g (16 B x N per rank),
+      3. rebuild sum_v basis(direction_v) x g_v with `SplatRaster.sph_grad_from_views` -- in view order, identical on every rank.
+    `sensor_positions` must list the sensor position of every rank's view of this step in rank order (each rank can compute all of
+    them from the step's poses with `SplatRaster.sensor_position`, or they are all-gathered with the batch metadata)."""
+
+    def __init__(self, raster, n: int, device, group=None):
+        self.raster, self.n, self.group = raster, int(n), group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.d_particles = torch.empty((self.n, 12), dtype=torch.float32, device=device)
+        self.g = torch.empty((self.n, 4), dtype=torch.float32, device=device)
+        self.g_all = torch.empty((self.world, self.n, 4), dtype=torch.float32, device=device)
+        self.d_sph = torch.empty((self.n, 48), dtype=torch.float32, device=device)
+
+    def out(self):
+        """The (d_particles, g) pair to pass as `out=` to trace_bwd_compact."""
+        return self.d_particles, self.g
+
+    def exchange(self, n_active_features: int, particle_density: torch.Tensor, sensor_positions):
+        if self.world > 1:
+            work = dist.all_gather_into_tensor(self.g_all.view(-1), self.g.view(-1), group=self.group, async_op=True)
+            dist.all_reduce(self.d_particles, op=dist.ReduceOp.SUM, group=self.group)
+            work.wait()
+        else:
+            self.g_all[0].copy_(self.g)
+        self.raster.sph_grad_from_views(n_active_features, particle_density, sensor_positions, self.g_all, out=self.d_sph)
+        return self.d_particles, self.d_sph

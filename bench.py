@@ -430,6 +430,9 @@ def main():
     ap.add_argument("--cpu-tile-stride", type=int, default=16)
     ap.add_argument("--cpu-ray-stride", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="compact", choices=["compact", "allreduce"],
+                    help="multi-GPU gradient exchange of the 3DGUT path: compact = all-reduce [N,12] + all-gather [N,4] + rebuild of the SH "
+                         "gradient (64 B per Gaussian on the wire), allreduce = one all-reduce of [N,60] (240 B)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -485,10 +488,22 @@ def main():
 
     grad_flat = torch.empty(n * 60, dtype=torch.float32, device=dev)  # [N,12] and [N,48] views of one bucket: one all-reduce
     grad_views = (grad_flat[: n * 12].view(n, 12), grad_flat[n * 12:].view(n, 48))
+    compact = None
+    if world > 1 and args.exchange == "compact":
+        import view_parallel
+
+        compact = view_parallel.CompactGradientExchange(raster, n, dev)
+        sensor_pos = [raster.sensor_position(sensor, p, p, W, H) for p in poses]  # every rank knows every view's pose
 
     def step_device(step):
         pose = poses[view_of(step)]
         rgba, dst, hits, vis = raster.trace(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose)
+        if compact is not None:
+            # 64 B instead of 240 B per Gaussian on the wire: all-reduce d_particles, all-gather the radiance gradients, rebuild d_sph
+            raster.trace_bwd_compact(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose, rgba, d_rgba, dst,
+                                     d_dist, out=compact.out())
+            positions = np.stack([sensor_pos[(step * world + r) % n_views] for r in range(world)])
+            return compact.exchange(sc.sph_degree, particles, positions)
         dp, ds = raster.trace_bwd(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose, rgba, d_rgba, dst, d_dist,
                                   out=grad_views)
         if world > 1:
@@ -625,7 +640,8 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": sc.name, "gaussians": n, "resolution": [W, H], "path": "3dgut", "views_per_step": world,
-                       "parallelism": f"view-parallel dp{world}" if world > 1 else "single", "l2": "flushed between timed steps (256 MiB fill)",
+                       "parallelism": f"view-parallel dp{world}" if world > 1 else "single",
+                       "exchange": (args.exchange if world > 1 else "none"), "l2": "flushed between timed steps (256 MiB fill)",
                        "N": N_, "V": V_, "I": I_, "T": T_, "P": P_},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,

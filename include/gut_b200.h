@@ -78,6 +78,18 @@ int gutb200_backward(gutb200_ctx* ctx, void* stream, const gutb200_camera* cam, 
                      float* d_particles, float* d_sph);
 
 /* Host-buffer variants: pinned or pageable host pointers; H2D/D2H copies happen inside on the context's stream. */
+/* View-parallel training (ours, no reference twin -- the reference is single-GPU): the [N,48] SH gradient row of a view is the outer
+ * product basis16(direction particle <- sensor) x g, g = masked dL/d(radiance) of the particle in that view.  gutb200_backward_compact
+ * emits g ([N,4], .w = 0) instead of the row; ranks all-gather the g's and all-reduce d_particles (16 + 48 instead of 240 bytes per
+ * particle on the wire), then gutb200_sph_grad_from_views rebuilds sum_v basis(direction_v) x g_v on every rank in view order.
+ * view_positions_host: [views,3] sensor positions from gutb200_camera_position (host pointers); d_radiance_all: [views,N,4] device. */
+int gutb200_backward_compact(gutb200_ctx* ctx, void* stream, const gutb200_camera* cam, int64_t n, const float* particles,
+                             const float* sph, int32_t sph_degree, const float* rays_o, const float* rays_d, const float* out_rgba,
+                             const float* d_rgba, const float* out_dist, const float* d_dist, float* d_particles, float* d_radiance);
+int gutb200_sph_grad_from_views(gutb200_ctx* ctx, void* stream, int64_t n, const float* particles, int32_t sph_degree, int32_t views,
+                                const float* view_positions_host, const float* d_radiance_all, float* d_sph);
+int gutb200_camera_position(const gutb200_camera* cam, float* pos3);
+
 int gutb200_forward_host(gutb200_ctx* ctx, const gutb200_camera* cam, int64_t n, const float* particles,
                          const float* sph, int32_t sph_degree, const float* rays_o, const float* rays_d,
                          float* out_rgba, float* out_dist, float* out_hits, float* visibility);

@@ -48,11 +48,12 @@ class _Batch:
         self.T_to_world = torch.from_numpy(np.asarray(c2w, np.float32))[None].to(device)
 
 
-@pytest.mark.parametrize("cam_index", [1, 6])
-def test_c4_like_forward_and_gradients(cam_index):
+@pytest.mark.parametrize("cam_index,size", [(1, (128, 128)), (6, (128, 128)), (3, (75, 53))])
+def test_c4_like_forward_and_gradients(cam_index, size):
+    """size (75, 53): ragged image -- partially filled 8x4 ray blocks (lanes without a ray take part in the packet votes)."""
     import threedgrt_tracer
 
-    sc = scenes.scene_c1()
+    sc = scenes.scene_c1(width=size[0], height=size[1])
     c2w = np.asarray(sc.camera(cam_index, 10), np.float32)
     cfg = go.grt_config()
     ro, rd = sc.rays()

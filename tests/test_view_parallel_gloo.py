@@ -65,3 +65,64 @@ def test_views_for_rank_partition():
         for step in range(5):
             seen = [v for r in range(world) for v in vp.views_for_rank(step, r, world, 1000, views_per_rank=3)]
             assert len(seen) == len(set(seen)) == world * 3
+
+
+class _OracleRaster:
+    """CPU stand-in for SplatRaster.sph_grad_from_views built on the oracle's SH evaluation (the product's version is a CUDA kernel;
+    this one only lets the gloo test run the exchange's collectives and check the identity d_sph = sum_v basis(dir_v) x g_v)."""
+
+    def sph_grad_from_views(self, deg, particle_density, positions, g_all, out=None):
+        from oracle import gut_oracle as go
+
+        pos = particle_density[:, 0:3].numpy()
+        n = pos.shape[0]
+        res = np.zeros((n, 16, 3), np.float64)
+        eye = np.eye(16, dtype=np.float32)
+        for v, cam in enumerate(np.asarray(positions, np.float32)):
+            d = pos - cam[None]
+            d = d / np.linalg.norm(d, axis=1, keepdims=True)
+            for i in range(n):
+                g = g_all[v, i, 0:3].numpy().astype(np.float64)
+                if not g.any():
+                    continue
+                # basis_j = SH evaluation of the unit coefficient e_j (the oracle adds 0.5 to the radiance: subtract it)
+                basis = np.array([go.sph_eval(deg, np.repeat(eye[j][:, None], 3, 1), d[i])[0] - 0.5 for j in range(16)])
+                res[i] += basis[:, None] * g[None, :]
+        out.copy_(torch.from_numpy(res.reshape(n, 48).astype(np.float32)))
+        return out
+
+
+def _compact_worker(rank, world, port, out_dir):
+    import view_parallel as vp
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = scenes.scene_c1(n=60, width=32, height=32)
+    views = [vp.views_for_rank(step=1, rank=r, world=world, num_views=10)[0] for r in range(world)]
+    ref = oracle_frame(sc, sc.camera(views[rank], 10), seed=views[rank])
+    ex = vp.CompactGradientExchange(_OracleRaster(), sc.n, torch.device("cpu"))
+    d_particles, g = ex.out()
+    d_particles.copy_(torch.from_numpy(ref["dp"]))
+    # a view's SH gradient row is basis x g and basis_0 is the constant 0.2820948: g = row[0] / basis_0
+    g[:, 0:3] = torch.from_numpy(ref["ds"][:, 0:3] / 0.28209479177387814)
+    g[:, 3] = 0
+    positions = np.stack([np.asarray(sc.camera(v, 10), np.float32)[:3, 3] for v in views])
+    dp, ds = ex.exchange(sc.sph_degree, torch.from_numpy(sc.particles), positions)
+    np.savez(os.path.join(out_dir, f"compact{rank}.npz"), views=np.array(views), dp=dp.numpy(), ds=ds.numpy())
+    dist.destroy_process_group()
+
+
+def test_compact_exchange_matches_serial_sum(tmp_path):
+    """all-reduce [N,12] + all-gather [N,4] + rebuild == the serial sum of the per-view [N,12] / [N,48] oracle gradients."""
+    world = 2
+    mp.spawn(_compact_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outs = [np.load(tmp_path / f"compact{r}.npz") for r in range(world)]
+    views = [int(v) for v in outs[0]["views"]]
+    sc = scenes.scene_c1(n=60, width=32, height=32)
+    refs = [oracle_frame(sc, sc.camera(v, 10), seed=v) for v in views]
+    dp_sum, ds_sum = sum(r["dp"] for r in refs), sum(r["ds"] for r in refs)
+    assert np.abs(ds_sum).max() > 0
+    for o in outs:
+        assert np.allclose(o["dp"], dp_sum, rtol=1e-6, atol=1e-7)
+        assert np.allclose(o["ds"], ds_sum, rtol=2e-5, atol=1e-6 * float(np.abs(ds_sum).max()))
+    assert np.array_equal(outs[0]["ds"], outs[1]["ds"])  # replicas stay bit-identical
