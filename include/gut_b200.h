@@ -11,6 +11,7 @@
  *   gutb200_backward              <- SplatRaster::traceBwd                      (src/splatRaster.cpp:264-350) -> GUTRenderer::renderBackward (src/gutRenderer.cu:423-519)
  *   gutb200_collect_times         <- SplatRaster::collectTimes                  (src/splatRaster.cpp:352-382)
  *   gutb200_forward_host/_backward_host : same calls with HOST buffers (copies inside), used for the e2e metric.
+ *   gutb200_backward_compact / gutb200_sph_grad_from_views / gutb200_camera_position : view-parallel training (no reference twin).
  *   gutb200_debug_copy            : test-only read-back of the binning artefacts (tile counts, sort keys, ranges).
  *
  * Data layouts (all fp32 unless noted; identical to the reference tensors):
