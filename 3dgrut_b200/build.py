@@ -24,6 +24,8 @@ UNITS = {
     "gut_render.cu": ["--use_fast_math"],
     "gut_api.cu": ["-fmad=false"],
     "grt.cu": ["--use_fast_math"],
+    # optimizer step: plain IEEE arithmetic (the reference plugin is built without fast-math, setup_optimizers.py)
+    "gut_optim.cu": [],
 }
 
 

@@ -197,6 +197,37 @@ def run_reference_arm(args, rank, world):
 
 
 
+def time_optimizer_step(torch, dev, n, flush, peak, peak_src, iters=20):
+    """Next-row measurement, reported beside the render metric, never inside it: the fused activation-chain +
+    Adam step of all six parameter tensors (gut_optim.cu) on this workload's N, CUDA events, L2 flushed between launches.
+    Algorithmic bytes = 1660 B per Gaussian (59 floats x (param r/w + two moments r/w) + 240 B gradients + 4 B visibility)."""
+    import optimizers
+
+    g = torch.Generator(device=dev).manual_seed(5)
+    widths = dict(zip(optimizers.GROUPS, optimizers.WIDTHS))
+    leaves = {k: torch.randn((n, w), device=dev, generator=g) for k, w in widths.items()}
+    lrs = dict(positions=1.6e-4, density=0.05, rotation=1e-3, scale=5e-3, features_albedo=2.5e-3, features_specular=1.25e-4)
+    opt = optimizers.FusedGaussianAdam(leaves, lrs, eps=1e-15)
+    dp = torch.randn((n, 12), device=dev, generator=g)
+    ds = torch.randn((n, 48), device=dev, generator=g)
+    for _ in range(3):
+        opt.step(dp, ds)
+    ms = []
+    for i in range(iters):
+        flush.fill_(float(i))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        opt.step(dp, ds)
+        b.record()
+        torch.cuda.synchronize(dev)
+        ms.append(a.elapsed_time(b))
+    t = float(np.median(ms))
+    nbytes = 1660 * n
+    ach = nbytes / (t * 1e-3) / 1e9
+    return {"kernel": "gaussian_adam_kernel", "ms": t, "algorithmic_bytes": nbytes, "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak if peak else None, "peak_source": peak_src, "bound": "hbm"}
+
+
 class HostFeed:
     """End-to-end input feed: every step's rays and target image are copied from pinned host memory on a copy stream
     while the previous step computes (what a DataLoader with pinned memory does), and every step's loss is read back
@@ -655,6 +686,8 @@ def main():
             "stage_ms": stage_ms,
             "frame_algorithmic_gbs": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9,
         }
+        if world == 1:
+            line["optimizer_step"] = time_optimizer_step(torch, dev, n, flush, peak, peak_src)
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             fps, _ = cpu_port_frames_per_s(sc, args.cpu_tile_stride, frames=1, warm=0)

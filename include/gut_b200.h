@@ -91,6 +91,22 @@ int gutb200_sph_grad_from_views(gutb200_ctx* ctx, void* stream, int64_t n, const
                                 const float* view_positions_host, const float* d_radiance_all, float* d_sph);
 int gutb200_camera_position(const gutb200_camera* cam, float* pos3);
 
+/* Optimizer step.  No context: plain launches on `stream` of the current device; 0 on success.
+ * gutb200_selective_adam_update replaces selective_adam_update of the reference's optimizer plugin
+ * (threedgrut/optimizers/optimizers.cu:49-108, optimizers.cpp): param/grad/exp_avg/exp_avg_sq [n,m] fp32, visibility [n] bytes
+ * (bool), Adam without bias correction on the visible rows.  visibility == NULL updates every row.
+ * gutb200_gaussian_adam_step (ours) updates the six raw parameter tensors of the SH model in ONE launch from the renderer's
+ * gradients: params6 / exp_avg6 / exp_avg_sq6 = {positions [n,3], density [n,1], rotation [n,4], scale [n,3], features_albedo [n,3],
+ * features_specular [n,45]} (device pointers in a host array), lr6 their learning rates, d_particles [n,12] and d_sph [n,48] the
+ * gradients w.r.t. the ACTIVATED values as gutb200_backward writes them; the activation chain rule (sigmoid / exp / normalize,
+ * threedgrut/model/model.py:102-118) is applied inside.  selective = 0: torch.optim.Adam with bias correction at `step` (>= 1,
+ * model.py:807-810); selective = 1: the plugin's rule on rows with visibility != 0 (visibility = the renderer's [n] float output). */
+int gutb200_selective_adam_update(void* stream, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                  const uint8_t* visibility, float lr, float b1, float b2, float eps, int64_t n, int64_t m);
+int gutb200_gaussian_adam_step(void* stream, int64_t n, float* const* params6, float* const* exp_avg6, float* const* exp_avg_sq6,
+                               const float* lr6, float b1, float b2, float eps, int64_t step, int32_t selective, const float* d_particles,
+                               const float* d_sph, const float* visibility);
+
 int gutb200_forward_host(gutb200_ctx* ctx, const gutb200_camera* cam, int64_t n, const float* particles,
                          const float* sph, int32_t sph_degree, const float* rays_o, const float* rays_d,
                          float* out_rgba, float* out_dist, float* out_hits, float* visibility);
