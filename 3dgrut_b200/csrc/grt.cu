@@ -5,13 +5,17 @@
 // and its traversal (src/kernels/cuda/referenceOptix.cu) are replaced by our own kernels:
 //   proxy_kernel      per particle: instance transform inverse, world box, conservative radius, scene box (atomics)
 //                     <- computeGaussianEnclosingInstancesKernel + kernelScale (src/particlePrimitives.cu:27-51,543-610)
-//   morton_kernel     30-bit Morton code of the proxy centre in the scene box (expand_bits/morton3D, :628-659 helper)
-//   (CUB radix sort of (code, particle) pairs -- library)
-//   hierarchy_kernel  Karras LBVH topology, one thread per internal node
+//   morton_kernel     32-bit key = size-class bit + 30-bit Morton code of the proxy centre in the scene box
+//   (CUB radix sort of (key, particle) pairs -- library)
+//   leaf_kernel       leaves of `leaf` consecutive sorted particles: leaf key, leaf box, proxies stored in leaf order
+//   hierarchy_kernel  Karras LBVH topology over the leaves, one thread per internal node
 //   refit_kernel      bottom-up boxes, both child boxes stored in the 64-byte parent node (one fetch per visit)
-//   trace_kernel<DEG,BWD>  one thread per ray; per optixTrace-equivalent query a stack traversal gathers the 16 nearest
-//                     hits (t* order, strict comparisons, same bubble insertion as __anyhit__ah), then the hits are
-//                     integrated / differentiated in order (__raygen__rg of referenceOptix.cu / referenceBwdOptix.cu).
+//   trace_kernel<DEG,BWD>  a warp owns an 8x4 block of rays; per optixTrace-equivalent query the 16 nearest hits are gathered
+//                     (t* order, strict comparisons, same bubble insertion as __anyhit__ah) -- coherent blocks walk the tree as a
+//                     PACKET (one stack, warp-uniform control flow, per-lane payloads), others one traversal per thread -- then the
+//                     hits are integrated / differentiated in order (__raygen__rg of referenceOptix.cu / referenceBwdOptix.cu).
+//                     The forward also records each ray's accepted hits;
+//   replay_bwd_kernel replays those lists in the backward (no traversal); trace_kernel<DEG,true> re-traces only overflowed rays.
 // Candidate rule: the ray segment of the query meets the proxy's oriented box and the custom
 // intersection of the reference accepts (intersectInstanceParticle).  Subtrees entered beyond the current 16th hit are
 // culled, which is what OptiX does when the any-hit program shrinks the ray's tmax.

@@ -7,7 +7,7 @@
 //   G7  gutKBufferRenderer.cuh:642-716 + kernels/cuda/models/gaussianParticles.cuh:484-751 (hand-written adjoint)
 //   G8  kernels/cuda/renderers/gutProjector.cuh:390-430 + slang/common/sphericalHarmonics.slang:21-64
 //
-// Design: one CTA per 16x16 tile (the tile id is part of the sort key, so the tile
+// Design (sub-tile culling: see the section comment below): one CTA per 16x16 tile (the tile id is part of the sort key, so the tile
 // shape is fixed by parity), 256 threads = 256 pixels, sorted particle lists consumed in batches staged in
 // shared memory as render-ready records (scale folded into the rotation rows once per staged particle
 // instead of once per pixel test).  Both kernels are FP32/SFU-issue bound, not HBM bound.

@@ -1,17 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- train frames/s (forward + backward render) of the B200-native 3DGUT path.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c3|c1]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c3|c1|c4] [--exchange compact|allreduce]
 
 One "step" = one view rendered forward + backward (trace + trace_bwd with dL/d(RGBA, dist) given) over the
-synthetic scene of BASELINE.json `configs[1]` (lego-like: 800x800, 300k Gaussians, 3DGUT) at N=1.  With N>1 every
-rank renders a different camera of the same replicated scene and the per-Gaussian gradients ([N,12]+[N,48] fp32)
-are summed with one NCCL all-reduce per step (view-parallel training); scaling is weak.
+synthetic scene of BASELINE.json `configs[1]` (lego-like: 800x800, 300k Gaussians, 3DGUT) at N=1 (c3 = 6M Gaussians at
+1237x822, c4 = the c2 scene through the 3DGRT path).  With N>1 every rank renders a different camera of the same replicated
+scene and the per-Gaussian gradients are summed once per step (view-parallel training; scaling is weak):
+`compact` = all-reduce [N,12] + all-gather [N,4] + local rebuild of the [N,48] SH gradient, `allreduce` = one NCCL all-reduce of
+[N,12]+[N,48].
 
 Prints ONE JSON line (rank 0).  `value` = device-timed frames/s with inputs resident in HBM; `e2e` = the same
-metric through the public API (threedgut_tracer.Tracer.render + loss.backward) with the step's camera batch coming
-from pinned host memory and the loss read back; `roofline` is for the dominant kernel of the step;
-`cpu_baseline` is the CPU oracle (oracle/gut_oracle.c) on a bounded sample.
+metric through the public API (threedgut_tracer.Tracer.render + loss.backward) with every step's camera batch copied from
+pinned host memory (one step ahead, on a copy stream) and every step's loss read back; `roofline` is for the dominant kernel
+of the step; `cpu_baseline` is the CPU oracle (oracle/gut_oracle.c) on a bounded sample; `optimizer_step` (N=1) times the fused
+Adam step of SURVEY 8f row 2 on the workload's N -- reported beside the metric, never inside it.
 
 --impl reference: the reference has no CPU implementation and its CUDA build cannot be produced in this image
 (needs slangc); per the tier rules this arm times the CPU port (oracle/) of the reference algorithm
