@@ -662,11 +662,13 @@ def main():
         dom = max(stage_ms, key=lambda k: stage_ms[k])
         dom_ms = stage_ms[dom]
         traffic = None  # dram__bytes_read+write of that kernel from the committed ncu --set full capture of this workload
+        issue_pct = None  # smsp__issue_active of that kernel from the same capture (the render kernels are issue-bound, not HBM-bound)
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if tj.get("workload") == sc.name:
                 traffic = tj["dram_bytes_per_launch"].get({"render": "render_forward"}.get(dom, dom))
+                issue_pct = tj.get("issue_active_pct", {}).get({"render": "render_forward"}.get(dom, dom))
         achieved = stage_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         frame_bytes = 356 * N_ + 796 * V_ + (156 + 24 * 6) * I_ + 24 * T_ + 136 * P_
         line = {
@@ -685,7 +687,9 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(stage_bytes[dom]),
                          "kernel_ms": dom_ms,
-                         "note": "render/render_backward are FP32-issue bound (SURVEY 7); the HBM fraction is reported as required"},
+                         "issue_active_pct_ncu": issue_pct,
+                         "note": "render/render_backward are FP32-issue bound (SURVEY 8d): the HBM fraction is reported as required, "
+                                 "issue_active_pct_ncu is the committed ncu smsp__issue_active of this kernel on this workload"},
             "stage_ms": stage_ms,
             "frame_algorithmic_gbs": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9,
         }
