@@ -18,6 +18,7 @@ class Camera(C.Structure):
         ("principal", C.c_float * 2), ("focal", C.c_float * 2),
         ("radial", C.c_float * 6), ("tangential", C.c_float * 2), ("thin_prism", C.c_float * 4),
         ("pose_start", C.c_float * 7), ("pose_end", C.c_float * 7),
+        ("model", C.c_int32), ("max_angle", C.c_float),
     ]
 
 

@@ -23,6 +23,8 @@ struct FrameCamera {
     float cam_pos[3];     // sensor position in world space (gutRenderer.cu:282)
     float res_x, res_y;   // float copies of width/height
     int has_distortion;   // any radial / tangential / thin-prism coefficient non-zero
+    int model;            // 0 OpenCV pinhole, 1 OpenCV fisheye (radial[0..3] = k1..k4)
+    float max_angle;      // fisheye: half-angle of the valid cone
 };
 
 struct FrameConfig {

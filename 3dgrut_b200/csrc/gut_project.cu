@@ -102,6 +102,30 @@ __device__ __forceinline__ bool project_pinhole(const FrameCamera& cam, float to
     return valid_radial && inside;
 }
 
+// OpenCV fisheye projection of a sensor-space point (cameraProjections.cuh:25-35 stableNorm2, :38-48 Horner, :120-146)
+__device__ __forceinline__ bool project_fisheye(const FrameCamera& cam, float tol, float x, float y, float z, float& ox, float& oy) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
+    float rho = 0.f;
+    if (mx > 0.f) {
+        const float ratio = mn / mx;
+        rho = mx * sqrtf(1.f + ratio * ratio);
+    }
+    if (rho <= 0.f) rho = 1.1920929e-07f;  // FLT_EPSILON
+    const float theta_full = atan2f(rho, z);
+    const float theta = fminf(theta_full, cam.max_angle);  // FOV-clamped projections are marked invalid below
+    const float theta2 = theta * theta;
+    float poly = cam.radial[3];
+    poly = theta2 * poly + cam.radial[2];
+    poly = theta2 * poly + cam.radial[1];
+    poly = theta2 * poly + cam.radial[0];
+    const float delta = (theta * (poly * theta2 + 1.0f)) / rho;
+    ox = cam.fx * x * delta + cam.cx;
+    oy = cam.fy * y * delta + cam.cy;
+    const float mx0 = cam.res_x * tol, my0 = cam.res_y * tol;
+    return (theta < cam.max_angle) && (ox > -mx0) && (oy > -my0) && (ox < cam.res_x + mx0) && (oy < cam.res_y + my0);
+}
+
 // world point -> pixel with the shutter-open pose (global shutter branch, cameraProjections.cuh:225-232)
 __device__ __forceinline__ bool project_world(const FrameCamera& cam, float tol, float px, float py, float pz, float& ox, float& oy) {
     float s[3];
@@ -113,6 +137,7 @@ __device__ __forceinline__ bool project_world(const FrameCamera& cam, float tol,
         acc += cam.rot_start[2 * 3 + j] * pz;
         s[j] = acc + cam.t_start[j];
     }
+    if (cam.model == 1) return project_fisheye(cam, tol, s[0], s[1], s[2], ox, oy);
     return project_pinhole(cam, tol, s[0], s[1], s[2], ox, oy);
 }
 

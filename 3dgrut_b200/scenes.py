@@ -71,6 +71,27 @@ def pinhole_rays(height: int, width: int, fx: float, fy: float, cx: float, cy: f
     return np.zeros((1, height, width, 3), np.float32), d[None].astype(np.float32)
 
 
+def fisheye_rays(height: int, width: int, fx: float, fy: float, cx: float, cy: float, fisheye):
+    """Sensor-space unit rays of an OpenCV fisheye camera (inverse of cameraProjections.cuh:120-146): the pixel centre at normalised
+    distance r_d = |((u+.5-cx)/fx, (v+.5-cy)/fy)| comes from the angle theta with theta (1 + k1 th^2 + k2 th^4 + k3 th^6 + k4 th^8) = r_d
+    (Newton iterations in float64).  Returns ([1,H,W,3] origins = 0, [1,H,W,3] directions) float32."""
+    k1, k2, k3, k4 = (float(v) for v in fisheye[:4])
+    v, u = np.meshgrid(np.arange(height, dtype=np.float64), np.arange(width, dtype=np.float64), indexing="ij")
+    x = (u + 0.5 - cx) / fx
+    y = (v + 0.5 - cy) / fy
+    rd = np.sqrt(x * x + y * y)
+    th = rd.copy()
+    for _ in range(20):
+        t2 = th * th
+        f = th * (1 + t2 * (k1 + t2 * (k2 + t2 * (k3 + t2 * k4)))) - rd
+        df = 1 + t2 * (3 * k1 + t2 * (5 * k2 + t2 * (7 * k3 + t2 * 9 * k4)))
+        th = th - f / df
+    s = np.where(rd > 0, np.sin(th) / np.maximum(rd, 1e-30), 0.0)
+    d = np.stack([x * s, y * s, np.cos(th)], -1)
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    return np.zeros((1, height, width, 3), np.float32), d[None].astype(np.float32)
+
+
 @dataclass
 class Scene:
     name: str
@@ -82,6 +103,7 @@ class Scene:
     sph: np.ndarray  # [N,48]
     sph_degree: int
     camera_radius: float
+    fisheye: tuple | None = None  # (k1, k2, k3, k4, max_angle): OpenCV fisheye camera instead of the pinhole (fx, fy = pixels per radian)
 
     @property
     def cx(self):
@@ -99,6 +121,8 @@ class Scene:
         return orbit_c2w(i, n, self.camera_radius)
 
     def rays(self):
+        if self.fisheye is not None:
+            return fisheye_rays(self.height, self.width, self.fx, self.fy, self.cx, self.cy, self.fisheye)
         return pinhole_rays(self.height, self.width, self.fx, self.fy, self.cx, self.cy)
 
 

@@ -3,7 +3,7 @@
 Same names, argument meaning and tensor contracts as the reference:
   Tracer / Tracer._Autograd            threedgut_tracer/tracer.py:158-349
   SplatRaster{trace,trace_bwd,collect_times}   threedgut_tracer/bindings.cpp:103-109, src/splatRaster.cpp:184-382
-  fromOpenCVPinholeCameraModelParameters, ShutterType            threedgut_tracer/bindings.cpp:34-101
+  fromOpenCVPinholeCameraModelParameters, fromOpenCVFisheyeCameraModelParameters, ShutterType   threedgut_tracer/bindings.cpp:34-101
 PyTorch is used for device memory, streams and autograd only; every kernel is ours (csrc/*.cu).
 """
 from __future__ import annotations
@@ -35,6 +35,20 @@ class CameraModelParameters:
     radial_coeffs: np.ndarray
     tangential_coeffs: np.ndarray
     thin_prism_coeffs: np.ndarray
+    model: int = 0          # CameraModelParameters::ModelType: 0 OpenCVPinholeModel, 1 OpenCVFisheyeModel
+    max_angle: float = 0.0  # fisheye only
+
+
+def fromOpenCVFisheyeCameraModelParameters(resolution, shutter_type, principal_point, focal_length, radial_coeffs, max_angle) -> CameraModelParameters:
+    """bindings.cpp:68-84: OpenCV fisheye (equidistant + 4 radial coefficients, valid cone max_angle)"""
+    if ShutterType(shutter_type) != ShutterType.GLOBAL:
+        raise NotImplementedError("rolling-shutter projection is not built yet (SURVEY 8f row 4); global shutter only")
+    f32 = lambda a, n: np.asarray(a, dtype=np.float32).reshape(n)  # noqa: E731
+    radial6 = np.zeros(6, np.float32)
+    radial6[:4] = f32(radial_coeffs, 4)
+    return CameraModelParameters(np.asarray(resolution, dtype=np.int64).reshape(2), ShutterType(shutter_type), f32(principal_point, 2),
+                                 f32(focal_length, 2), radial6, np.zeros(2, np.float32), np.zeros(4, np.float32), model=1,
+                                 max_angle=float(max_angle))
 
 
 def fromOpenCVPinholeCameraModelParameters(resolution, shutter_type, principal_point, focal_length, radial_coeffs,
@@ -141,6 +155,8 @@ class SplatRaster:
         cam.thin_prism[:] = [float(v) for v in sensor.thin_prism_coeffs]
         cam.pose_start[:] = [float(v) for v in pose_start]  # .cpu() as in toSensorState (splatRaster.cpp:108-116)
         cam.pose_end[:] = [float(v) for v in pose_end]
+        cam.model = int(getattr(sensor, "model", 0))
+        cam.max_angle = float(getattr(sensor, "max_angle", 0.0))
         return cam
 
     def trace(self, frame_id, n_active_features, particle_density, particle_radiance, ray_ori, ray_dir, ray_time, sensor_params,
@@ -363,4 +379,12 @@ class Tracer:
                 radial_coeffs=K["radial_coeffs"], tangential_coeffs=K["tangential_coeffs"],
                 thin_prism_coeffs=K.get("thin_prism_coeffs", np.zeros((4,), dtype=np.float32)))
             return sensor, poses
-        raise ValueError("Camera intrinsics unavailable or unsupported (pinhole models only in this build)")
+        K = getattr(gpu_batch, "intrinsics_OpenCVFisheyeCameraModelParameters", None)
+        if K is not None:  # tracer.py:458-467
+            shutter = K["shutter_type"]
+            shutter = ShutterType[shutter] if isinstance(shutter, str) else ShutterType(shutter)
+            sensor = fromOpenCVFisheyeCameraModelParameters(
+                resolution=K["resolution"], shutter_type=shutter, principal_point=K["principal_point"], focal_length=K["focal_length"],
+                radial_coeffs=K["radial_coeffs"], max_angle=K["max_angle"])
+            return sensor, poses
+        raise ValueError("Camera intrinsics unavailable or unsupported (OpenCV pinhole and fisheye models in this build; f-theta is not built)")

@@ -43,6 +43,9 @@ typedef struct gutb200_camera {
     float thin_prism[4];
     float pose_start[7];
     float pose_end[7];
+    int32_t model;      /* TSensorModel::ModelType (sensors/cameraModels.h:59-72): 0 = OpenCV pinhole (radial[6], tangential, thin prism),
+                         * 1 = OpenCV fisheye (radial[0..3] = k1..k4, max_angle; bindings.cpp:68-84).  F-theta: not built. */
+    float max_angle;    /* OpenCVFisheyeProjectionParameters::maxAngle (cameraModels.h:30-35) */
 } gutb200_camera;
 
 /* Render configuration == the reference's compile-time -D constants (threedgut_tracer/setup_3dgut.py:64-95). */

@@ -340,11 +340,39 @@ static int project_pinhole(const gut_oracle_camera* cam, v3 p, float tol, float 
     return valid_radial && within_resolution((float)cam->width, (float)cam->height, tol, out[0], out[1]);
 }
 
+/* OpenCV fisheye projection: cameraProjections.cuh:25-35 (stableNorm2), 38-48 (evalPolyHorner), 120-146 */
+static float stable_norm2(float x, float y) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
+    if (mx <= 0.f) return 0.f;
+    const float ratio = mn / mx;
+    return mx * sqrtf(1.f + ratio * ratio);
+}
+
+static int project_fisheye(const gut_oracle_camera* cam, v3 p, float tol, float out[2]) {
+    const float px = (float)p.x, py = (float)p.y, pz = (float)p.z;
+    float rho = stable_norm2(px, py);
+    if (rho <= 0.f) rho = FLT_EPSILON;
+    const float theta_full = atan2f(rho, pz);
+    const float theta = fminf(theta_full, cam->max_angle);   /* FOV-clamped projections are marked invalid below */
+    const float theta2 = theta * theta;
+    const float* k = cam->radial;
+    float poly = k[3];
+    poly = theta2 * poly + k[2];
+    poly = theta2 * poly + k[1];
+    poly = theta2 * poly + k[0];
+    const float delta = (theta * (poly * theta2 + 1.0f)) / rho;
+    out[0] = cam->focal[0] * px * delta + cam->principal[0];
+    out[1] = cam->focal[1] * py * delta + cam->principal[1];
+    return (theta < cam->max_angle) && within_resolution((float)cam->width, (float)cam->height, tol, out[0], out[1]);
+}
+
 /* projectPointWithShutter, global shutter branch: start pose only (cameraProjections.cuh:225-232) */
 static int project_world_point(const gut_oracle_camera* cam, const mat3c* rstart, const float tstart[3], v3 p,
                                float tol, float out[2]) {
     v3 s = mat3c_mul(rstart, p);
     s = V3(s.x + tstart[0], s.y + tstart[1], s.z + tstart[2]);
+    if (cam->model == 1) return project_fisheye(cam, s, tol, out);
     return project_pinhole(cam, s, tol, out);
 }
 

@@ -22,7 +22,8 @@
 extern "C" {
 #endif
 
-/* OpenCV pinhole camera, global shutter (reference: sensors/cameraModels.h:22-72). */
+/* OpenCV pinhole (model 0) or OpenCV fisheye (model 1: radial[0..3] = k1..k4, max_angle) camera, global shutter
+ * (reference: sensors/cameraModels.h:22-35,59-72). */
 typedef struct {
     int32_t width, height;
     float principal[2];
@@ -32,6 +33,8 @@ typedef struct {
     float thin_prism[4];
     float pose_start[7]; /* t.xyz, q.xyzw ; world -> sensor (sensors.h:33) */
     float pose_end[7];
+    int32_t model;       /* TSensorModel::ModelType: 0 OpenCVPinholeModel, 1 OpenCVFisheyeModel */
+    float max_angle;     /* OpenCVFisheyeProjectionParameters::maxAngle */
 } gut_oracle_camera;
 
 /* Render configuration = the reference's compile-time -D constants (setup_3dgut.py:64-95). */

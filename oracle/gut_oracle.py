@@ -23,6 +23,7 @@ class Camera(C.Structure):
         ("principal", C.c_float * 2), ("focal", C.c_float * 2),
         ("radial", C.c_float * 6), ("tangential", C.c_float * 2), ("thin_prism", C.c_float * 4),
         ("pose_start", C.c_float * 7), ("pose_end", C.c_float * 7),
+        ("model", C.c_int32), ("max_angle", C.c_float),
     ]
 
 
@@ -71,13 +72,18 @@ def default_config() -> Config:
     return cfg
 
 
-def make_camera(width, height, fx, fy, cx, cy, pose_start, pose_end=None) -> Camera:
+def make_camera(width, height, fx, fy, cx, cy, pose_start, pose_end=None, fisheye=None) -> Camera:
+    """fisheye: None (OpenCV pinhole) or (k1, k2, k3, k4, max_angle) for the OpenCV fisheye model."""
     cam = Camera()
     cam.width, cam.height = int(width), int(height)
     cam.principal[:] = [cx, cy]
     cam.focal[:] = [fx, fy]
     cam.pose_start[:] = [float(v) for v in pose_start]
     cam.pose_end[:] = [float(v) for v in (pose_end if pose_end is not None else pose_start)]
+    if fisheye is not None:
+        cam.model = 1
+        cam.radial[0:4] = [float(v) for v in fisheye[0:4]]
+        cam.max_angle = float(fisheye[4])
     return cam
 
 

@@ -50,6 +50,15 @@ def sensor_matrices(p0, p1):
     return view.reshape(4, 3), inv.reshape(4, 3), pos
 
 
+def set_camera_model(fisheye=None):
+    """Camera model of the following project() / expand() calls: None = OpenCV pinhole, (k1,k2,k3,k4,max_angle) = OpenCV fisheye."""
+    if fisheye is None:
+        lib().ref_set_camera_model(C.c_int(0), None)
+    else:
+        f = _f(np.asarray(fisheye, np.float32).reshape(5))
+        lib().ref_set_camera_model(C.c_int(1), _p(f))
+
+
 def project(particles, sph, degree, width, height, focal, pp, p0, p1):
     particles, sph, focal, pp, p0, p1 = map(_f, (particles, sph, focal, pp, p0, p1))
     n = particles.shape[0]

@@ -32,6 +32,29 @@ def projection():
     np.savez_compressed(os.path.join(HERE, "gut_projection_ref.npz"), **out)
 
 
+FISHEYE = (0.05, -0.01, 0.002, -0.0003, 0.33)  # k1..k4, max angle
+
+
+def projection_fisheye():
+    """Same pins through the OpenCV fisheye model (cameraProjections.cuh:120-146).  atan2f comes from the libm of the machine that
+    runs this script; the fixture therefore pins the oracle bit for bit only where libm agrees (glibc 2.3x: correctly rounded in
+    practice) -- the test accepts a <= 1e-3 fraction of differing tile counts and compares float fields with a 1e-6 tolerance."""
+    sc = scenes.scene_c1(n=300, seed=3, width=96, height=64)
+    f = 1.2 * sc.width
+    out = dict(particles=sc.particles, sph=sc.sph, width=sc.width, height=sc.height, fx=f, fy=f, cx=sc.cx, cy=sc.cy, fisheye=np.asarray(FISHEYE, np.float32))
+    gr.set_camera_model(FISHEYE)
+    try:
+        for i in range(3):
+            pose = scenes.pose7_from_c2w(sc.camera(i, 3))
+            rf = gr.project(sc.particles, sc.sph, 3, sc.width, sc.height, [f, f], [sc.cx, sc.cy], pose, pose)
+            keys, vals = gr.expand(sc.width, sc.height, rf["tiles_count"], rf["proj_pos"], rf["conic_opacity"], rf["extent"], rf["depth"])
+            out.update({f"pose{i}": pose, f"keys{i}": keys, f"vals{i}": vals})
+            out.update({f"{k}{i}": v for k, v in rf.items()})
+    finally:
+        gr.set_camera_model(None)
+    np.savez_compressed(os.path.join(HERE, "gut_projection_fisheye_ref.npz"), **out)
+
+
 def hits():
     rng = np.random.default_rng(2024)
     rows = []
@@ -68,6 +91,7 @@ def sph():
 if __name__ == "__main__":
     assert gr.available(), "oracle/_ref could not be built (needs /root/reference)"
     projection()
+    projection_fisheye()
     hits()
     sph()
     print("golden fixtures written to", HERE)

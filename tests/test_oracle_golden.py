@@ -34,6 +34,27 @@ def test_projection_keys_and_pose_maths_match_reference_fixture():
             assert np.all(tiles[b:e] == t) and (e - b) == np.sum(tiles == t)
 
 
+def test_fisheye_projection_matches_reference_fixture():
+    """OpenCV fisheye model: the fixture was produced by the reference's own projection code on the build machine's libm (atan2f);
+    on the same libm the oracle is bit-identical (tests/test_oracle_vs_ref.py), elsewhere a last-bit atan2f difference may flip a
+    borderline tile count."""
+    z = np.load(os.path.join(G, "gut_projection_fisheye_ref.npz"))
+    cfg = go.default_config()
+    for i in range(3):
+        cam = go.make_camera(int(z["width"]), int(z["height"]), float(z["fx"]), float(z["fy"]), float(z["cx"]), float(z["cy"]), z[f"pose{i}"],
+                             fisheye=tuple(float(v) for v in z["fisheye"]))
+        pr = go.project(cfg, cam, z["particles"], z["sph"], 3)
+        same = pr.tiles_count == z[f"tiles_count{i}"]
+        assert same.mean() >= 0.999 and (z[f"tiles_count{i}"] == 0).sum() > 0 and z[f"tiles_count{i}"].sum() > 100
+        assert np.array_equal(pr.depth.view(np.uint32), z[f"depth{i}"].view(np.uint32))
+        vis = same & (pr.tiles_count > 0)
+        for k in ("proj_pos", "conic_opacity", "extent"):
+            assert np.allclose(getattr(pr, k)[vis], z[f"{k}{i}"][vis], rtol=1e-5, atol=1e-5), k
+        if same.all():
+            bn = go.bin_tiles(cfg, cam, pr)
+            assert np.array_equal(bn.unsorted_keys, z[f"keys{i}"]) and np.array_equal(bn.unsorted_values, z[f"vals{i}"])
+
+
 def test_single_hit_forward_and_adjoint_match_reference_fixture():
     rows = np.load(os.path.join(G, "gut_hits_ref.npz"))["rows"]
     cfg = go.default_config()

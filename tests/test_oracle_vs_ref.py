@@ -41,6 +41,38 @@ def test_projection_and_keys_bit_identical(cam_index):
     assert np.array_equal(keys[order], bn.sorted_keys) and np.array_equal(vals[order], bn.sorted_values)
 
 
+FISHEYE = (0.05, -0.01, 0.002, -0.0003, 0.33)  # k1..k4, max angle (rad): some particles fall outside the valid cone
+
+
+@pytest.mark.parametrize("cam_index", range(4))
+def test_fisheye_projection_bit_identical(cam_index):
+    """OpenCV fisheye model (cameraProjections.cuh:120-146) through the whole projection + key expansion: bit-identical with the
+    reference's own code compiled for the host (both sides call the same libm atan2f)."""
+    sc = scenes.scene_c1(bands=True)
+    cfg = go.default_config()
+    pose = scenes.pose7_from_c2w(sc.camera(cam_index, 4))
+    f = 1.2 * sc.width  # fisheye focal: pixels per radian (the image spans about +-0.4 rad, the valid cone 0.33)
+    cam = go.make_camera(sc.width, sc.height, f, f, sc.cx, sc.cy, pose, fisheye=FISHEYE)
+    pr = go.project(cfg, cam, sc.particles, sc.sph, 3)
+    gr.set_camera_model(FISHEYE)
+    try:
+        rf = gr.project(sc.particles, sc.sph, 3, sc.width, sc.height, [f, f], [sc.cx, sc.cy], pose, pose)
+        keys, vals = gr.expand(sc.width, sc.height, rf["tiles_count"], rf["proj_pos"], rf["conic_opacity"], rf["extent"], rf["depth"])
+    finally:
+        gr.set_camera_model(None)
+    assert pr.tiles_count.sum() > 500
+    assert (pr.tiles_count == 0).sum() > 0  # the max-angle / resolution rejections are exercised
+    assert np.array_equal(pr.tiles_count, rf["tiles_count"])
+    assert np.array_equal(pr.depth.view(np.uint32), rf["depth"].view(np.uint32))
+    for k in ("proj_pos", "conic_opacity", "extent"):
+        assert np.array_equal(getattr(pr, k), rf[k]), k
+    bn = go.bin_tiles(cfg, cam, pr)
+    assert np.array_equal(keys, bn.unsorted_keys) and np.array_equal(vals, bn.unsorted_values)
+    # and it differs from the pinhole projection of the same scene (the model switch is really taken)
+    pin = go.project(cfg, go.make_camera(sc.width, sc.height, f, f, sc.cx, sc.cy, pose), sc.particles, sc.sph, 3)
+    assert not np.array_equal(pin.proj_pos, pr.proj_pos)
+
+
 def test_sensor_pose_maths_identical():
     sc = scenes.scene_c1()
     for i in range(8):
