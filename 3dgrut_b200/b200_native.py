@@ -19,6 +19,7 @@ class Camera(C.Structure):
         ("radial", C.c_float * 6), ("tangential", C.c_float * 2), ("thin_prism", C.c_float * 4),
         ("pose_start", C.c_float * 7), ("pose_end", C.c_float * 7),
         ("model", C.c_int32), ("max_angle", C.c_float),
+        ("ftheta_reference_poly", C.c_int32), ("ftheta_bw", C.c_float * 6), ("ftheta_fw", C.c_float * 6), ("ftheta_cde", C.c_float * 3),
     ]
 
 

@@ -223,6 +223,10 @@ void fill_frame(gutb200_ctx* c, const gutb200_camera* cam) {
     f.res_y = static_cast<float>(cam->height);
     f.model = cam->model;
     f.max_angle = cam->max_angle;
+    f.ft_reference_poly = cam->ftheta_reference_poly;
+    memcpy(f.ft_bw, cam->ftheta_bw, sizeof(f.ft_bw));
+    memcpy(f.ft_fw, cam->ftheta_fw, sizeof(f.ft_fw));
+    memcpy(f.ft_cde, cam->ftheta_cde, sizeof(f.ft_cde));
     const Pose ps = pose_from7(cam->pose_start), pe = pose_from7(cam->pose_end);
     const Mat3 rs = to_mat3(ps.q);
     for (int cc = 0; cc < 3; ++cc)
@@ -261,7 +265,7 @@ void fill_frame(gutb200_ctx* c, const gutb200_camera* cam) {
 int check_args(gutb200_ctx* c, const gutb200_camera* cam, int64_t n, const void* particles) {
     if (!c) return 1;
     if (!cam || cam->width <= 0 || cam->height <= 0) return fail(c, "invalid camera resolution");
-    if (cam->model != 0 && cam->model != 1) return fail(c, "camera model %d not built (0 = OpenCV pinhole, 1 = OpenCV fisheye)", cam->model);
+    if (cam->model < 0 || cam->model > 2) return fail(c, "camera model %d unknown (0 = OpenCV pinhole, 1 = OpenCV fisheye, 2 = f-theta)", cam->model);
     if (n < 0 || n > 0x7FFFFFFF) return fail(c, "particle count %lld out of range", static_cast<long long>(n));
     if (reinterpret_cast<uintptr_t>(particles) & 15) return fail(c, "particle buffer must be 16-byte aligned");
     if (c->cfg.kernel_degree != 2 && c->cfg.kernel_degree != 4) return fail(c, "kernel_degree %d not built (2 or 4)", c->cfg.kernel_degree);

@@ -23,8 +23,10 @@ struct FrameCamera {
     float cam_pos[3];     // sensor position in world space (gutRenderer.cu:282)
     float res_x, res_y;   // float copies of width/height
     int has_distortion;   // any radial / tangential / thin-prism coefficient non-zero
-    int model;            // 0 OpenCV pinhole, 1 OpenCV fisheye (radial[0..3] = k1..k4)
-    float max_angle;      // fisheye: half-angle of the valid cone
+    int model;            // 0 OpenCV pinhole, 1 OpenCV fisheye (radial[0..3] = k1..k4), 2 f-theta
+    float max_angle;      // fisheye / f-theta: half-angle of the valid cone
+    int ft_reference_poly;          // f-theta (model 2): 0 backward polynomial is the reference, 1 forward
+    float ft_bw[6], ft_fw[6], ft_cde[3];
 };
 
 struct FrameConfig {

@@ -126,6 +126,47 @@ __device__ __forceinline__ bool project_fisheye(const FrameCamera& cam, float to
     return (theta < cam.max_angle) && (ox > -mx0) && (oy > -my0) && (ox < cam.res_x + mx0) && (oy < cam.res_y + my0);
 }
 
+// f-theta projection of a sensor-space point (cameraProjections.cuh:148-198: 6-coefficient polynomials, 3 Newton iterations)
+template <int N>
+__device__ __forceinline__ float horner(const float* c, float x) {  // evalPolyHorner<N>, :38-48
+    float y = c[N - 1];
+#pragma unroll
+    for (int i = N - 2; i >= 0; --i) y = x * y + c[i];
+    return y;
+}
+
+__device__ __forceinline__ bool project_ftheta(const FrameCamera& cam, float tol, float x, float y, float z, float& ox, float& oy) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
+    float rho = 0.f;
+    if (mx > 0.f) {
+        const float ratio = mn / mx;
+        rho = mx * sqrtf(1.f + ratio * ratio);
+    }
+    if (rho <= 0.f) rho = 1.1920929e-07f;  // FLT_EPSILON
+    const float theta_full = atan2f(rho, z);
+    const float theta = fminf(theta_full, cam.max_angle);
+    float delta = horner<6>(cam.ft_fw, theta);
+    if (cam.ft_reference_poly == 0) {  // invert the backward polynomial, started from the forward one
+        float dpoly[5];
+#pragma unroll
+        for (int i = 1; i < 6; ++i) dpoly[i - 1] = i * cam.ft_bw[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float dfdx = horner<5>(dpoly, delta);
+            const float residual = horner<6>(cam.ft_bw, delta) - theta;
+            delta -= residual / dfdx;
+        }
+    }
+    const float s = delta / rho;
+    ox = s * (cam.ft_cde[0] * x + cam.ft_cde[1] * y);
+    oy = s * (cam.ft_cde[2] * x + y);
+    ox += cam.cx + .5f;  // image coordinate origin = centre of the first pixel
+    oy += cam.cy + .5f;
+    const float mx0 = cam.res_x * tol, my0 = cam.res_y * tol;
+    return (theta < cam.max_angle) && (ox > -mx0) && (oy > -my0) && (ox < cam.res_x + mx0) && (oy < cam.res_y + my0);
+}
+
 // world point -> pixel with the shutter-open pose (global shutter branch, cameraProjections.cuh:225-232)
 __device__ __forceinline__ bool project_world(const FrameCamera& cam, float tol, float px, float py, float pz, float& ox, float& oy) {
     float s[3];
@@ -138,6 +179,7 @@ __device__ __forceinline__ bool project_world(const FrameCamera& cam, float tol,
         s[j] = acc + cam.t_start[j];
     }
     if (cam.model == 1) return project_fisheye(cam, tol, s[0], s[1], s[2], ox, oy);
+    if (cam.model == 2) return project_ftheta(cam, tol, s[0], s[1], s[2], ox, oy);
     return project_pinhole(cam, tol, s[0], s[1], s[2], ox, oy);
 }
 

@@ -92,6 +92,27 @@ def fisheye_rays(height: int, width: int, fx: float, fy: float, cx: float, cy: f
     return np.zeros((1, height, width, 3), np.float32), d[None].astype(np.float32)
 
 
+def ftheta_rays(height: int, width: int, ft: dict):
+    """Sensor-space unit rays of an f-theta camera (inverse of cameraProjections.cuh:148-198): pixel centre (u+.5, v+.5) lies at the
+    offset (u - px, v - py) from the principal point (the model's origin is the centre of the first pixel); the offset is mapped
+    through the inverse of the linear term [c d; e 1] and its length r through the BACKWARD polynomial theta = bw(r)."""
+    c, d, e = (float(v) for v in ft["cde"])
+    px, py = (float(v) for v in ft["principal"])
+    v, u = np.meshgrid(np.arange(height, dtype=np.float64), np.arange(width, dtype=np.float64), indexing="ij")
+    ox, oy = u - px, v - py
+    det = c - d * e
+    x = (ox - d * oy) / det
+    y = (-e * ox + c * oy) / det
+    r = np.sqrt(x * x + y * y)
+    th = np.zeros_like(r)
+    for k in reversed(range(6)):
+        th = th * r + float(ft["bw"][k])
+    s = np.where(r > 0, np.sin(th) / np.maximum(r, 1e-30), 0.0)
+    dirs = np.stack([x * s, y * s, np.cos(th)], -1)
+    dirs /= np.linalg.norm(dirs, axis=-1, keepdims=True)
+    return np.zeros((1, height, width, 3), np.float32), dirs[None].astype(np.float32)
+
+
 @dataclass
 class Scene:
     name: str
@@ -104,6 +125,7 @@ class Scene:
     sph_degree: int
     camera_radius: float
     fisheye: tuple | None = None  # (k1, k2, k3, k4, max_angle): OpenCV fisheye camera instead of the pinhole (fx, fy = pixels per radian)
+    ftheta: dict | None = None    # f-theta camera: dict(reference_poly=0|1, bw=[6], fw=[6], cde=[3], max_angle=..., principal=(px, py))
 
     @property
     def cx(self):
@@ -121,6 +143,8 @@ class Scene:
         return orbit_c2w(i, n, self.camera_radius)
 
     def rays(self):
+        if self.ftheta is not None:
+            return ftheta_rays(self.height, self.width, self.ftheta)
         if self.fisheye is not None:
             return fisheye_rays(self.height, self.width, self.fx, self.fy, self.cx, self.cy, self.fisheye)
         return pinhole_rays(self.height, self.width, self.fx, self.fy, self.cx, self.cy)

@@ -35,8 +35,27 @@ class CameraModelParameters:
     radial_coeffs: np.ndarray
     tangential_coeffs: np.ndarray
     thin_prism_coeffs: np.ndarray
-    model: int = 0          # CameraModelParameters::ModelType: 0 OpenCVPinholeModel, 1 OpenCVFisheyeModel
-    max_angle: float = 0.0  # fisheye only
+    model: int = 0          # CameraModelParameters::ModelType: 0 OpenCVPinholeModel, 1 OpenCVFisheyeModel, 2 FThetaModel
+    max_angle: float = 0.0  # fisheye / f-theta
+    ftheta: dict | None = None  # f-theta: reference_poly (0 / 1), bw [6], fw [6], cde [3]
+
+
+class PolynomialType(enum.IntEnum):  # bindings.cpp:44-48
+    PIXELDIST_TO_ANGLE = 0
+    ANGLE_TO_PIXELDIST = 1
+
+
+def fromFThetaCameraModelParameters(resolution, shutter_type, principal_point, reference_poly, pixeldist_to_angle_poly, angle_to_pixeldist_poly,
+                                    max_angle, linear_cde) -> CameraModelParameters:
+    """bindings.cpp:86-101: f-theta camera (polynomials of 6 coefficients, linear term [c d; e 1])"""
+    if ShutterType(shutter_type) != ShutterType.GLOBAL:
+        raise NotImplementedError("rolling-shutter projection is not built yet (SURVEY 8f row 4); global shutter only")
+    f32 = lambda a, n: np.asarray(a, dtype=np.float32).reshape(n)  # noqa: E731
+    ft = dict(reference_poly=int(PolynomialType(reference_poly)), bw=f32(pixeldist_to_angle_poly, 6), fw=f32(angle_to_pixeldist_poly, 6),
+              cde=f32(linear_cde, 3))
+    return CameraModelParameters(np.asarray(resolution, dtype=np.int64).reshape(2), ShutterType(shutter_type), f32(principal_point, 2),
+                                 np.ones(2, np.float32), np.zeros(6, np.float32), np.zeros(2, np.float32), np.zeros(4, np.float32), model=2,
+                                 max_angle=float(max_angle), ftheta=ft)
 
 
 def fromOpenCVFisheyeCameraModelParameters(resolution, shutter_type, principal_point, focal_length, radial_coeffs, max_angle) -> CameraModelParameters:
@@ -157,6 +176,12 @@ class SplatRaster:
         cam.pose_end[:] = [float(v) for v in pose_end]
         cam.model = int(getattr(sensor, "model", 0))
         cam.max_angle = float(getattr(sensor, "max_angle", 0.0))
+        ft = getattr(sensor, "ftheta", None)
+        if ft is not None:
+            cam.ftheta_reference_poly = int(ft["reference_poly"])
+            cam.ftheta_bw[:] = [float(v) for v in ft["bw"]]
+            cam.ftheta_fw[:] = [float(v) for v in ft["fw"]]
+            cam.ftheta_cde[:] = [float(v) for v in ft["cde"]]
         return cam
 
     def trace(self, frame_id, n_active_features, particle_density, particle_radiance, ray_ori, ray_dir, ray_time, sensor_params,
@@ -387,4 +412,15 @@ class Tracer:
                 resolution=K["resolution"], shutter_type=shutter, principal_point=K["principal_point"], focal_length=K["focal_length"],
                 radial_coeffs=K["radial_coeffs"], max_angle=K["max_angle"])
             return sensor, poses
-        raise ValueError("Camera intrinsics unavailable or unsupported (OpenCV pinhole and fisheye models in this build; f-theta is not built)")
+        K = getattr(gpu_batch, "intrinsics_FThetaCameraModelParameters", None)
+        if K is not None:  # tracer.py:469-485
+            shutter = K["shutter_type"]
+            shutter = ShutterType[shutter] if isinstance(shutter, str) else ShutterType(shutter)
+            ref_poly = K["reference_poly"]
+            ref_poly = PolynomialType[ref_poly] if isinstance(ref_poly, str) else PolynomialType(ref_poly)
+            sensor = fromFThetaCameraModelParameters(
+                resolution=K["resolution"], shutter_type=shutter, principal_point=K["principal_point"], reference_poly=ref_poly,
+                pixeldist_to_angle_poly=K["pixeldist_to_angle_poly"], angle_to_pixeldist_poly=K["angle_to_pixeldist_poly"],
+                max_angle=K["max_angle"], linear_cde=K["linear_cde"])
+            return sensor, poses
+        raise ValueError("Camera intrinsics unavailable or unsupported (OpenCV pinhole, OpenCV fisheye and f-theta models)")

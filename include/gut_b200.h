@@ -44,8 +44,13 @@ typedef struct gutb200_camera {
     float pose_start[7];
     float pose_end[7];
     int32_t model;      /* TSensorModel::ModelType (sensors/cameraModels.h:59-72): 0 = OpenCV pinhole (radial[6], tangential, thin prism),
-                         * 1 = OpenCV fisheye (radial[0..3] = k1..k4, max_angle; bindings.cpp:68-84).  F-theta: not built. */
-    float max_angle;    /* OpenCVFisheyeProjectionParameters::maxAngle (cameraModels.h:30-35) */
+                         * 1 = OpenCV fisheye (radial[0..3] = k1..k4, max_angle; bindings.cpp:68-84), 2 = f-theta (fields below). */
+    float max_angle;    /* OpenCVFisheyeProjectionParameters::maxAngle (cameraModels.h:30-35) / FThetaProjectionParameters::maxAngle */
+    /* model 2 = f-theta (FThetaProjectionParameters, cameraModels.h:37-47; bindings.cpp:86-101); principal point = principal[] */
+    int32_t ftheta_reference_poly;  /* 0 PIXELDIST_TO_ANGLE, 1 ANGLE_TO_PIXELDIST */
+    float ftheta_bw[6];             /* pixeldist_to_angle_poly (backward) */
+    float ftheta_fw[6];             /* angle_to_pixeldist_poly (forward)  */
+    float ftheta_cde[3];            /* linear_cde */
 } gutb200_camera;
 
 /* Render configuration == the reference's compile-time -D constants (threedgut_tracer/setup_3dgut.py:64-95). */

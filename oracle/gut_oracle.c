@@ -367,12 +367,50 @@ static int project_fisheye(const gut_oracle_camera* cam, v3 p, float tol, float 
     return (theta < cam->max_angle) && within_resolution((float)cam->width, (float)cam->height, tol, out[0], out[1]);
 }
 
+/* f-theta projection: cameraProjections.cuh:148-198 (PolynomialDegree = 6 coefficients, 3 Newton iterations) */
+static float horner(const float* c, int n, float x) { /* evalPolyHorner<N>, :38-48 */
+    float y = c[n - 1];
+    for (int i = n - 2; i >= 0; --i) y = x * y + c[i];
+    return y;
+}
+
+static int project_ftheta(const gut_oracle_camera* cam, v3 p, float tol, float out[2]) {
+    const float px = (float)p.x, py = (float)p.y, pz = (float)p.z;
+    float rho = stable_norm2(px, py);
+    if (rho <= 0.f) rho = FLT_EPSILON;
+    const float theta_full = atan2f(rho, pz);
+    const float theta = fminf(theta_full, cam->max_angle);
+    float delta = 0.f;
+    if (cam->ftheta_reference_poly == 0) {
+        /* the backward polynomial is the reference: invert it with Newton iterations started from the forward polynomial */
+        delta = horner(cam->ftheta_fw, 6, theta);
+        float dpoly[5];
+        for (int i = 1; i < 6; ++i) dpoly[i - 1] = i * cam->ftheta_bw[i];
+        for (int i = 0; i < 3; ++i) {
+            const float dfdx = horner(dpoly, 5, delta);
+            const float residual = horner(cam->ftheta_bw, 6, delta) - theta;
+            delta -= residual / dfdx;
+        }
+    } else {
+        delta = horner(cam->ftheta_fw, 6, theta);
+    }
+    const float* cde = cam->ftheta_cde;
+    const float s = delta / rho;
+    out[0] = s * (cde[0] * px + cde[1] * py);
+    out[1] = s * (cde[2] * px + py);
+    /* the image coordinate origin of the f-theta model is the centre of the first pixel */
+    out[0] += cam->principal[0] + .5f;
+    out[1] += cam->principal[1] + .5f;
+    return (theta < cam->max_angle) && within_resolution((float)cam->width, (float)cam->height, tol, out[0], out[1]);
+}
+
 /* projectPointWithShutter, global shutter branch: start pose only (cameraProjections.cuh:225-232) */
 static int project_world_point(const gut_oracle_camera* cam, const mat3c* rstart, const float tstart[3], v3 p,
                                float tol, float out[2]) {
     v3 s = mat3c_mul(rstart, p);
     s = V3(s.x + tstart[0], s.y + tstart[1], s.z + tstart[2]);
     if (cam->model == 1) return project_fisheye(cam, s, tol, out);
+    if (cam->model == 2) return project_ftheta(cam, s, tol, out);
     return project_pinhole(cam, s, tol, out);
 }
 

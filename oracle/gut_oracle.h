@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-/* OpenCV pinhole (model 0) or OpenCV fisheye (model 1: radial[0..3] = k1..k4, max_angle) camera, global shutter
+/* OpenCV pinhole (model 0), OpenCV fisheye (model 1: radial[0..3] = k1..k4, max_angle) or f-theta (model 2) camera, global shutter
  * (reference: sensors/cameraModels.h:22-35,59-72). */
 typedef struct {
     int32_t width, height;
@@ -33,8 +33,13 @@ typedef struct {
     float thin_prism[4];
     float pose_start[7]; /* t.xyz, q.xyzw ; world -> sensor (sensors.h:33) */
     float pose_end[7];
-    int32_t model;       /* TSensorModel::ModelType: 0 OpenCVPinholeModel, 1 OpenCVFisheyeModel */
-    float max_angle;     /* OpenCVFisheyeProjectionParameters::maxAngle */
+    int32_t model;       /* TSensorModel::ModelType: 0 OpenCVPinholeModel, 1 OpenCVFisheyeModel, 2 FThetaModel */
+    float max_angle;     /* OpenCVFisheyeProjectionParameters::maxAngle / FThetaProjectionParameters::maxAngle */
+    /* FThetaProjectionParameters (sensors/cameraModels.h:37-47); principal point = principal[] */
+    int32_t ftheta_reference_poly; /* 0 PIXELDIST_TO_ANGLE, 1 ANGLE_TO_PIXELDIST */
+    float ftheta_bw[6];            /* pixeldistToAnglePoly (backward) */
+    float ftheta_fw[6];            /* angleToPixeldistPoly (forward)  */
+    float ftheta_cde[3];           /* linear_cde */
 } gut_oracle_camera;
 
 /* Render configuration = the reference's compile-time -D constants (setup_3dgut.py:64-95). */

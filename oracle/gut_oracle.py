@@ -24,6 +24,7 @@ class Camera(C.Structure):
         ("radial", C.c_float * 6), ("tangential", C.c_float * 2), ("thin_prism", C.c_float * 4),
         ("pose_start", C.c_float * 7), ("pose_end", C.c_float * 7),
         ("model", C.c_int32), ("max_angle", C.c_float),
+        ("ftheta_reference_poly", C.c_int32), ("ftheta_bw", C.c_float * 6), ("ftheta_fw", C.c_float * 6), ("ftheta_cde", C.c_float * 3),
     ]
 
 
@@ -72,8 +73,9 @@ def default_config() -> Config:
     return cfg
 
 
-def make_camera(width, height, fx, fy, cx, cy, pose_start, pose_end=None, fisheye=None) -> Camera:
-    """fisheye: None (OpenCV pinhole) or (k1, k2, k3, k4, max_angle) for the OpenCV fisheye model."""
+def make_camera(width, height, fx, fy, cx, cy, pose_start, pose_end=None, fisheye=None, ftheta=None) -> Camera:
+    """fisheye: None (OpenCV pinhole) or (k1, k2, k3, k4, max_angle) for the OpenCV fisheye model.
+    ftheta: None or dict(reference_poly=0|1, bw=[6], fw=[6], cde=[3], max_angle=..., principal=(px, py)) for the f-theta model."""
     cam = Camera()
     cam.width, cam.height = int(width), int(height)
     cam.principal[:] = [cx, cy]
@@ -84,6 +86,14 @@ def make_camera(width, height, fx, fy, cx, cy, pose_start, pose_end=None, fishey
         cam.model = 1
         cam.radial[0:4] = [float(v) for v in fisheye[0:4]]
         cam.max_angle = float(fisheye[4])
+    if ftheta is not None:
+        cam.model = 2
+        cam.principal[:] = [float(v) for v in ftheta["principal"]]
+        cam.ftheta_reference_poly = int(ftheta["reference_poly"])
+        cam.ftheta_bw[:] = [float(v) for v in ftheta["bw"]]
+        cam.ftheta_fw[:] = [float(v) for v in ftheta["fw"]]
+        cam.ftheta_cde[:] = [float(v) for v in ftheta["cde"]]
+        cam.max_angle = float(ftheta["max_angle"])
     return cam
 
 

@@ -59,6 +59,12 @@ def set_camera_model(fisheye=None):
         lib().ref_set_camera_model(C.c_int(1), _p(f))
 
 
+def set_ftheta(ftheta):
+    """f-theta model for the following project() calls (dict as in gut_oracle.make_camera); set_camera_model(None) resets."""
+    v = _f(np.concatenate([ftheta["bw"], ftheta["fw"], ftheta["cde"], [ftheta["max_angle"]]]).astype(np.float32))
+    lib().ref_set_ftheta(C.c_int(int(ftheta["reference_poly"])), _p(v))
+
+
 def project(particles, sph, degree, width, height, focal, pp, p0, p1):
     particles, sph, focal, pp, p0, p1 = map(_f, (particles, sph, focal, pp, p0, p1))
     n = particles.shape[0]

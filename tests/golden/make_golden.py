@@ -49,10 +49,32 @@ def projection_fisheye():
             rf = gr.project(sc.particles, sc.sph, 3, sc.width, sc.height, [f, f], [sc.cx, sc.cy], pose, pose)
             keys, vals = gr.expand(sc.width, sc.height, rf["tiles_count"], rf["proj_pos"], rf["conic_opacity"], rf["extent"], rf["depth"])
             out.update({f"pose{i}": pose, f"keys{i}": keys, f"vals{i}": vals})
-            out.update({f"{k}{i}": v for k, v in rf.items()})
+            out.update({f"{k}{i}": v for k, v in rf.items() if k != "visibility"})  # undefined for rejected particles in the reference
     finally:
         gr.set_camera_model(None)
     np.savez_compressed(os.path.join(HERE, "gut_projection_fisheye_ref.npz"), **out)
+
+
+def projection_ftheta():
+    """f-theta model (cameraProjections.cuh:148-198), backward polynomial as the reference (Newton inversion)."""
+    sc = scenes.scene_c1(n=300, seed=3, width=96, height=64)
+    f = 1.2 * sc.width
+    a1, a3 = 1.0 / f, 0.04 / f ** 3
+    ft = dict(reference_poly=0, bw=[0.0, a1, 0.0, a3, 0.0, 0.0], fw=[0.0, f, 0.0, -0.04 * f, 0.0, 0.0], cde=[1.0, 0.001, -0.002], max_angle=0.36,
+              principal=(sc.width / 2.0 - 0.5, sc.height / 2.0 - 0.5))
+    out = dict(particles=sc.particles, sph=sc.sph, width=sc.width, height=sc.height, bw=np.asarray(ft["bw"], np.float32),
+               fw=np.asarray(ft["fw"], np.float32), cde=np.asarray(ft["cde"], np.float32), max_angle=np.float32(ft["max_angle"]),
+               principal=np.asarray(ft["principal"], np.float32))
+    gr.set_ftheta(ft)
+    try:
+        for i in range(3):
+            pose = scenes.pose7_from_c2w(sc.camera(i, 3))
+            rf = gr.project(sc.particles, sc.sph, 3, sc.width, sc.height, [1.0, 1.0], list(ft["principal"]), pose, pose)
+            out.update({f"pose{i}": pose})
+            out.update({f"{k}{i}": v for k, v in rf.items() if k != "visibility"})
+    finally:
+        gr.set_camera_model(None)
+    np.savez_compressed(os.path.join(HERE, "gut_projection_ftheta_ref.npz"), **out)
 
 
 def hits():
@@ -92,6 +114,7 @@ if __name__ == "__main__":
     assert gr.available(), "oracle/_ref could not be built (needs /root/reference)"
     projection()
     projection_fisheye()
+    projection_ftheta()
     hits()
     sph()
     print("golden fixtures written to", HERE)

@@ -7,7 +7,8 @@ from oracle import gut_oracle as go
 
 def oracle_camera(sc, c2w, pose=None):
     pose = scenes.pose7_from_c2w(c2w) if pose is None else pose
-    return go.make_camera(sc.width, sc.height, sc.fx, sc.fy, sc.cx, sc.cy, pose, fisheye=getattr(sc, "fisheye", None)), pose
+    return go.make_camera(sc.width, sc.height, sc.fx, sc.fy, sc.cx, sc.cy, pose, fisheye=getattr(sc, "fisheye", None),
+                          ftheta=getattr(sc, "ftheta", None)), pose
 
 
 def tracer_pose(c2w):

@@ -66,7 +66,15 @@ class _Batch:
             resolution=np.array([sc.width, sc.height]), shutter_type="GLOBAL", principal_point=np.array([sc.cx, sc.cy], np.float32),
             focal_length=np.array([sc.fx, sc.fy], np.float32), radial_coeffs=np.zeros(6, np.float32),
             tangential_coeffs=np.zeros(2, np.float32), thin_prism_coeffs=np.zeros(4, np.float32))
-        if getattr(sc, "fisheye", None) is not None:
+        if getattr(sc, "ftheta", None) is not None:
+            ft = sc.ftheta
+            self.intrinsics_OpenCVPinholeCameraModelParameters = None
+            self.intrinsics_FThetaCameraModelParameters = dict(
+                resolution=np.array([sc.width, sc.height]), shutter_type="GLOBAL", principal_point=np.asarray(ft["principal"], np.float32),
+                reference_poly="PIXELDIST_TO_ANGLE" if ft["reference_poly"] == 0 else "ANGLE_TO_PIXELDIST",
+                pixeldist_to_angle_poly=np.asarray(ft["bw"], np.float32), angle_to_pixeldist_poly=np.asarray(ft["fw"], np.float32),
+                max_angle=float(ft["max_angle"]), linear_cde=np.asarray(ft["cde"], np.float32))
+        elif getattr(sc, "fisheye", None) is not None:
             self.intrinsics_OpenCVPinholeCameraModelParameters = None
             self.intrinsics_OpenCVFisheyeCameraModelParameters = dict(
                 resolution=np.array([sc.width, sc.height]), shutter_type="GLOBAL", principal_point=np.array([sc.cx, sc.cy], np.float32),
@@ -395,34 +403,45 @@ def test_compact_exchange_rebuilds_the_sh_gradient():
     assert rel_l2(one, full_ds[1].cpu().numpy()) <= 1e-6
 
 
-@pytest.mark.parametrize("cam_index", [1, 4])
-def test_fisheye_camera_parity(cam_index):
-    """OpenCV fisheye sensor (cameraProjections.cuh:120-146) with matching fisheye rays.  The projection calls atan2f, which is not
-    correctly rounded on either side (CUDA <= 2 ulp, glibc <= 1 ulp), so the integer artefacts are compared per particle instead of
-    bit for bit as a whole: tile counts equal on >= 99.9 % of the particles, depth bits (no atan2f involved) exactly equal."""
+def _wide_angle_scene(model):
     import dataclasses
 
     base = scenes.scene_c1()
     f = 0.9 * base.width
-    sc = dataclasses.replace(base, fx=f, fy=f, fisheye=(0.05, -0.01, 0.002, -0.0003, 0.6))
+    if model == "fisheye":
+        return dataclasses.replace(base, fx=f, fy=f, fisheye=(0.05, -0.01, 0.002, -0.0003, 0.6))
+    a1, a3 = 1.0 / f, 0.04 / f ** 3
+    ft = dict(reference_poly=0 if model == "ftheta_bw" else 1, bw=[0.0, a1, 0.0, a3, 0.0, 0.0], fw=[0.0, f, 0.0, -0.04 * f, 0.0, 0.0],
+              cde=[1.0, 0.001, -0.002], max_angle=0.6, principal=(base.width / 2.0 - 0.5, base.height / 2.0 - 0.5))
+    return dataclasses.replace(base, fx=1.0, fy=1.0, ftheta=ft)
+
+
+@pytest.mark.parametrize("cam_index,model", [(1, "fisheye"), (4, "fisheye"), (2, "ftheta_bw"), (5, "ftheta_fw")])
+def test_fisheye_camera_parity(cam_index, model):
+    """OpenCV fisheye (cameraProjections.cuh:120-146) and f-theta (:148-198) sensors with rays of the same camera.  The projections
+    call atan2f, which is not correctly rounded on either side (CUDA <= 2 ulp, glibc <= 1 ulp), so the integer artefacts are compared
+    per particle instead of bit for bit as a whole: tile counts equal on >= 99.9 % of the particles, depth bits (no atan2f involved)
+    exactly equal.  (ftheta_fw: the rays come from the backward polynomial while the projection uses the forward one, which is only
+    its low-order inverse -- both sides see the same inconsistency.)"""
+    sc = _wide_angle_scene(model)
     c2w = sc.camera(cam_index, 10)
     ref = oracle_frame(sc, c2w, seed=cam_index, pose=tracer_pose(c2w))
     assert ref["pr"].tiles_count.sum() > 500  # (rejections by the valid cone are pinned on the CPU: tests/test_oracle_vs_ref.py)
     tr, g, out, dbg = _run(sc, c2w, ref)
     same = dbg["count"] == ref["pr"].tiles_count
-    print(f"[parity] fisheye cam{cam_index}: tile counts equal on {same.mean() * 100:.3f} % of the particles")
+    print(f"[parity] {model} cam{cam_index}: tile counts equal on {same.mean() * 100:.3f} % of the particles")
     assert same.mean() >= 0.999
     assert np.array_equal(dbg["depth"].view(np.uint32)[same & (dbg["count"] > 0)], ref["pr"].depth.view(np.uint32)[same & (dbg["count"] > 0)])
     if same.all():
         assert np.array_equal(dbg["keys"], ref["bn"].sorted_keys) and np.array_equal(dbg["vals"], ref["bn"].sorted_values)
     rgba = torch.cat([out["pred_features"], out["pred_opacity"]], -1)[0].detach().cpu().numpy()
     P = rgba.shape[0] * rgba.shape[1]
-    mean_e, max_e, bad = image_error_report(f"fisheye cam{cam_index} rgba", rgba, ref["rgba"])
+    mean_e, max_e, bad = image_error_report(f"{model} cam{cam_index} rgba", rgba, ref["rgba"])
     assert mean_e <= 1e-5 and bad <= max(3, int(2e-4 * P)) + 16 * int((~same).sum())
     if same.all():
         dp = ref["dp"]
         errs = dict(pos=rel_l2(g.positions.grad.cpu().numpy(), dp[:, 0:3]), dns=rel_l2(g._dns.grad.cpu().numpy(), dp[:, 3:4]),
                     quat=rel_l2(g._rot.grad.cpu().numpy(), dp[:, 4:8]), scl=rel_l2(g._scl.grad.cpu().numpy(), dp[:, 8:11]),
                     sph=rel_l2(g._sph.grad.cpu().numpy(), ref["ds"]))
-        print("[parity] fisheye cam%d gradient rel-L2:" % cam_index, {k: f"{v:.2e}" for k, v in errs.items()})
+        print("[parity] %s cam%d gradient rel-L2:" % (model, cam_index), {k: f"{v:.2e}" for k, v in errs.items()})
         assert max(errs.values()) <= 1e-3

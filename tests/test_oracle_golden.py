@@ -55,6 +55,21 @@ def test_fisheye_projection_matches_reference_fixture():
             assert np.array_equal(bn.unsorted_keys, z[f"keys{i}"]) and np.array_equal(bn.unsorted_values, z[f"vals{i}"])
 
 
+def test_ftheta_projection_matches_reference_fixture():
+    """f-theta model, same libm caveat as the fisheye fixture."""
+    z = np.load(os.path.join(G, "gut_projection_ftheta_ref.npz"))
+    cfg = go.default_config()
+    ft = dict(reference_poly=0, bw=z["bw"], fw=z["fw"], cde=z["cde"], max_angle=float(z["max_angle"]), principal=tuple(float(v) for v in z["principal"]))
+    for i in range(3):
+        cam = go.make_camera(int(z["width"]), int(z["height"]), 1.0, 1.0, 0.0, 0.0, z[f"pose{i}"], ftheta=ft)
+        pr = go.project(cfg, cam, z["particles"], z["sph"], 3)
+        same = pr.tiles_count == z[f"tiles_count{i}"]
+        assert same.mean() >= 0.999 and (z[f"tiles_count{i}"] == 0).sum() > 0 and z[f"tiles_count{i}"].sum() > 100
+        vis = same & (pr.tiles_count > 0)
+        for k in ("proj_pos", "conic_opacity", "extent"):
+            assert np.allclose(getattr(pr, k)[vis], z[f"{k}{i}"][vis], rtol=1e-5, atol=1e-5), k
+
+
 def test_single_hit_forward_and_adjoint_match_reference_fixture():
     rows = np.load(os.path.join(G, "gut_hits_ref.npz"))["rows"]
     cfg = go.default_config()

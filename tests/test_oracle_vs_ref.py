@@ -73,6 +73,39 @@ def test_fisheye_projection_bit_identical(cam_index):
     assert not np.array_equal(pin.proj_pos, pr.proj_pos)
 
 
+def _ftheta(width, height, reference_poly):
+    """equidistant-like f-theta camera: backward polynomial theta = a1 r + a3 r^3, forward its low-order inverse"""
+    f = 1.2 * width
+    a1, a3 = 1.0 / f, 0.04 / f ** 3
+    return dict(reference_poly=reference_poly, bw=[0.0, a1, 0.0, a3, 0.0, 0.0], fw=[0.0, f, 0.0, -0.04 * f, 0.0, 0.0], cde=[1.0, 0.001, -0.002],
+                max_angle=0.36, principal=(width / 2.0 - 0.5, height / 2.0 - 0.5))
+
+
+@pytest.mark.parametrize("reference_poly", [0, 1])
+@pytest.mark.parametrize("cam_index", range(3))
+def test_ftheta_projection_bit_identical(cam_index, reference_poly):
+    """f-theta model (cameraProjections.cuh:148-198), both reference polynomials (Newton inversion of the backward polynomial /
+    direct forward polynomial), through projection + key expansion: bit-identical with the reference's code compiled for the host."""
+    sc = scenes.scene_c1(bands=True)
+    cfg = go.default_config()
+    pose = scenes.pose7_from_c2w(sc.camera(cam_index, 3))
+    ft = _ftheta(sc.width, sc.height, reference_poly)
+    cam = go.make_camera(sc.width, sc.height, 1.0, 1.0, 0.0, 0.0, pose, ftheta=ft)
+    pr = go.project(cfg, cam, sc.particles, sc.sph, 3)
+    gr.set_ftheta(ft)
+    try:
+        rf = gr.project(sc.particles, sc.sph, 3, sc.width, sc.height, [1.0, 1.0], list(ft["principal"]), pose, pose)
+        keys, vals = gr.expand(sc.width, sc.height, rf["tiles_count"], rf["proj_pos"], rf["conic_opacity"], rf["extent"], rf["depth"])
+    finally:
+        gr.set_camera_model(None)
+    assert pr.tiles_count.sum() > 500 and (pr.tiles_count == 0).sum() > 0
+    assert np.array_equal(pr.tiles_count, rf["tiles_count"])
+    for k in ("proj_pos", "conic_opacity", "extent"):
+        assert np.array_equal(getattr(pr, k), rf[k]), k
+    bn = go.bin_tiles(cfg, cam, pr)
+    assert np.array_equal(keys, bn.unsorted_keys) and np.array_equal(vals, bn.unsorted_values)
+
+
 def test_sensor_pose_maths_identical():
     sc = scenes.scene_c1()
     for i in range(8):
