@@ -20,6 +20,7 @@ class Camera(C.Structure):
         ("pose_start", C.c_float * 7), ("pose_end", C.c_float * 7),
         ("model", C.c_int32), ("max_angle", C.c_float),
         ("ftheta_reference_poly", C.c_int32), ("ftheta_bw", C.c_float * 6), ("ftheta_fw", C.c_float * 6), ("ftheta_cde", C.c_float * 3),
+        ("rolling_shutter", C.c_int32),
     ]
 
 
@@ -32,7 +33,8 @@ class Config(C.Structure):
         ("ut_alpha", C.c_float), ("ut_beta", C.c_float), ("ut_kappa", C.c_float), ("ut_delta", C.c_float),
         ("ut_margin", C.c_float),
         ("rect_bounding", C.c_int32), ("tight_opacity_bounding", C.c_int32), ("tile_culling", C.c_int32),
-        ("global_z_order", C.c_int32), ("enable_timings", C.c_int32), ("subtile_culling", C.c_int32),
+        ("global_z_order", C.c_int32), ("enable_timings", C.c_int32), ("n_rolling_shutter_iterations", C.c_int32),
+        ("subtile_culling", C.c_int32),
     ]
 
 

@@ -232,6 +232,11 @@ void fill_frame(gutb200_ctx* c, const gutb200_camera* cam) {
     for (int cc = 0; cc < 3; ++cc)
         for (int k = 0; k < 3; ++k) f.rot_start[cc * 3 + k] = rs.m[cc][k];
     for (int k = 0; k < 3; ++k) f.t_start[k] = ps.t[k];
+    f.rolling_shutter = cam->rolling_shutter;
+    f.rs_iterations = c->cfg.n_rolling_shutter_iterations;
+    f.q_start[0] = ps.q.w; f.q_start[1] = ps.q.x; f.q_start[2] = ps.q.y; f.q_start[3] = ps.q.z;
+    f.q_end[0] = pe.q.w; f.q_end[1] = pe.q.x; f.q_end[2] = pe.q.y; f.q_end[3] = pe.q.z;
+    for (int k = 0; k < 3; ++k) f.t_end[k] = pe.t[k];
     // pose at mid exposure (gutRenderer.cu:266-267)
     Pose mid;
     mid.q = slerp(ps.q, pe.q, 0.5f);
@@ -265,6 +270,7 @@ void fill_frame(gutb200_ctx* c, const gutb200_camera* cam) {
 int check_args(gutb200_ctx* c, const gutb200_camera* cam, int64_t n, const void* particles) {
     if (!c) return 1;
     if (!cam || cam->width <= 0 || cam->height <= 0) return fail(c, "invalid camera resolution");
+    if (cam->rolling_shutter < 0 || cam->rolling_shutter > 4) return fail(c, "rolling_shutter %d out of range (0 global, 1..4 readout directions)", cam->rolling_shutter);
     if (cam->model < 0 || cam->model > 2) return fail(c, "camera model %d unknown (0 = OpenCV pinhole, 1 = OpenCV fisheye, 2 = f-theta)", cam->model);
     if (n < 0 || n > 0x7FFFFFFF) return fail(c, "particle count %lld out of range", static_cast<long long>(n));
     if (reinterpret_cast<uintptr_t>(particles) & 15) return fail(c, "particle buffer must be 16-byte aligned");
@@ -339,6 +345,7 @@ void gutb200_default_config(gutb200_config* c) {  // configs/render/3dgut.yaml, 
     c->global_z_order = 1;
     c->enable_timings = 0;
     c->subtile_culling = 3;  // bit 0: renderBackward, bit 1: render
+    c->n_rolling_shutter_iterations = 5;  // configs/render/3dgut.yaml:18
     if (const char* e = std::getenv("GUTB200_SUBTILE_CULLING")) c->subtile_culling = std::atoi(e);  // A/B switch for profiling
 }
 

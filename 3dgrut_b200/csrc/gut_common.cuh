@@ -27,6 +27,10 @@ struct FrameCamera {
     float max_angle;      // fisheye / f-theta: half-angle of the valid cone
     int ft_reference_poly;          // f-theta (model 2): 0 backward polynomial is the reference, 1 forward
     float ft_bw[6], ft_fw[6], ft_cde[3];
+    // rolling shutter (projectPointWithShutter, cameraProjections.cuh:218-257): 0 global, 1..4 = readout top-to-bottom, left-to-right,
+    // bottom-to-top, right-to-left; poses at shutter open / close as quaternion (wxyz) + translation
+    int rolling_shutter, rs_iterations;
+    float q_start[4], q_end[4], t_end[3];
 };
 
 struct FrameConfig {

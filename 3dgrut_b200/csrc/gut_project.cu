@@ -167,20 +167,86 @@ __device__ __forceinline__ bool project_ftheta(const FrameCamera& cam, float tol
     return (theta < cam.max_angle) && (ox > -mx0) && (oy > -my0) && (ox < cam.res_x + mx0) && (oy < cam.res_y + my0);
 }
 
-// world point -> pixel with the shutter-open pose (global shutter branch, cameraProjections.cuh:225-232)
-__device__ __forceinline__ bool project_world(const FrameCamera& cam, float tol, float px, float py, float pz, float& ox, float& oy) {
+__device__ __forceinline__ bool project_sensor(const FrameCamera& cam, float tol, float sx, float sy, float sz, float& ox, float& oy) {
+    if (cam.model == 1) return project_fisheye(cam, tol, sx, sy, sz, ox, oy);
+    if (cam.model == 2) return project_ftheta(cam, tol, sx, sy, sz, ox, oy);
+    return project_pinhole(cam, tol, sx, sy, sz, ox, oy);
+}
+
+// column-major rotation (m[c*3+r]) applied like tcnn's tmat * tvec (vec.h:595-605), then the translation
+__device__ __forceinline__ bool project_with_rotation(const FrameCamera& cam, float tol, const float* rot, const float* t, float px, float py,
+                                                      float pz, float& ox, float& oy) {
     float s[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         float acc = 0.f;
-        acc += cam.rot_start[0 * 3 + j] * px;
-        acc += cam.rot_start[1 * 3 + j] * py;
-        acc += cam.rot_start[2 * 3 + j] * pz;
-        s[j] = acc + cam.t_start[j];
+        acc += rot[0 * 3 + j] * px;
+        acc += rot[1 * 3 + j] * py;
+        acc += rot[2 * 3 + j] * pz;
+        s[j] = acc + t[j];
     }
-    if (cam.model == 1) return project_fisheye(cam, tol, s[0], s[1], s[2], ox, oy);
-    if (cam.model == 2) return project_ftheta(cam, tol, s[0], s[1], s[2], ox, oy);
-    return project_pinhole(cam, tol, s[0], s[1], s[2], ox, oy);
+    return project_sensor(cam, tol, s[0], s[1], s[2], ox, oy);
+}
+
+// tcnn::to_mat3 (vec.h:1185-1199), column major
+__device__ __forceinline__ void quat_to_mat3(float w, float x, float y, float z, float* m) {
+    const float qxx = x * x, qyy = y * y, qzz = z * z;
+    const float qxz = x * z, qxy = x * y, qyz = y * z;
+    const float qwx = w * x, qwy = w * y, qwz = w * z;
+    m[0] = 1.f - 2.f * (qyy + qzz); m[1] = 2.f * (qxy + qwz); m[2] = 2.f * (qxz - qwy);
+    m[3] = 2.f * (qxy - qwz); m[4] = 1.f - 2.f * (qxx + qzz); m[5] = 2.f * (qyz + qwx);
+    m[6] = 2.f * (qxz + qwy); m[7] = 2.f * (qyz - qwx); m[8] = 1.f - 2.f * (qxx + qyy);
+}
+
+// pose at relative exposure time alpha: tcnn::slerp (vec.h:1146-1167) + tcnn::mix (vec.h:183), then project
+__device__ __noinline__ bool project_at_time(const FrameCamera& cam, float tol, float alpha, float px, float py, float pz, float& ox, float& oy) {
+    const float* a = cam.q_start;
+    float zw = cam.q_end[0], zx = cam.q_end[1], zy = cam.q_end[2], zz = cam.q_end[3];
+    float c = (a[0] * zw + a[1] * zx) + (a[2] * zy + a[3] * zz);
+    if (c < 0.f) {
+        zw = -zw; zx = -zx; zy = -zy; zz = -zz;
+        c = -c;
+    }
+    float qw, qx, qy, qz;
+    if (c > 1.f - 1.1920929e-07f) {
+        const float k = 1.f - alpha;
+        qw = a[0] * k + zw * alpha; qx = a[1] * k + zx * alpha; qy = a[2] * k + zy * alpha; qz = a[3] * k + zz * alpha;
+    } else {
+        const float ang = acosf(c);
+        const float s0 = sinf((1.f - alpha) * ang), s1 = sinf(alpha * ang), sd = sinf(ang);
+        qw = (s0 * a[0] + s1 * zw) / sd; qx = (s0 * a[1] + s1 * zx) / sd; qy = (s0 * a[2] + s1 * zy) / sd; qz = (s0 * a[3] + s1 * zz) / sd;
+    }
+    float rot[9], t[3];
+    quat_to_mat3(qw, qx, qy, qz, rot);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t[k] = cam.t_start[k] * (1.f - alpha) + cam.t_end[k] * alpha;
+    return project_with_rotation(cam, tol, rot, t, px, py, pz, ox, oy);
+}
+
+// relativeShutterTime (cameraProjections.cuh:50-65)
+__device__ __forceinline__ float relative_shutter_time(const FrameCamera& cam, float x, float y) {
+    switch (cam.rolling_shutter) {
+        case 1: return floorf(y) / (cam.res_y - 1.f);
+        case 2: return floorf(x) / (cam.res_x - 1.f);
+        case 3: return (cam.res_y - ceilf(y)) / (cam.res_y - 1.f);
+        case 4: return (cam.res_x - ceilf(x)) / (cam.res_x - 1.f);
+        default: return 0.5f;
+    }
+}
+
+// world point -> pixel: projectPointWithShutter (cameraProjections.cuh:218-257).  Global shutter: the shutter-open pose only.
+template <bool ROLLING>
+__device__ __forceinline__ bool project_world(const FrameCamera& cam, float tol, float px, float py, float pz, float& ox, float& oy) {
+    bool valid = project_with_rotation(cam, tol, cam.rot_start, cam.t_start, px, py, pz, ox, oy);
+    if (!ROLLING || cam.rolling_shutter == 0) return valid;
+    if (!valid) {
+        float rot[9];
+        quat_to_mat3(cam.q_end[0], cam.q_end[1], cam.q_end[2], cam.q_end[3], rot);
+        valid = project_with_rotation(cam, tol, rot, cam.t_end, px, py, pz, ox, oy);
+        if (!valid) return false;
+    }
+    for (int i = 0; i < cam.rs_iterations; ++i) valid = project_at_time(cam, tol, relative_shutter_time(cam, ox, oy), px, py, pz, ox, oy);
+    return valid;
 }
 
 constexpr float kC0 = 0.28209479177387814f;
@@ -226,6 +292,8 @@ __device__ __forceinline__ void sph_radiance(int deg, const float* __restrict__ 
 }
 
 // G1: one thread per particle (projectOnTiles -> GUTProjector::eval, gutProjector.cuh:217-322)
+// ROLLING = false is the global-shutter instantiation (no pose interpolation code, no stack frame)
+template <bool ROLLING>
 __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, FrameConfig cfg, int64_t n,
                                                                const float* __restrict__ particles,
                                                                const float* __restrict__ sph, int sph_degree,
@@ -278,17 +346,17 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
     if (in_range && !(opacity < cfg.min_alpha) && !(zc < 0.2f)) {
         float spx[7], spy[7];
         int nvalid = 0;
-        nvalid += project_world(cam, cfg.ut_margin, px, py, pz, spx[0], spy[0]) ? 1 : 0;
+        nvalid += project_world<ROLLING>(cam, cfg.ut_margin, px, py, pz, spx[0], spy[0]) ? 1 : 0;
         pcx = spx[0] * cfg.w0_mean;
         pcy = spy[0] * cfg.w0_mean;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const float f = cfg.ut_delta * scl[k];
             const float dx = rot[k][0] * f, dy = rot[k][1] * f, dz = rot[k][2] * f;
-            nvalid += project_world(cam, cfg.ut_margin, px + dx, py + dy, pz + dz, spx[k + 1], spy[k + 1]) ? 1 : 0;
+            nvalid += project_world<ROLLING>(cam, cfg.ut_margin, px + dx, py + dy, pz + dz, spx[k + 1], spy[k + 1]) ? 1 : 0;
             pcx += cfg.wi * spx[k + 1];
             pcy += cfg.wi * spy[k + 1];
-            nvalid += project_world(cam, cfg.ut_margin, px - dx, py - dy, pz - dz, spx[k + 4], spy[k + 4]) ? 1 : 0;
+            nvalid += project_world<ROLLING>(cam, cfg.ut_margin, px - dx, py - dy, pz - dz, spx[k + 4], spy[k + 4]) ? 1 : 0;
             pcx += cfg.wi * spx[k + 4];
             pcy += cfg.wi * spy[k + 4];
         }
@@ -551,7 +619,10 @@ void launch_project(cudaStream_t s, const FrameCamera& cam, const FrameConfig& c
                     float* visibility, uint32_t* ids) {
     if (n <= 0) return;
     const unsigned blocks = static_cast<unsigned>((n + kProjThreads - 1) / kProjThreads);
-    project_kernel<<<blocks, kProjThreads, 0, s>>>(cam, cfg, n, particles, sph, sph_degree, tiles_count, proj, depth, rgb, visibility, ids);
+    if (cam.rolling_shutter != 0)
+        project_kernel<true><<<blocks, kProjThreads, 0, s>>>(cam, cfg, n, particles, sph, sph_degree, tiles_count, proj, depth, rgb, visibility, ids);
+    else
+        project_kernel<false><<<blocks, kProjThreads, 0, s>>>(cam, cfg, n, particles, sph, sph_degree, tiles_count, proj, depth, rgb, visibility, ids);
 }
 
 void launch_expand(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const uint32_t* perm, const uint32_t* offsets,

@@ -48,8 +48,6 @@ class PolynomialType(enum.IntEnum):  # bindings.cpp:44-48
 def fromFThetaCameraModelParameters(resolution, shutter_type, principal_point, reference_poly, pixeldist_to_angle_poly, angle_to_pixeldist_poly,
                                     max_angle, linear_cde) -> CameraModelParameters:
     """bindings.cpp:86-101: f-theta camera (polynomials of 6 coefficients, linear term [c d; e 1])"""
-    if ShutterType(shutter_type) != ShutterType.GLOBAL:
-        raise NotImplementedError("rolling-shutter projection is not built yet (SURVEY 8f row 4); global shutter only")
     f32 = lambda a, n: np.asarray(a, dtype=np.float32).reshape(n)  # noqa: E731
     ft = dict(reference_poly=int(PolynomialType(reference_poly)), bw=f32(pixeldist_to_angle_poly, 6), fw=f32(angle_to_pixeldist_poly, 6),
               cde=f32(linear_cde, 3))
@@ -60,8 +58,6 @@ def fromFThetaCameraModelParameters(resolution, shutter_type, principal_point, r
 
 def fromOpenCVFisheyeCameraModelParameters(resolution, shutter_type, principal_point, focal_length, radial_coeffs, max_angle) -> CameraModelParameters:
     """bindings.cpp:68-84: OpenCV fisheye (equidistant + 4 radial coefficients, valid cone max_angle)"""
-    if ShutterType(shutter_type) != ShutterType.GLOBAL:
-        raise NotImplementedError("rolling-shutter projection is not built yet (SURVEY 8f row 4); global shutter only")
     f32 = lambda a, n: np.asarray(a, dtype=np.float32).reshape(n)  # noqa: E731
     radial6 = np.zeros(6, np.float32)
     radial6[:4] = f32(radial_coeffs, 4)
@@ -73,8 +69,6 @@ def fromOpenCVFisheyeCameraModelParameters(resolution, shutter_type, principal_p
 def fromOpenCVPinholeCameraModelParameters(resolution, shutter_type, principal_point, focal_length, radial_coeffs,
                                             tangential_coeffs, thin_prism_coeffs) -> CameraModelParameters:
     """bindings.cpp:50-66"""
-    if ShutterType(shutter_type) != ShutterType.GLOBAL:
-        raise NotImplementedError("rolling-shutter projection is not built yet (SURVEY 8f row 4); global shutter only")
     f32 = lambda a, n: np.asarray(a, dtype=np.float32).reshape(n)  # noqa: E731
     return CameraModelParameters(np.asarray(resolution, dtype=np.int64).reshape(2), ShutterType(shutter_type), f32(principal_point, 2),
                                  f32(focal_length, 2), f32(radial_coeffs, 6), f32(tangential_coeffs, 2), f32(thin_prism_coeffs, 4))
@@ -137,6 +131,7 @@ def _native_config(conf) -> native.Config:
     cfg.tile_culling = int(bool(_cfg_get(conf, "render.splat.tile_based_culling", True)))
     cfg.global_z_order = int(bool(_cfg_get(conf, "render.splat.global_z_order", True)))
     cfg.enable_timings = int(bool(_cfg_get(conf, "render.enable_kernel_timings", False)))
+    cfg.n_rolling_shutter_iterations = int(_cfg_get(conf, "render.splat.n_rolling_shutter_iterations", 5))
     if int(_cfg_get(conf, "render.splat.k_buffer_size", 0)) != 0:
         raise NotImplementedError("k_buffer_size > 0 (sorted 3DGUT) is not built yet (SURVEY 8f row 4)")
     if int(_cfg_get(conf, "render.particle_radiance_sph_degree", 3)) != 3:
@@ -174,6 +169,8 @@ class SplatRaster:
         cam.thin_prism[:] = [float(v) for v in sensor.thin_prism_coeffs]
         cam.pose_start[:] = [float(v) for v in pose_start]  # .cpu() as in toSensorState (splatRaster.cpp:108-116)
         cam.pose_end[:] = [float(v) for v in pose_end]
+        shutter = ShutterType(getattr(sensor, "shutter_type", ShutterType.GLOBAL))
+        cam.rolling_shutter = 0 if shutter == ShutterType.GLOBAL else int(shutter) + 1  # gutb200_camera.rolling_shutter
         cam.model = int(getattr(sensor, "model", 0))
         cam.max_angle = float(getattr(sensor, "max_angle", 0.0))
         ft = getattr(sensor, "ftheta", None)

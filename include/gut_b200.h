@@ -51,6 +51,10 @@ typedef struct gutb200_camera {
     float ftheta_bw[6];             /* pixeldist_to_angle_poly (backward) */
     float ftheta_fw[6];             /* angle_to_pixeldist_poly (forward)  */
     float ftheta_cde[3];            /* linear_cde */
+    int32_t rolling_shutter;        /* 0 global shutter; 1..4 = CameraModelParameters::ShutterType + 1 (cameraModels.h:49-57): rolling
+                                     * top-to-bottom, left-to-right, bottom-to-top, right-to-left.  Affects the projection only
+                                     * (projectPointWithShutter, cameraProjections.cuh:218-257); rays use the mid-exposure pose like the
+                                     * reference (gutRenderer.cu:266-267,406). */
 } gutb200_camera;
 
 /* Render configuration == the reference's compile-time -D constants (threedgut_tracer/setup_3dgut.py:64-95). */
@@ -65,6 +69,7 @@ typedef struct gutb200_config {
     int32_t rect_bounding, tight_opacity_bounding, tile_culling;
     int32_t global_z_order;
     int32_t enable_timings;   /* render.enable_kernel_timings (src/splatRaster.cpp:168-169); 2 = also per-stage events */
+    int32_t n_rolling_shutter_iterations; /* GAUSSIAN_N_ROLLING_SHUTTER_ITERATIONS (configs/render/3dgut.yaml:18): 5 */
     int32_t subtile_culling;  /* ours (no reference twin): exact-conservative sub-tile culling in render/renderBackward; 0 = off.
                                * Results are bit-identical either way (forward) -- the switch exists for the A/B test. */
 } gutb200_config;

@@ -71,6 +71,7 @@ void gut_oracle_default_config(gut_oracle_config* c) {
     c->tight_opacity_bounding = 1;
     c->tile_culling = 1;
     c->global_z_order = 1;
+    c->n_rolling_shutter_iterations = 5;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -404,14 +405,49 @@ static int project_ftheta(const gut_oracle_camera* cam, v3 p, float tol, float o
     return (theta < cam->max_angle) && within_resolution((float)cam->width, (float)cam->height, tol, out[0], out[1]);
 }
 
-/* projectPointWithShutter, global shutter branch: start pose only (cameraProjections.cuh:225-232) */
-static int project_world_point(const gut_oracle_camera* cam, const mat3c* rstart, const float tstart[3], v3 p,
-                               float tol, float out[2]) {
-    v3 s = mat3c_mul(rstart, p);
-    s = V3(s.x + tstart[0], s.y + tstart[1], s.z + tstart[2]);
+static int project_sensor_point(const gut_oracle_camera* cam, v3 s, float tol, float out[2]) { /* projectPoint(TSensorModel), :200-216 */
     if (cam->model == 1) return project_fisheye(cam, s, tol, out);
     if (cam->model == 2) return project_ftheta(cam, s, tol, out);
     return project_pinhole(cam, s, tol, out);
+}
+
+static int project_with_pose(const gut_oracle_camera* cam, quat q, const float t[3], v3 p, float tol, float out[2]) {
+    const mat3c r = quat_to_mat3(q);
+    v3 s = mat3c_mul(&r, p);
+    s = V3(s.x + t[0], s.y + t[1], s.z + t[2]);
+    return project_sensor_point(cam, s, tol, out);
+}
+
+/* relativeShutterTime (cameraProjections.cuh:50-65) */
+static float relative_shutter_time(const gut_oracle_camera* cam, const float pos[2]) {
+    const float rx = (float)cam->width, ry = (float)cam->height;
+    switch (cam->rolling_shutter) {
+        case 1: return floorf(pos[1]) / (ry - 1.f);
+        case 2: return floorf(pos[0]) / (rx - 1.f);
+        case 3: return (ry - ceilf(pos[1])) / (ry - 1.f);
+        case 4: return (rx - ceilf(pos[0])) / (rx - 1.f);
+        default: return 0.5f;
+    }
+}
+
+/* projectPointWithShutter (cameraProjections.cuh:218-257): start pose; for a rolling shutter fall back to the end pose when the
+ * start pose fails, then iterate pose(time of the projected row / column) -> projection */
+static int project_world_point(const gut_oracle_camera* cam, int iterations, const pose* ps, const pose* pe, v3 p, float tol,
+                               float out[2]) {
+    int valid = project_with_pose(cam, ps->q, ps->t, p, tol, out);
+    if (cam->rolling_shutter == 0) return valid;
+    if (!valid) {
+        valid = project_with_pose(cam, pe->q, pe->t, p, tol, out);
+        if (!valid) return 0;
+    }
+    for (int i = 0; i < iterations; ++i) {
+        const float alpha = relative_shutter_time(cam, out);
+        const quat q = quat_slerp(ps->q, pe->q, alpha);
+        float t[3];
+        for (int k = 0; k < 3; ++k) t[k] = ps->t[k] * (1.f - alpha) + pe->t[k] * alpha;  /* tcnn::mix (vec.h:183) */
+        valid = project_with_pose(cam, q, t, p, tol, out);
+    }
+    return valid;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -466,8 +502,8 @@ void gut_oracle_project(const gut_oracle_config* cfg, const gut_oracle_camera* c
                         float* conic_opacity, float* extent, float* depth, float* rgb, int32_t* visibility) {
     float view[12], inv[12], campos[3];
     gut_oracle_sensor_matrices(cam, view, inv, campos);
-    const pose ps = pose_from7(cam->pose_start);
-    const mat3c rstart = quat_to_mat3(ps.q);
+    const pose ps = pose_from7(cam->pose_start), pe = pose_from7(cam->pose_end);
+    const int rs_iters = cfg->n_rolling_shutter_iterations;
     const int gx = (cam->width + TILE - 1) / TILE, gy = (cam->height + TILE - 1) / TILE;
     const float D = 3.f;
     const float lambda = cfg->ut_alpha * cfg->ut_alpha * (D + cfg->ut_kappa) - D;
@@ -490,16 +526,16 @@ void gut_oracle_project(const gut_oracle_config* cfg, const gut_oracle_camera* c
             sray = sub3(g.pos, V3(campos[0], campos[1], campos[2]));
             float sp[7][2];
             int nvalid = 0;
-            nvalid += project_world_point(cam, &rstart, ps.t, g.pos, cfg->ut_margin, sp[0]);
+            nvalid += project_world_point(cam, rs_iters, &ps, &pe, g.pos, cfg->ut_margin, sp[0]);
             pc[0] = sp[0][0] * w0m;
             pc[1] = sp[0][1] * w0m;
             const float sc[3] = {g.scl.x, g.scl.y, g.scl.z};
             for (int k = 0; k < 3; ++k) {
                 const v3 delta = scl3(g.rot[k], cfg->ut_delta * sc[k]);
-                nvalid += project_world_point(cam, &rstart, ps.t, add3(g.pos, delta), cfg->ut_margin, sp[k + 1]);
+                nvalid += project_world_point(cam, rs_iters, &ps, &pe, add3(g.pos, delta), cfg->ut_margin, sp[k + 1]);
                 pc[0] += wi * sp[k + 1][0];
                 pc[1] += wi * sp[k + 1][1];
-                nvalid += project_world_point(cam, &rstart, ps.t, sub3(g.pos, delta), cfg->ut_margin, sp[k + 4]);
+                nvalid += project_world_point(cam, rs_iters, &ps, &pe, sub3(g.pos, delta), cfg->ut_margin, sp[k + 4]);
                 pc[0] += wi * sp[k + 4][0];
                 pc[1] += wi * sp[k + 4][1];
             }

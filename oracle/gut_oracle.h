@@ -40,6 +40,8 @@ typedef struct {
     float ftheta_bw[6];            /* pixeldistToAnglePoly (backward) */
     float ftheta_fw[6];            /* angleToPixeldistPoly (forward)  */
     float ftheta_cde[3];           /* linear_cde */
+    int32_t rolling_shutter;       /* 0 global shutter, 1..4 = TSensorModel::ShutterType + 1: rolling top-to-bottom, left-to-right,
+                                    * bottom-to-top, right-to-left (sensors/cameraModels.h:49-57) */
 } gut_oracle_camera;
 
 /* Render configuration = the reference's compile-time -D constants (setup_3dgut.py:64-95). */
@@ -53,6 +55,7 @@ typedef struct {
     float ut_margin;             /* GAUSSIAN_UT_IN_IMAGE_MARGIN_FACTOR    0.1       */
     int32_t rect_bounding, tight_opacity_bounding, tile_culling; /* all 1 */
     int32_t global_z_order;      /* 1 */
+    int32_t n_rolling_shutter_iterations; /* GAUSSIAN_N_ROLLING_SHUTTER_ITERATIONS 5 (configs/render/3dgut.yaml:18) */
 } gut_oracle_config;
 
 void gut_oracle_default_config(gut_oracle_config* cfg);

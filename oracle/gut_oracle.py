@@ -25,6 +25,7 @@ class Camera(C.Structure):
         ("pose_start", C.c_float * 7), ("pose_end", C.c_float * 7),
         ("model", C.c_int32), ("max_angle", C.c_float),
         ("ftheta_reference_poly", C.c_int32), ("ftheta_bw", C.c_float * 6), ("ftheta_fw", C.c_float * 6), ("ftheta_cde", C.c_float * 3),
+        ("rolling_shutter", C.c_int32),
     ]
 
 
@@ -35,7 +36,7 @@ class Config(C.Structure):
         ("ut_alpha", C.c_float), ("ut_beta", C.c_float), ("ut_kappa", C.c_float), ("ut_delta", C.c_float),
         ("ut_margin", C.c_float),
         ("rect_bounding", C.c_int32), ("tight_opacity_bounding", C.c_int32), ("tile_culling", C.c_int32),
-        ("global_z_order", C.c_int32),
+        ("global_z_order", C.c_int32), ("n_rolling_shutter_iterations", C.c_int32),
     ]
 
 
@@ -73,7 +74,7 @@ def default_config() -> Config:
     return cfg
 
 
-def make_camera(width, height, fx, fy, cx, cy, pose_start, pose_end=None, fisheye=None, ftheta=None) -> Camera:
+def make_camera(width, height, fx, fy, cx, cy, pose_start, pose_end=None, fisheye=None, ftheta=None, rolling_shutter=0) -> Camera:
     """fisheye: None (OpenCV pinhole) or (k1, k2, k3, k4, max_angle) for the OpenCV fisheye model.
     ftheta: None or dict(reference_poly=0|1, bw=[6], fw=[6], cde=[3], max_angle=..., principal=(px, py)) for the f-theta model."""
     cam = Camera()
@@ -94,6 +95,7 @@ def make_camera(width, height, fx, fy, cx, cy, pose_start, pose_end=None, fishey
         cam.ftheta_fw[:] = [float(v) for v in ftheta["fw"]]
         cam.ftheta_cde[:] = [float(v) for v in ftheta["cde"]]
         cam.max_angle = float(ftheta["max_angle"])
+    cam.rolling_shutter = int(rolling_shutter)  # 0 global, 1..4 = rolling top-to-bottom / left-to-right / bottom-to-top / right-to-left
     return cam
 
 

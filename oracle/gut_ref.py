@@ -59,6 +59,11 @@ def set_camera_model(fisheye=None):
         lib().ref_set_camera_model(C.c_int(1), _p(f))
 
 
+def set_rolling_shutter(kind=0):
+    """0 = global shutter, 1..4 = rolling top-to-bottom / left-to-right / bottom-to-top / right-to-left (the oracle's numbering)."""
+    lib().ref_set_shutter(C.c_int(4 if kind == 0 else kind - 1))
+
+
 def set_ftheta(ftheta):
     """f-theta model for the following project() calls (dict as in gut_oracle.make_camera); set_camera_model(None) resets."""
     v = _f(np.concatenate([ftheta["bw"], ftheta["fw"], ftheta["cde"], [ftheta["max_angle"]]]).astype(np.float32))

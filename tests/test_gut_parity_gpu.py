@@ -445,3 +445,47 @@ def test_fisheye_camera_parity(cam_index, model):
                     sph=rel_l2(g._sph.grad.cpu().numpy(), ref["ds"]))
         print("[parity] %s cam%d gradient rel-L2:" % (model, cam_index), {k: f"{v:.2e}" for k, v in errs.items()})
         assert max(errs.values()) <= 1e-3
+
+
+@pytest.mark.parametrize("kind", [1, 4])
+def test_rolling_shutter_parity(kind):
+    """Rolling shutter (projectPointWithShutter, cameraProjections.cuh:218-257; pinned on the CPU by
+    test_rolling_shutter_projection_bit_identical): sensor moving between shutter open and close, 5 pose / projection iterations per sigma
+    point.  The pose interpolation calls acosf / sinf (not correctly rounded on either side), so tile counts are compared per particle
+    (>= 99.9 % equal); the image is rendered with the mid-exposure pose on both sides."""
+    import b200_native as nat
+    from oracle import gut_oracle as go
+
+    sc = scenes.scene_c1()
+    p0 = scenes.pose7_from_c2w(sc.camera(1, 40))
+    p1 = scenes.pose7_from_c2w(sc.camera(2, 40))
+    cfg = go.default_config()
+    ocam = go.make_camera(sc.width, sc.height, sc.fx, sc.fy, sc.cx, sc.cy, p0, p1, rolling_shutter=kind)
+    ro, rd = sc.rays()
+    pr, bn, rgba_ref, dist_ref, hits_ref = go.forward_all(cfg, ocam, ro, rd, sc.particles, sc.sph, 3)
+    glob = go.project(cfg, go.make_camera(sc.width, sc.height, sc.fx, sc.fy, sc.cx, sc.cy, p0, p1), sc.particles, sc.sph, 3)
+    assert not np.array_equal(glob.tiles_count, pr.tiles_count)  # the shutter matters for this motion
+
+    ctx = nat.Context(nat.default_config(), 0)
+    cam = nat.Camera()
+    cam.width, cam.height = sc.width, sc.height
+    cam.principal[:] = [sc.cx, sc.cy]
+    cam.focal[:] = [sc.fx, sc.fy]
+    cam.pose_start[:] = [float(v) for v in p0]
+    cam.pose_end[:] = [float(v) for v in p1]
+    cam.rolling_shutter = kind
+    n, hw = sc.n, sc.width * sc.height
+    rgba, dist, hits, vis = (np.zeros((hw, 4), np.float32), np.zeros(hw, np.float32), np.zeros(hw, np.float32), np.zeros(n, np.float32))
+    p = lambda a: a.ctypes.data  # noqa: E731
+    ro_c, rd_c = np.ascontiguousarray(ro), np.ascontiguousarray(rd)
+    ctx.forward_host(cam, n, p(sc.particles), p(sc.sph), 3, p(ro_c), p(rd_c), p(rgba), p(dist), p(hits), p(vis))
+    count = ctx.debug_copy(nat.DBG_TILES_COUNT)
+    depth = ctx.debug_copy(nat.DBG_DEPTH)
+    same = count == pr.tiles_count
+    print(f"[parity] rolling shutter {kind}: tile counts equal on {same.mean() * 100:.3f} % of the particles")
+    assert same.mean() >= 0.999
+    vis_same = same & (count > 0)
+    assert np.array_equal(depth.view(np.uint32)[vis_same], pr.depth.view(np.uint32)[vis_same])
+    mean_e, max_e, bad = image_error_report(f"rolling shutter {kind} rgba", rgba.reshape(rgba_ref.shape), rgba_ref)
+    assert mean_e <= 1e-5 and bad <= max(3, int(2e-4 * hw)) + 16 * int((~same).sum())
+    ctx.close()

@@ -106,6 +106,36 @@ def test_ftheta_projection_bit_identical(cam_index, reference_poly):
     assert np.array_equal(keys, bn.unsorted_keys) and np.array_equal(vals, bn.unsorted_values)
 
 
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+@pytest.mark.parametrize("model", ["pinhole", "fisheye"])
+def test_rolling_shutter_projection_bit_identical(kind, model):
+    """projectPointWithShutter (cameraProjections.cuh:218-257) with a sensor that moves and rotates during the exposure: 5 iterations of
+    pose(time of the projected row / column) -> projection, for the four readout directions."""
+    sc = scenes.scene_c1(bands=True)
+    cfg = go.default_config()
+    p0 = scenes.pose7_from_c2w(sc.camera(1, 40))
+    p1 = scenes.pose7_from_c2w(sc.camera(2, 40))  # 9 degrees further along the orbit
+    fe = FISHEYE if model == "fisheye" else None
+    f = 1.2 * sc.width if model == "fisheye" else sc.fx
+    cam = go.make_camera(sc.width, sc.height, f, f, sc.cx, sc.cy, p0, p1, fisheye=fe, rolling_shutter=kind)
+    pr = go.project(cfg, cam, sc.particles, sc.sph, 3)
+    gr.set_camera_model(fe)
+    gr.set_rolling_shutter(kind)
+    try:
+        rf = gr.project(sc.particles, sc.sph, 3, sc.width, sc.height, [f, f], [sc.cx, sc.cy], p0, p1)
+    finally:
+        gr.set_rolling_shutter(0)
+        gr.set_camera_model(None)
+    assert pr.tiles_count.sum() > 500
+    assert np.array_equal(pr.tiles_count, rf["tiles_count"])
+    assert np.array_equal(pr.depth.view(np.uint32), rf["depth"].view(np.uint32))
+    for k in ("proj_pos", "conic_opacity", "extent"):
+        assert np.array_equal(getattr(pr, k), rf[k]), k
+    # the shutter really matters: the global-shutter projection of the same poses differs
+    glob = go.project(cfg, go.make_camera(sc.width, sc.height, f, f, sc.cx, sc.cy, p0, p1, fisheye=fe), sc.particles, sc.sph, 3)
+    assert not np.array_equal(glob.proj_pos, pr.proj_pos)
+
+
 def test_sensor_pose_maths_identical():
     sc = scenes.scene_c1()
     for i in range(8):
