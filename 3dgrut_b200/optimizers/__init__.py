@@ -86,19 +86,27 @@ class FusedGaussianAdam:
     (Tracer / SplatRaster.trace_bwd outputs, or the view-parallel exchange's) -- no autograd pass over the activations is needed."""
 
     def __init__(self, params: dict, lrs: dict, betas=(0.9, 0.999), eps=1e-15, selective=False):
-        self.params = {k: params[k] for k in GROUPS}
-        n = int(self.params["positions"].shape[0])
-        for (k, t), w in zip(self.params.items(), WIDTHS):
-            _check(t.data, k)
-            if tuple(t.shape) != (n, w):
-                raise RuntimeError(f"{k}: expected shape {(n, w)}, got {tuple(t.shape)}")
-        self.n = n
+        # the dict itself is kept (not copied) when it holds exactly the six groups: densification replaces the tensors inside it
+        self.params = params if set(params.keys()) == set(GROUPS) else {k: params[k] for k in GROUPS}
+        self._validate()
         self.lrs = {k: float(lrs[k]) for k in GROUPS}
         self.betas, self.eps, self.selective = (float(betas[0]), float(betas[1])), float(eps), bool(selective)
         self.exp_avg = {k: torch.zeros_like(t.data) for k, t in self.params.items()}
         self.exp_avg_sq = {k: torch.zeros_like(t.data) for k, t in self.params.items()}
         self.steps = 0
         _lib()
+
+    @property
+    def n(self) -> int:
+        return int(self.params["positions"].shape[0])
+
+    def _validate(self):
+        n = self.n
+        for k, w in zip(GROUPS, WIDTHS):
+            t = self.params[k]
+            _check(t.data, k)
+            if tuple(t.shape) != (n, w):
+                raise RuntimeError(f"{k}: expected shape {(n, w)}, got {tuple(t.shape)}")
 
     def _array(self, tensors):
         arr = (C.c_void_p * 6)()
@@ -110,6 +118,10 @@ class FusedGaussianAdam:
     def step(self, d_particles: torch.Tensor, d_sph: torch.Tensor, visibility: torch.Tensor | None = None):
         _check(d_particles, "d_particles")
         _check(d_sph, "d_sph")
+        self._validate()  # the tensors may have been replaced (densification); moments must have followed
+        for k in GROUPS:
+            if self.exp_avg[k].shape != self.params[k].shape or self.exp_avg_sq[k].shape != self.params[k].shape:
+                raise RuntimeError(f"{k}: optimizer state does not match the parameter shape {tuple(self.params[k].shape)}")
         if tuple(d_particles.shape) != (self.n, 12) or tuple(d_sph.shape) != (self.n, 48):
             raise RuntimeError("gradient shapes must be [N,12] and [N,48]")
         vis_ptr = None

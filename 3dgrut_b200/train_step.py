@@ -22,10 +22,11 @@ from threedgut_tracer.tracer import SplatRaster
 
 
 class GaussianTrainStep:
-    def __init__(self, params: dict, lrs: dict, conf=None, sph_degree: int = 3, selective: bool = False, group=None, eps: float = 1e-15):
-        """params: raw leaf tensors for optimizers.GROUPS (positions, density, rotation, scale, features_albedo, features_specular)."""
-        self.params = {k: params[k] for k in optimizers.GROUPS}
-        self.n = int(self.params["positions"].shape[0])
+    def __init__(self, params: dict, lrs: dict, conf=None, sph_degree: int = 3, selective: bool = False, group=None, eps: float = 1e-15,
+                 densify_conf=None, scene_extent: float = 1.0):
+        """params: raw leaf tensors for optimizers.GROUPS (positions, density, rotation, scale, features_albedo, features_specular).
+        densify_conf: a densify.DensifyConfig turns on the replica-consistent densification / pruning / density reset."""
+        self.params = {k: params[k] for k in optimizers.GROUPS}  # ONE dict shared with the optimizer and the densifier
         self.device = self.params["positions"].device
         self.sph_degree = int(sph_degree)
         self.group = group
@@ -34,6 +35,16 @@ class GaussianTrainStep:
         self.optimizer = optimizers.FusedGaussianAdam(self.params, lrs, eps=eps, selective=selective)
         self.exchange = view_parallel.CompactGradientExchange(self.raster, self.n, self.device, group=group)
         self.frame = 0
+        self.scene_extent = float(scene_extent)
+        self.densifier = None
+        if densify_conf is not None:
+            import densify
+
+            self.densifier = densify.GSDensifier(self.params, [self.optimizer.exp_avg, self.optimizer.exp_avg_sq], densify_conf, group=group)
+
+    @property
+    def n(self) -> int:
+        return int(self.params["positions"].shape[0])
 
     @torch.no_grad()
     def activated(self):
@@ -65,13 +76,23 @@ class GaussianTrainStep:
         d_dist = torch.zeros_like(dst)
         self.raster.trace_bwd_compact(self.frame, self.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose, rgba, d_rgba,
                                       dst, d_dist, out=self.exchange.out())
+        my_position = self.raster.sensor_position(sensor, pose, pose, W, H)
         if all_sensor_positions is None:
             if self.world != 1:
                 raise RuntimeError("all_sensor_positions is required when more than one rank trains")
-            all_sensor_positions = self.raster.sensor_position(sensor, pose, pose, W, H)[None]
+            all_sensor_positions = my_position[None]
+        if self.densifier is not None:
+            # this view's own position gradient, before the exchange (it is weighted by the distance to THIS view's sensor, gs.py:127-137);
+            # x world undoes the global-batch normalisation so that the thresholds keep their per-view meaning
+            self.densifier.update_gradient_buffer(self.exchange.d_particles[:, 0:3] * float(self.world), my_position)
         d_particles, d_sph = self.exchange.exchange(self.sph_degree, particles, np.asarray(all_sensor_positions, np.float32))
         if self.optimizer.selective and self.world > 1:
             dist.all_reduce(vis, op=dist.ReduceOp.MAX, group=self.group)  # visible in any view of the batch
         self.optimizer.step(d_particles, d_sph, visibility=vis if self.optimizer.selective else None)
         self.frame += 1
+        if self.densifier is not None and self.densifier.post_optimizer_step(self.frame, self.scene_extent):
+            # the number of Gaussians may have changed (identically on every rank): re-capacity the exchange buffers; the renderer's
+            # scratch grows by itself
+            if self.exchange.n != self.n:
+                self.exchange = view_parallel.CompactGradientExchange(self.raster, self.n, self.device, group=self.group)
         return loss
