@@ -26,6 +26,7 @@ UNITS = {
     "grt.cu": ["--use_fast_math"],
     # optimizer step: plain IEEE arithmetic (the reference plugin is built without fast-math, setup_optimizers.py)
     "gut_optim.cu": [],
+    "gut_loss.cu": [],
 }
 
 

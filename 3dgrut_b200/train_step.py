@@ -23,7 +23,7 @@ from threedgut_tracer.tracer import SplatRaster
 
 class GaussianTrainStep:
     def __init__(self, params: dict, lrs: dict, conf=None, sph_degree: int = 3, selective: bool = False, group=None, eps: float = 1e-15,
-                 densify_conf=None, scene_extent: float = 1.0):
+                 densify_conf=None, scene_extent: float = 1.0, lambda_l1: float = 1.0, lambda_ssim: float = 0.0):
         """params: raw leaf tensors for optimizers.GROUPS (positions, density, rotation, scale, features_albedo, features_specular).
         densify_conf: a densify.DensifyConfig turns on the replica-consistent densification / pruning / density reset."""
         self.params = {k: params[k] for k in optimizers.GROUPS}  # ONE dict shared with the optimizer and the densifier
@@ -35,6 +35,7 @@ class GaussianTrainStep:
         self.optimizer = optimizers.FusedGaussianAdam(self.params, lrs, eps=eps, selective=selective)
         self.exchange = view_parallel.CompactGradientExchange(self.raster, self.n, self.device, group=group)
         self.frame = 0
+        self.lambda_l1, self.lambda_ssim = float(lambda_l1), float(lambda_ssim)  # reference defaults: 0.8 / 0.2 (configs/base_gs.yaml:172-179)
         self.scene_extent = float(scene_extent)
         self.densifier = None
         if densify_conf is not None:
@@ -65,14 +66,21 @@ class GaussianTrainStep:
     @torch.no_grad()
     def step(self, rays_o, rays_d, sensor, pose, target_rgb, all_sensor_positions=None):
         """One optimisation step on this rank's view.  target_rgb: [H,W,3].  all_sensor_positions: [world,3] sensor positions of every
-        rank's view of this step in rank order (omit on a single GPU).  Returns this view's L1 loss (a device scalar)."""
+        rank's view of this step in rank order (omit on a single GPU).  Returns this view's loss (a device scalar)."""
         H, W = int(rays_o.shape[1]), int(rays_o.shape[2])
         particles, sph = self.activated()
         rgba, dst, hits, vis = self.raster.trace(self.frame, self.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose)
-        diff = rgba[..., :3] - target_rgb
-        loss = diff.abs().mean()
-        d_rgba = torch.zeros_like(rgba)
-        d_rgba[..., :3] = torch.sign(diff) / (diff.numel() * self.world)  # d mean|.| / d rgb, global-batch normalisation
+        if self.lambda_ssim != 0.0:
+            import losses
+
+            # lambda_l1 L1 + lambda_ssim (1 - SSIM) and its image gradient in two launches (gut_loss.cu); global-batch normalisation
+            loss, _, _, d_rgba = losses.image_loss(rgba, target_rgb.contiguous(), self.lambda_l1 / self.world, self.lambda_ssim / self.world)
+            loss = loss * self.world
+        else:
+            diff = rgba[..., :3] - target_rgb
+            loss = self.lambda_l1 * diff.abs().mean()
+            d_rgba = torch.zeros_like(rgba)
+            d_rgba[..., :3] = self.lambda_l1 * torch.sign(diff) / (diff.numel() * self.world)  # d mean|.| / d rgb, global-batch normalisation
         d_dist = torch.zeros_like(dst)
         self.raster.trace_bwd_compact(self.frame, self.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose, rgba, d_rgba,
                                       dst, d_dist, out=self.exchange.out())

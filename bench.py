@@ -231,6 +231,34 @@ def time_optimizer_step(torch, dev, n, flush, peak, peak_src, iters=20):
             "frac": ach / peak if peak else None, "peak_source": peak_src, "bound": "hbm"}
 
 
+def time_image_loss(torch, dev, H, W, flush, peak, peak_src, iters=20):
+    """Next-row measurement, beside the metric: lambda_l1 L1 + lambda_ssim (1 - SSIM) and its image gradient
+    (gut_loss.cu, two launches) at the workload's resolution.  Algorithmic bytes per pixel: 16 prediction + 12 target read twice, 36
+    derivative maps written and read, 16 gradient written = 116 B."""
+    import losses
+
+    g = torch.Generator(device=dev).manual_seed(3)
+    pred = torch.rand((H, W, 4), device=dev, generator=g)
+    tgt = torch.rand((H, W, 3), device=dev, generator=g)
+    out = torch.empty((H, W, 4), device=dev)
+    for _ in range(3):
+        losses.image_loss(pred, tgt, 0.8, 0.2, d_rgba=out)
+    ms = []
+    for i in range(iters):
+        flush.fill_(float(i))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        losses.image_loss(pred, tgt, 0.8, 0.2, d_rgba=out)
+        b.record()
+        torch.cuda.synchronize(dev)
+        ms.append(a.elapsed_time(b))
+    t = float(np.median(ms))
+    nbytes = 116 * H * W
+    ach = nbytes / (t * 1e-3) / 1e9
+    return {"kernel": "ssim_stats_kernel + loss_grad_kernel", "ms": t, "algorithmic_bytes": nbytes, "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak if peak else None, "peak_source": peak_src, "bound": "hbm (the 11x11 window makes it FP32-bound at this size)"}
+
+
 class HostFeed:
     """End-to-end input feed: every step's rays and target image are copied from pinned host memory on a copy stream
     while the previous step computes (what a DataLoader with pinned memory does), and every step's loss is read back
@@ -695,6 +723,7 @@ def main():
         }
         if world == 1:
             line["optimizer_step"] = time_optimizer_step(torch, dev, n, flush, peak, peak_src)
+            line["image_loss"] = time_image_loss(torch, dev, H, W, flush, peak, peak_src)
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             fps, _ = cpu_port_frames_per_s(sc, args.cpu_tile_stride, frames=1, warm=0)

@@ -120,6 +120,15 @@ int gutb200_gaussian_adam_step(void* stream, int64_t n, float* const* params6, f
                                const float* lr6, float b1, float b2, float eps, int64_t step, int32_t selective, const float* d_particles,
                                const float* d_sph, const float* visibility);
 
+/* Image loss of the training step and its gradient: loss = lambda_l1 mean|x - y| + lambda_ssim (1 - SSIM(x, y))
+ * (threedgrut/trainer.py:698-739, model/losses.py:20-33 -> fused_ssim(..., padding="valid"), third-party fused-ssim @ 1272e21).
+ * pred_rgba [H,W,4] (the renderer's output, channels 0..2 are used), target_rgb [H,W,3], d_rgba [H,W,4] = d loss / d pred with a zero
+ * alpha gradient (directly the d_rgba of gutb200_backward), sums2 [2] device floats = (sum |x - y|, sum of the SSIM map over the valid
+ * region): l1 = sums2[0] / (3 H W), ssim = sums2[1] / (3 (H-10) (W-10)).  scratch: gutb200_image_loss_scratch_bytes(H, W) device bytes. */
+size_t gutb200_image_loss_scratch_bytes(int32_t height, int32_t width);
+int gutb200_image_loss(void* stream, int32_t height, int32_t width, const float* pred_rgba, const float* target_rgb, float lambda_l1,
+                       float lambda_ssim, void* scratch, float* d_rgba, float* sums2);
+
 int gutb200_forward_host(gutb200_ctx* ctx, const gutb200_camera* cam, int64_t n, const float* particles,
                          const float* sph, int32_t sph_degree, const float* rays_o, const float* rays_d,
                          float* out_rgba, float* out_dist, float* out_hits, float* visibility);

@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-def test_short_fit_reduces_the_loss():
+@pytest.mark.parametrize("loss_weights", [(1.0, 0.0), (0.8, 0.2)])
+def test_short_fit_reduces_the_loss(loss_weights):
     import train_step
     from threedgut_tracer.tracer import ShutterType, fromOpenCVPinholeCameraModelParameters
 
@@ -39,7 +40,7 @@ def test_short_fit_reduces_the_loss():
     P2[:, 0:3] += 0.02 * torch.randn((sc.n, 3), device=dev, generator=gen)
     P2[:, 8:11] *= torch.exp(0.2 * torch.randn((sc.n, 3), device=dev, generator=gen))
     S2[:, 0:3] += 0.5 * torch.randn((sc.n, 3), device=dev, generator=gen)
-    fit = train_step.GaussianTrainStep(raw_from(P2, S2), lrs)
+    fit = train_step.GaussianTrainStep(raw_from(P2, S2), lrs, lambda_l1=loss_weights[0], lambda_ssim=loss_weights[1])
 
     def mean_loss():
         return float(np.mean([float((fit.render(rays_o, rays_d, sensor, p)[0][..., :3] - t).abs().mean()) for p, t in zip(views, targets)]))
