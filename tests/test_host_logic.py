@@ -60,3 +60,48 @@ def test_camera_parameters_from_batch_intrinsics():
     assert list(sensor.resolution) == [800, 800]
     assert np.allclose(sensor.focal_length, [1111.0, 1111.0], rtol=1e-5) and np.allclose(sensor.principal_point, [400, 400])
     assert np.allclose(poses.T_world_sensors[0], [0, 0, 0, 0, 0, 0, 1], atol=1e-7)
+
+
+def test_camera_factories_fill_the_native_camera():
+    """bindings.cpp:50-101 factories -> gutb200_camera fields (model, rolling_shutter, fisheye / f-theta parameters)."""
+    from threedgut_tracer.tracer import (PolynomialType, ShutterType, SplatRaster, Tracer, fromFThetaCameraModelParameters,
+                                         fromOpenCVFisheyeCameraModelParameters, fromOpenCVPinholeCameraModelParameters)
+
+    pose = np.array([0, 0, 0, 0, 0, 0, 1], np.float32)
+    pin = fromOpenCVPinholeCameraModelParameters(np.array([64, 48]), ShutterType.ROLLING_LEFT_TO_RIGHT, [32, 24], [50, 51], np.arange(6) * 0.01,
+                                                 [0.001, 0.002], [0.1, 0.2, 0.3, 0.4])
+    cam = SplatRaster._camera(pin, pose, pose, 64, 48)
+    assert cam.model == 0 and cam.rolling_shutter == 2 and abs(cam.radial[5] - 0.05) < 1e-7 and abs(cam.thin_prism[3] - 0.4) < 1e-7
+    glob = fromOpenCVPinholeCameraModelParameters(np.array([64, 48]), ShutterType.GLOBAL, [32, 24], [50, 51], np.zeros(6), np.zeros(2), np.zeros(4))
+    assert SplatRaster._camera(glob, pose, pose, 64, 48).rolling_shutter == 0
+    fe = fromOpenCVFisheyeCameraModelParameters(np.array([64, 48]), ShutterType.ROLLING_TOP_TO_BOTTOM, [32, 24], [40, 40], [0.1, 0.2, 0.3, 0.4], 1.5)
+    cam = SplatRaster._camera(fe, pose, pose, 64, 48)
+    assert cam.model == 1 and cam.rolling_shutter == 1 and abs(cam.max_angle - 1.5) < 1e-7 and abs(cam.radial[3] - 0.4) < 1e-7 and cam.radial[4] == 0
+    ft = fromFThetaCameraModelParameters(np.array([64, 48]), ShutterType.GLOBAL, [31.5, 23.5], PolynomialType.ANGLE_TO_PIXELDIST,
+                                         [0, 0.02, 0, 0, 0, 0], [0, 50, 0, 0, 0, 0], 1.2, [1.0, 0.0, 0.0])
+    cam = SplatRaster._camera(ft, pose, pose, 64, 48)
+    assert cam.model == 2 and cam.ftheta_reference_poly == 1 and abs(cam.ftheta_fw[1] - 50) < 1e-6 and abs(cam.ftheta_cde[0] - 1.0) < 1e-7
+    assert abs(cam.principal[0] - 31.5) < 1e-6
+
+    class Batch:  # the intrinsics dictionaries of threedgrut/datasets/protocols.py:24-43 as the tracer receives them
+        rays_in_world_space = False
+        T_to_world = np.eye(4, dtype=np.float32)[None]
+        T_to_world_end = None
+        intrinsics = None
+        intrinsics_OpenCVPinholeCameraModelParameters = None
+        intrinsics_OpenCVFisheyeCameraModelParameters = dict(resolution=np.array([64, 48]), shutter_type="ROLLING_BOTTOM_TO_TOP",
+                                                             principal_point=np.array([32, 24], np.float32), focal_length=np.array([40, 40], np.float32),
+                                                             radial_coeffs=np.zeros(4, np.float32), max_angle=1.0)
+
+    sensor, poses = Tracer._create_camera_parameters(Batch)
+    assert sensor.model == 1 and sensor.shutter_type == ShutterType.ROLLING_BOTTOM_TO_TOP
+    assert SplatRaster._camera(sensor, poses.T_world_sensors[0], poses.T_world_sensors[1], 64, 48).rolling_shutter == 3
+
+
+def test_densify_step_schedule_and_optimizer_groups_are_consistent():
+    import densify
+
+    assert densify.GROUPS == ("positions", "density", "rotation", "scale", "features_albedo", "features_specular")
+    c = densify.DensifyConfig()
+    fired = [s for s in range(1, 2001) if densify.check_step_condition(s, c.densify_start, c.densify_end, c.densify_frequency)]
+    assert fired == [600, 900, 1200, 1500, 1800]  # configs/strategy/gs.yaml: start 500, every 300
