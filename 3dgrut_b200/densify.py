@@ -181,7 +181,7 @@ class GSDensifier:
         self._apply(lambda name, p: torch.clamp(p, max=cap), lambda v: torch.zeros_like(v), names=("density",))
 
     # ---- gs.py:74-125: what runs after the optimizer step; returns True when the number of Gaussians may have changed
-    def post_optimizer_step(self, step: int, scene_extent: float) -> bool:
+    def post_optimizer_step(self, step: int, scene_extent: float, positions_lr: float = 0.0) -> bool:
         c, changed = self.conf, False
         if check_step_condition(step, c.densify_start, c.densify_end, c.densify_frequency):
             self.densify(scene_extent)
@@ -191,4 +191,141 @@ class GSDensifier:
             changed = True
         if check_step_condition(step, c.reset_start, c.densify_end, c.reset_frequency):
             self.reset_density()
+        return changed
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# MCMC strategy (threedgrut/strategy/mcmc.py:50-224, strategy/src/gaussian_mcmc.cu:36-70, configs/strategy/mcmc.yaml), replica-consistent:
+# every random draw (multinomial sampling of the relocation targets, the positional noise) comes from a generator all ranks seed
+# identically and every decision depends only on the (identical) parameters, so replicas stay bit-identical.
+
+@dataclass
+class MCMCConfig:  # configs/strategy/mcmc.yaml
+    binom_n_max: int = 51
+    opacity_threshold: float = 0.005
+    relocate_start: int = 500
+    relocate_end: int = 25000
+    relocate_frequency: int = 100
+    add_start: int = 500
+    add_end: int = 25000
+    add_frequency: int = 100
+    max_n_gaussians: int = 1_000_000
+    perturb_start: int = 0
+    perturb_end: int = 27500
+    perturb_frequency: int = 1
+    noise_lr: float = 500000.0
+    seed: int = 0
+
+
+def compute_relocation(opacities: torch.Tensor, scales: torch.Tensor, ratios: torch.Tensor, binoms: torch.Tensor):
+    """compute_relocation_kernel (gaussian_mcmc.cu:36-70), vectorised: new opacity 1 - (1 - o)^(1/n); new scale = o / denom * scale with
+    denom = sum_{i=1..n} sum_{k<i} C(i-1, k) (-1)^k / sqrt(k+1) * new_opacity^(k+1)."""
+    n_max = binoms.shape[0]
+    n = ratios.to(torch.int64).reshape(-1)
+    o = opacities.reshape(-1)
+    new_o = 1.0 - torch.pow(1.0 - o, 1.0 / n.to(o.dtype))
+    k = torch.arange(n_max, device=o.device)
+    coeff = torch.pow(-1.0, k.to(o.dtype)) / torch.sqrt(k.to(o.dtype) + 1.0)              # [K]
+    powers = torch.pow(new_o[:, None], (k + 1).to(o.dtype)[None, :])                         # [M, K]
+    cum_binoms = torch.cumsum(binoms, dim=0)                                                 # row i-1: sum_{j<i} C(j, k)
+    rows = cum_binoms[(n - 1).clamp(min=0, max=n_max - 1)]                                   # [M, K]
+    denom = (rows * coeff[None, :] * powers).sum(1)
+    return new_o.reshape(opacities.shape), (o / denom)[:, None] * scales
+
+
+class MCMCDensifier:
+    """Same contract as GSDensifier: operates on the raw parameter dict and the optimizer's moment dicts."""
+
+    def __init__(self, params: dict, moments: list, conf: MCMCConfig | None = None, group=None):
+        import math
+
+        self.params, self.moments, self.conf, self.group = params, moments, conf or MCMCConfig(), group
+        dev = params["positions"].device
+        n_max = int(self.conf.binom_n_max)
+        self.binoms = torch.tensor([[math.comb(n, k) if k <= n else 0 for k in range(n_max)] for n in range(n_max)], dtype=torch.float32, device=dev)
+        self.generator = torch.Generator(device=dev)
+        self.generator.manual_seed(int(self.conf.seed))
+
+    @property
+    def n(self) -> int:
+        return int(self.params["positions"].shape[0])
+
+    def update_gradient_buffer(self, positions_grad, sensor_position) -> None:  # the MCMC strategy keeps no gradient statistics
+        return None
+
+    def _sample(self, count: int, valid_indices: torch.Tensor | None):
+        """sample_new_gaussians (mcmc.py:188-222)"""
+        densities = torch.sigmoid(self.params["density"])
+        scales = torch.exp(self.params["scale"])
+        if valid_indices is None:
+            valid_indices = torch.arange(densities.shape[0], device=densities.device)
+        probabilities = densities[valid_indices].flatten()
+        picked = torch.multinomial(probabilities, count, replacement=True, generator=self.generator)
+        sampled = valid_indices[picked]
+        ratios = (torch.bincount(sampled)[sampled] + 1).clamp_(min=1, max=self.conf.binom_n_max).int()
+        new_o, new_s = compute_relocation(densities[sampled, 0], scales[sampled], ratios, self.binoms)
+        new_o = torch.clamp(new_o, max=1.0 - torch.finfo(torch.float32).eps, min=self.conf.opacity_threshold)
+        return sampled, torch.log(new_o / (1.0 - new_o))[:, None], torch.log(new_s)
+
+    @torch.no_grad()
+    def relocate(self) -> int:
+        """mcmc.py:104-131: dead Gaussians (opacity <= threshold) jump onto live ones sampled by opacity"""
+        densities = torch.sigmoid(self.params["density"])[:, 0]
+        dead = torch.where(densities <= self.conf.opacity_threshold)[0]
+        alive = torch.where(densities > self.conf.opacity_threshold)[0]
+        if len(dead) == 0 or len(alive) == 0:
+            return 0
+        sampled, new_d, new_s = self._sample(len(dead), alive)
+        for name in GROUPS:
+            p = self.params[name]
+            if name == "density":
+                p[sampled] = new_d
+            elif name == "scale":
+                p[sampled] = new_s
+            p[dead] = p[sampled]
+            for m in self.moments:
+                m[name][sampled] = 0
+        return int(len(dead))
+
+    @torch.no_grad()
+    def add(self) -> int:
+        """mcmc.py:133-160: grow by 5 % up to max_n_gaussians, new Gaussians are copies of opacity-sampled ones"""
+        cur = self.n
+        target = min(int(self.conf.max_n_gaussians), int(1.05 * cur))
+        count = max(0, target - cur)
+        if count == 0:
+            return 0
+        sampled, new_d, new_s = self._sample(count, None)
+        for name in GROUPS:
+            p = self.params[name]
+            if name == "density":
+                p[sampled] = new_d
+            elif name == "scale":
+                p[sampled] = new_s
+            self.params[name] = torch.cat([p, p[sampled]]).contiguous()
+            for m in self.moments:
+                m[name] = torch.cat([m[name], torch.zeros((count, *m[name].shape[1:]), dtype=m[name].dtype, device=m[name].device)]).contiguous()
+        return count
+
+    @torch.no_grad()
+    def perturb(self, positions_lr: float) -> None:
+        """mcmc.py:162-186: covariance-shaped noise on the positions, gated towards low-opacity Gaussians"""
+        scales = torch.exp(self.params["scale"])
+        R = quaternion_to_so3(self.params["rotation"])
+        S = torch.diag_embed(scales)
+        cov = R @ S @ S.transpose(1, 2) @ R.transpose(1, 2)
+        densities = torch.sigmoid(self.params["density"])
+        gate = 1 / (1 + torch.exp(-100 * ((1 - densities) - 0.995)))
+        pos = self.params["positions"]
+        noise = torch.randn(pos.shape, generator=self.generator, device=pos.device, dtype=pos.dtype) * gate * self.conf.noise_lr * positions_lr
+        pos.add_(torch.bmm(cov, noise.unsqueeze(-1)).squeeze(-1))
+
+    def post_optimizer_step(self, step: int, scene_extent: float = 1.0, positions_lr: float = 0.0) -> bool:
+        c, changed = self.conf, False
+        if check_step_condition(step, c.relocate_start, c.relocate_end, c.relocate_frequency):
+            self.relocate()
+        if check_step_condition(step, c.add_start, c.add_end, c.add_frequency):
+            changed = self.add() > 0
+        if check_step_condition(step, c.perturb_start, c.perturb_end, c.perturb_frequency):
+            self.perturb(positions_lr)
         return changed

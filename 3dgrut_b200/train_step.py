@@ -25,7 +25,8 @@ class GaussianTrainStep:
     def __init__(self, params: dict, lrs: dict, conf=None, sph_degree: int = 3, selective: bool = False, group=None, eps: float = 1e-15,
                  densify_conf=None, scene_extent: float = 1.0, lambda_l1: float = 1.0, lambda_ssim: float = 0.0):
         """params: raw leaf tensors for optimizers.GROUPS (positions, density, rotation, scale, features_albedo, features_specular).
-        densify_conf: a densify.DensifyConfig turns on the replica-consistent densification / pruning / density reset."""
+        densify_conf: a densify.DensifyConfig (GS strategy: clone / split / prune / reset) or densify.MCMCConfig (relocate / add / perturb)
+        turns on the replica-consistent strategy."""
         self.params = {k: params[k] for k in optimizers.GROUPS}  # ONE dict shared with the optimizer and the densifier
         self.device = self.params["positions"].device
         self.sph_degree = int(sph_degree)
@@ -41,7 +42,8 @@ class GaussianTrainStep:
         if densify_conf is not None:
             import densify
 
-            self.densifier = densify.GSDensifier(self.params, [self.optimizer.exp_avg, self.optimizer.exp_avg_sq], densify_conf, group=group)
+            cls = densify.MCMCDensifier if isinstance(densify_conf, densify.MCMCConfig) else densify.GSDensifier
+            self.densifier = cls(self.params, [self.optimizer.exp_avg, self.optimizer.exp_avg_sq], densify_conf, group=group)
 
     @property
     def n(self) -> int:
@@ -98,7 +100,7 @@ class GaussianTrainStep:
             dist.all_reduce(vis, op=dist.ReduceOp.MAX, group=self.group)  # visible in any view of the batch
         self.optimizer.step(d_particles, d_sph, visibility=vis if self.optimizer.selective else None)
         self.frame += 1
-        if self.densifier is not None and self.densifier.post_optimizer_step(self.frame, self.scene_extent):
+        if self.densifier is not None and self.densifier.post_optimizer_step(self.frame, self.scene_extent, positions_lr=self.optimizer.lrs["positions"]):
             # the number of Gaussians may have changed (identically on every rank): re-capacity the exchange buffers; the renderer's
             # scratch grows by itself
             if self.exchange.n != self.n:

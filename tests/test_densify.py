@@ -120,3 +120,53 @@ def test_replicas_stay_bit_identical_through_densification(tmp_path):
     assert a["positions"].shape[0] != 400  # something happened
     for k in a.files:
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_mcmc_relocation_formula_matches_the_reference_kernel_loops():
+    """compute_relocation vs gaussian_mcmc.cu:36-70 restated literally (double loops)."""
+    import math
+
+    rng = np.random.default_rng(0)
+    M, n_max = 64, 51
+    binoms = torch.tensor([[math.comb(n, k) if k <= n else 0 for k in range(n_max)] for n in range(n_max)], dtype=torch.float32)
+    o = torch.from_numpy(rng.uniform(0.01, 0.95, M).astype(np.float32))
+    s = torch.from_numpy(rng.uniform(0.01, 0.3, (M, 3)).astype(np.float32))
+    ratios = torch.from_numpy(rng.integers(1, 9, M).astype(np.int32))
+    new_o, new_s = densify.compute_relocation(o, s, ratios, binoms)
+    for idx in range(M):
+        n = int(ratios[idx])
+        no = 1.0 - (1.0 - float(o[idx])) ** (1.0 / n)
+        denom = 0.0
+        for i in range(1, n + 1):
+            for k in range(i):
+                denom += float(binoms[i - 1, k]) * ((-1.0) ** k / math.sqrt(k + 1)) * no ** (k + 1)
+        assert abs(float(new_o[idx]) - no) <= 1e-6
+        assert np.allclose(new_s[idx].numpy(), float(o[idx]) / denom * s[idx].numpy(), rtol=2e-4)
+
+
+def _mcmc_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params = _params()
+    params["density"][::7] = -8.0  # some dead Gaussians (opacity 3e-4)
+    moments = [_moments(params, 1), _moments(params, 2)]
+    d = densify.MCMCDensifier(params, moments, densify.MCMCConfig(seed=5))
+    dead_before = int((torch.sigmoid(params["density"]) <= 0.005).sum())
+    moved = d.relocate()
+    added = d.add()
+    d.perturb(1.6e-4)
+    np.savez(os.path.join(out_dir, f"mcmc{rank}.npz"), moved=moved, added=added, dead_before=dead_before,
+             dead_after=int((torch.sigmoid(params["density"]) <= 0.005).sum()), **{k: v.numpy() for k, v in params.items()},
+             m=moments[0]["positions"].numpy())
+    dist.destroy_process_group()
+
+
+def test_mcmc_relocate_add_perturb_and_replica_consistency(tmp_path):
+    world = 2
+    mp.spawn(_mcmc_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a, b = (np.load(tmp_path / f"mcmc{r}.npz") for r in range(world))
+    assert int(a["moved"]) == int(a["dead_before"]) > 0 and int(a["dead_after"]) == 0  # every dead Gaussian moved onto a live one
+    assert int(a["added"]) == 20 and a["positions"].shape[0] == 420                      # +5 %
+    assert np.all(a["m"][400:] == 0)                                                      # new Gaussians start with empty moments
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), k                                              # replicas bit-identical
