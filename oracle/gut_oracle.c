@@ -883,6 +883,78 @@ void gut_oracle_render_forward(const gut_oracle_config* cfg, const gut_oracle_ca
     }
 }
 
+/* G6 with a k-buffer (GAUSSIAN_K_BUFFER_SIZE = K > 0, "sorted" 3DGUT: renderers/gutKBufferRenderer.cuh:62-112 insert / closestHit,
+ * :150-225 processHitParticle forward branch, :274-352 evalKBuffer).  Hits enter a per-ray buffer of the K farthest-so-far hits sorted
+ * by hit distance; when it is full the closest one is composited before the new hit is inserted; the rest is composited in order at the
+ * end.  Groundwork for the next round: the CUDA path builds K = 0 only (threedgut_tracer/tracer.py raises for k_buffer_size > 0). */
+typedef struct { int idx; real t, alpha; } khit_t;
+
+void gut_oracle_render_forward_kbuffer(const gut_oracle_config* cfg, const gut_oracle_camera* cam, int32_t K, const float* rays_o,
+                                       const float* rays_d, const float* particles, const float* rgb, const uint32_t* svals,
+                                       const uint32_t* ranges, float* out_rgba, float* out_dist, float* out_hits) {
+    float view[12], inv[12], campos[3];
+    gut_oracle_sensor_matrices(cam, view, inv, campos);
+    const int W = cam->width, H = cam->height;
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    if (K < 1 || K > 64) return;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int tile = 0; tile < gx * gy; ++tile) {
+        if (tile % g_tile_stride) continue;
+        const int tx = tile % gx, ty = tile / gx;
+        const uint32_t b = ranges[tile * 2], e = ranges[tile * 2 + 1];
+        for (int py = ty * TILE; py < imin(H, (ty + 1) * TILE); ++py)
+            for (int px = tx * TILE; px < imin(W, (tx + 1) * TILE); ++px) {
+                const int64_t pix = px + (int64_t)W * py;
+                ray_t r = init_ray(inv, rays_o + pix * 3, rays_d + pix * 3);
+                out_rgba[pix * 4] = out_rgba[pix * 4 + 1] = out_rgba[pix * 4 + 2] = out_rgba[pix * 4 + 3] = 0.f;
+                out_dist[pix] = 1e06f;
+                out_hits[pix] = 0.f;
+                if (!r.alive) continue;
+                real T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, dist = 0.f;
+                uint32_t hits = 0;
+                int alive = 1, num = 0;
+                khit_t kb[64];
+                for (int i = 0; i < K; ++i) { kb[i].idx = -1; kb[i].t = -1.0f; kb[i].alpha = 0.f; }  /* InvalidHitT = -1 (:31) */
+#define KB_PROCESS(HIT)                                                                         \
+    do {                                                                                        \
+        const khit_t hp_ = (HIT);                                                               \
+        const real w_ = hp_.alpha * T;                                                          \
+        dist += hp_.t * w_;                                                                     \
+        T *= (1 - hp_.alpha);                                                                   \
+        if (w_ > 0.0f) {                                                                        \
+            cr += R_FMAX(rgb[hp_.idx * 3], 0.f) * w_;                                           \
+            cg += R_FMAX(rgb[hp_.idx * 3 + 1], 0.f) * w_;                                       \
+            cb += R_FMAX(rgb[hp_.idx * 3 + 2], 0.f) * w_;                                       \
+            hits++;                                                                             \
+        }                                                                                       \
+        if (T < cfg->min_transmittance) alive = 0;                                              \
+    } while (0)
+                for (uint32_t k = b; alive && k < e; ++k) {
+                    const uint32_t idx = svals[k];
+                    if (idx == INVALID_U32) break;
+                    const particle g = load_particle(particles + (int64_t)idx * 12);
+                    const hit_t h = eval_hit(cfg, &g, r.o, r.d);
+                    if (!h.accept) continue;
+                    const real t = hit_distance(&g, &h);
+                    if (!(t > r.tmin && t < r.tmax)) continue;
+                    khit_t hp = {(int)idx, t, h.galpha};
+                    const int full = (num == K);
+                    if (full) KB_PROCESS(kb[0]);          /* closestHit (:101-103) */
+                    /* insert (:78-92): when full the closest entry is overwritten, else the count grows; bubble towards the far end */
+                    if (full) kb[0].t = -1.0f; else num++;
+                    for (int i = K - 1; i >= 0; --i)
+                        if (hp.t > kb[i].t) { const khit_t tmp = kb[i]; kb[i] = hp; hp = tmp; }
+                }
+                for (int i = 0; alive && i < num; ++i) KB_PROCESS(kb[K - num + i]);   /* :337-345 */
+#undef KB_PROCESS
+                out_rgba[pix * 4] = cr; out_rgba[pix * 4 + 1] = cg; out_rgba[pix * 4 + 2] = cb;
+                out_rgba[pix * 4 + 3] = 1.0f - T;
+                out_dist[pix] = dist;
+                out_hits[pix] = (real)hits;
+            }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* G7 processHitBwd<degree,false,false> (models/gaussianParticles.cuh:484-751)                  */
 

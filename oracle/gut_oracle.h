@@ -91,6 +91,11 @@ void gut_oracle_render_forward(const gut_oracle_config* cfg, const gut_oracle_ca
                                const uint32_t* sorted_values, const uint32_t* ranges,
                                float* out_rgba /*[H,W,4]*/, float* out_dist /*[H,W]*/, float* out_hits /*[H,W]*/);
 
+/* G6 with GAUSSIAN_K_BUFFER_SIZE = K > 0 (sorted 3DGUT, gutKBufferRenderer.cuh:62-112,274-352); K <= 64 */
+void gut_oracle_render_forward_kbuffer(const gut_oracle_config* cfg, const gut_oracle_camera* cam, int32_t K, const float* rays_o,
+                                       const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
+                                       const uint32_t* ranges, float* out_rgba, float* out_dist, float* out_hits);
+
 /* G7+G8: renderBackward + projectBackward. grads: d_particles [N,12], d_sph [N,48] (zeroed inside). */
 void gut_oracle_render_backward(const gut_oracle_config* cfg, const gut_oracle_camera* cam,
                                 int64_t n, const float* rays_o, const float* rays_d,

@@ -179,6 +179,20 @@ def render_forward(cfg, cam, rays_o, rays_d, particles, pr: Projection, bn: Binn
     return rgba, dist, hits
 
 
+def render_forward_kbuffer(cfg, cam, k: int, rays_o, rays_d, particles, pr: Projection, bn: Binning, f64: bool = False):
+    """Sorted 3DGUT forward (GAUSSIAN_K_BUFFER_SIZE = k > 0, gutKBufferRenderer.cuh:62-112,274-352); groundwork, no CUDA twin yet."""
+    rays_o, rays_d, particles = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3), _f32(particles)
+    h, w = cam.height, cam.width
+    rgba = np.zeros((h, w, 4), np.float32)
+    dist = np.zeros((h, w, 1), np.float32)
+    hits = np.zeros((h, w, 1), np.float32)
+    sv = bn.sorted_values if bn.sorted_values.size else np.zeros(1, np.uint32)
+    lib(f64).gut_oracle_render_forward_kbuffer(C.byref(cfg), C.byref(cam), C.c_int32(int(k)), _p(rays_o, C.c_float), _p(rays_d, C.c_float),
+                                               _p(particles, C.c_float), _p(pr.rgb, C.c_float), _p(sv, C.c_uint32),
+                                               _p(bn.ranges, C.c_uint32), _p(rgba, C.c_float), _p(dist, C.c_float), _p(hits, C.c_float))
+    return rgba, dist, hits
+
+
 def render_backward(cfg, cam, rays_o, rays_d, particles, sph, sph_degree, pr, bn, rgba, dist, d_rgba, d_dist, f64: bool = False):
     rays_o, rays_d = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
     particles, sph = _f32(particles), _f32(sph)
