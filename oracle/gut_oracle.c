@@ -1103,12 +1103,12 @@ static void sh_dir_jacobian(int deg, const float* c, v3 d, real drgb_dx[3], real
     }
 }
 
-void gut_oracle_render_backward(const gut_oracle_config* cfg, const gut_oracle_camera* cam, int64_t n,
-                                const float* rays_o, const float* rays_d, const float* particles, const float* sph,
-                                int32_t sph_degree, const float* rgb, const uint32_t* tiles_count,
-                                const uint32_t* svals, const uint32_t* ranges, const float* out_rgba,
-                                const float* out_dist, const float* d_rgba, const float* d_dist, float* d_particles,
-                                float* d_sph) {
+static void render_backward_impl(const gut_oracle_config* cfg, const gut_oracle_camera* cam, int32_t K, int64_t n,
+                                 const float* rays_o, const float* rays_d, const float* particles, const float* sph,
+                                 int32_t sph_degree, const float* rgb, const uint32_t* tiles_count,
+                                 const uint32_t* svals, const uint32_t* ranges, const float* out_rgba,
+                                 const float* out_dist, const float* d_rgba, const float* d_dist, float* d_particles,
+                                 float* d_sph) {
     float view[12], inv[12], campos[3];
     gut_oracle_sensor_matrices(cam, view, inv, campos);
     const int W = cam->width, H = cam->height;
@@ -1142,19 +1142,56 @@ void gut_oracle_render_backward(const gut_oracle_config* cfg, const gut_oracle_c
                 const real Tgrad = -1.f * d_rgba[pix * 4 + 3];
                 const real Dint = out_dist[pix], Dgrad = d_dist[pix];
                 real T = 1.f, C[3] = {0.f, 0.f, 0.f}, Dp = 0.f;
-                for (uint32_t k = b; k < e; ++k) {
-                    const uint32_t idx = svals[k];
-                    if (idx == INVALID_U32) break;
-                    const particle g = load_particle(particles + (int64_t)idx * 12);
-                    const real prgb[3] = {R_FMAX(rgb[idx * 3], 0.f), R_FMAX(rgb[idx * 3 + 1], 0.f), R_FMAX(rgb[idx * 3 + 2], 0.f)};
-                    real grad[11], rg[3];
-                    if (hit_backward(cfg, &g, r.o, r.d, prgb, Tint, &T, Tgrad, Cint, C, Cgrad, Dint, &Dp, Dgrad, grad, rg)) {
-                        double* ai = a + (size_t)idx * 14;
-                        for (int q = 0; q < 11; ++q) ai[q] += (double)grad[q];
-                        for (int q = 0; q < 3; ++q) ai[11 + q] += (double)rg[q];
+#define BWD_PROCESS(IDX)                                                                                                          \
+    do {                                                                                                                          \
+        const uint32_t id_ = (IDX);                                                                                               \
+        const particle g_ = load_particle(particles + (int64_t)id_ * 12);                                                         \
+        const real prgb_[3] = {R_FMAX(rgb[id_ * 3], 0.f), R_FMAX(rgb[id_ * 3 + 1], 0.f), R_FMAX(rgb[id_ * 3 + 2], 0.f)};          \
+        real grad_[11], rg_[3];                                                                                                   \
+        if (hit_backward(cfg, &g_, r.o, r.d, prgb_, Tint, &T, Tgrad, Cint, C, Cgrad, Dint, &Dp, Dgrad, grad_, rg_)) {             \
+            double* ai_ = a + (size_t)id_ * 14;                                                                                   \
+            for (int q = 0; q < 11; ++q) ai_[q] += (double)grad_[q];                                                              \
+            for (int q = 0; q < 3; ++q) ai_[11 + q] += (double)rg_[q];                                                            \
+        }                                                                                                                         \
+    } while (0)
+                if (K == 0) {
+                    for (uint32_t k = b; k < e; ++k) {
+                        const uint32_t idx = svals[k];
+                        if (idx == INVALID_U32) break;
+                        BWD_PROCESS(idx);
+                        if (T < cfg->min_transmittance) break;
                     }
-                    if (T < cfg->min_transmittance) break;
+                } else {
+                    /* sorted variant: the same traversal as gut_oracle_render_forward_kbuffer, the per-hit adjoint applied in the
+                     * buffer's processing order (the exact gradient of that forward; the reference gets it from Slang autodiff,
+                     * gutKBufferRenderer.cuh:158-199) */
+                    khit_t kb[64];
+                    int num = 0, alive = 1;
+                    for (int i = 0; i < K; ++i) { kb[i].idx = -1; kb[i].t = -1.0f; kb[i].alpha = 0.f; }
+                    for (uint32_t k = b; alive && k < e; ++k) {
+                        const uint32_t idx = svals[k];
+                        if (idx == INVALID_U32) break;
+                        const particle g = load_particle(particles + (int64_t)idx * 12);
+                        const hit_t h = eval_hit(cfg, &g, r.o, r.d);
+                        if (!h.accept) continue;
+                        const real t = hit_distance(&g, &h);
+                        if (!(t > r.tmin && t < r.tmax)) continue;
+                        khit_t hp = {(int)idx, t, h.galpha};
+                        const int full = (num == K);
+                        if (full) {
+                            BWD_PROCESS((uint32_t)kb[0].idx);
+                            if (T < cfg->min_transmittance) alive = 0;
+                        }
+                        if (full) kb[0].t = -1.0f; else num++;
+                        for (int i = K - 1; i >= 0; --i)
+                            if (hp.t > kb[i].t) { const khit_t tmp = kb[i]; kb[i] = hp; hp = tmp; }
+                    }
+                    for (int i = 0; alive && i < num; ++i) {
+                        BWD_PROCESS((uint32_t)kb[K - num + i].idx);
+                        if (T < cfg->min_transmittance) alive = 0;
+                    }
                 }
+#undef BWD_PROCESS
             }
     }
 
@@ -1194,6 +1231,27 @@ void gut_oracle_render_backward(const gut_oracle_config* cfg, const gut_oracle_c
         }
     }
     free(acc);
+}
+
+void gut_oracle_render_backward(const gut_oracle_config* cfg, const gut_oracle_camera* cam, int64_t n,
+                                const float* rays_o, const float* rays_d, const float* particles, const float* sph,
+                                int32_t sph_degree, const float* rgb, const uint32_t* tiles_count,
+                                const uint32_t* svals, const uint32_t* ranges, const float* out_rgba,
+                                const float* out_dist, const float* d_rgba, const float* d_dist, float* d_particles,
+                                float* d_sph) {
+    render_backward_impl(cfg, cam, 0, n, rays_o, rays_d, particles, sph, sph_degree, rgb, tiles_count, svals, ranges, out_rgba, out_dist,
+                         d_rgba, d_dist, d_particles, d_sph);
+}
+
+void gut_oracle_render_backward_kbuffer(const gut_oracle_config* cfg, const gut_oracle_camera* cam, int32_t K, int64_t n,
+                                        const float* rays_o, const float* rays_d, const float* particles, const float* sph,
+                                        int32_t sph_degree, const float* rgb, const uint32_t* tiles_count,
+                                        const uint32_t* svals, const uint32_t* ranges, const float* out_rgba,
+                                        const float* out_dist, const float* d_rgba, const float* d_dist, float* d_particles,
+                                        float* d_sph) {
+    if (K < 1 || K > 64) return;
+    render_backward_impl(cfg, cam, K, n, rays_o, rays_d, particles, sph, sph_degree, rgb, tiles_count, svals, ranges, out_rgba, out_dist,
+                         d_rgba, d_dist, d_particles, d_sph);
 }
 
 /* single-hit backward exposed for pinning against processHitBwd compiled from the reference (oracle/ref_gut.cpp) */

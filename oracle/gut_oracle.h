@@ -106,6 +106,14 @@ void gut_oracle_render_backward(const gut_oracle_config* cfg, const gut_oracle_c
                                 const float* d_rgba, const float* d_dist,
                                 float* d_particles, float* d_sph);
 
+/* adjoint of gut_oracle_render_forward_kbuffer (per-hit adjoint in the buffer's processing order) + G8 */
+void gut_oracle_render_backward_kbuffer(const gut_oracle_config* cfg, const gut_oracle_camera* cam, int32_t K, int64_t n,
+                                        const float* rays_o, const float* rays_d, const float* particles, const float* sph,
+                                        int32_t sph_degree, const float* rgb, const uint32_t* tiles_count,
+                                        const uint32_t* sorted_values, const uint32_t* ranges, const float* out_rgba,
+                                        const float* out_dist, const float* d_rgba, const float* d_dist, float* d_particles,
+                                        float* d_sph);
+
 /* bench-only: render loops visit every k-th tile (bounded CPU sample of a full-size frame); default 1 */
 void gut_oracle_set_tile_stride(int k);
 

@@ -209,6 +209,23 @@ def render_backward(cfg, cam, rays_o, rays_d, particles, sph, sph_degree, pr, bn
     return dp, ds
 
 
+def render_backward_kbuffer(cfg, cam, k: int, rays_o, rays_d, particles, sph, sph_degree, pr, bn, rgba, dist, d_rgba, d_dist, f64: bool = False):
+    """Adjoint of render_forward_kbuffer (the per-hit adjoint applied in the buffer's processing order) + the SH adjoint."""
+    rays_o, rays_d = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
+    particles, sph = _f32(particles), _f32(sph)
+    rgba, dist, d_rgba, d_dist = _f32(rgba), _f32(dist), _f32(d_rgba), _f32(d_dist)
+    n = particles.shape[0]
+    dp = np.zeros((n, 12), np.float32)
+    ds = np.zeros((n, 48), np.float32)
+    sv = bn.sorted_values if bn.sorted_values.size else np.zeros(1, np.uint32)
+    lib(f64).gut_oracle_render_backward_kbuffer(C.byref(cfg), C.byref(cam), C.c_int32(int(k)), C.c_int64(n), _p(rays_o, C.c_float),
+                                                _p(rays_d, C.c_float), _p(particles, C.c_float), _p(sph, C.c_float), C.c_int32(sph_degree),
+                                                _p(pr.rgb, C.c_float), _p(pr.tiles_count, C.c_uint32), _p(sv, C.c_uint32),
+                                                _p(bn.ranges, C.c_uint32), _p(rgba, C.c_float), _p(dist, C.c_float),
+                                                _p(d_rgba, C.c_float), _p(d_dist, C.c_float), _p(dp, C.c_float), _p(ds, C.c_float))
+    return dp, ds
+
+
 def forward_all(cfg, cam, rays_o, rays_d, particles, sph, sph_degree):
     pr = project(cfg, cam, particles, sph, sph_degree)
     bn = bin_tiles(cfg, cam, pr)
