@@ -34,7 +34,7 @@ class Config(C.Structure):
         ("ut_margin", C.c_float),
         ("rect_bounding", C.c_int32), ("tight_opacity_bounding", C.c_int32), ("tile_culling", C.c_int32),
         ("global_z_order", C.c_int32), ("enable_timings", C.c_int32), ("n_rolling_shutter_iterations", C.c_int32),
-        ("subtile_culling", C.c_int32),
+        ("k_buffer_size", C.c_int32), ("subtile_culling", C.c_int32),
     ]
 
 

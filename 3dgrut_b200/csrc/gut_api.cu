@@ -265,6 +265,7 @@ void fill_frame(gutb200_ctx* c, const gutb200_camera* cam) {
     g.tile_culling = s.tile_culling;
     g.global_z_order = s.global_z_order;
     g.subtile_culling = s.subtile_culling;
+    g.k_buffer_size = s.k_buffer_size;
 }
 
 int check_args(gutb200_ctx* c, const gutb200_camera* cam, int64_t n, const void* particles) {
@@ -274,6 +275,10 @@ int check_args(gutb200_ctx* c, const gutb200_camera* cam, int64_t n, const void*
     if (cam->model < 0 || cam->model > 2) return fail(c, "camera model %d unknown (0 = OpenCV pinhole, 1 = OpenCV fisheye, 2 = f-theta)", cam->model);
     if (n < 0 || n > 0x7FFFFFFF) return fail(c, "particle count %lld out of range", static_cast<long long>(n));
     if (reinterpret_cast<uintptr_t>(particles) & 15) return fail(c, "particle buffer must be 16-byte aligned");
+    if (c->cfg.k_buffer_size < 0 || c->cfg.k_buffer_size > 16) return fail(c, "k_buffer_size %d out of range (0..16)", c->cfg.k_buffer_size);
+    if (c->cfg.k_buffer_size > 0 && !std::getenv("GUTB200_EXPERIMENTAL_KBUFFER"))
+        return fail(c, "k_buffer_size > 0 (sorted 3DGUT, gut_render_kbuffer.cu) is experimental: the kernels have not been verified on hardware "
+                       "yet; set GUTB200_EXPERIMENTAL_KBUFFER=1 to run them");
     if (c->cfg.kernel_degree != 2 && c->cfg.kernel_degree != 4) return fail(c, "kernel_degree %d not built (2 or 4)", c->cfg.kernel_degree);
     return 0;
 }
@@ -346,6 +351,7 @@ void gutb200_default_config(gutb200_config* c) {  // configs/render/3dgut.yaml, 
     c->enable_timings = 0;
     c->subtile_culling = 3;  // bit 0: renderBackward, bit 1: render
     c->n_rolling_shutter_iterations = 5;  // configs/render/3dgut.yaml:18
+    c->k_buffer_size = 0;                 // configs/render/3dgut.yaml: k_buffer_size 0 (unsorted)
     if (const char* e = std::getenv("GUTB200_SUBTILE_CULLING")) c->subtile_culling = std::atoi(e);  // A/B switch for profiling
 }
 
@@ -473,8 +479,12 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     {
         StageTimer t(c, 5, s);
         launch_tile_order(s, c->cam, c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>());
-        launch_render_forward(s, c->cam, c->fcfg, rays_o, rays_d, particles, c->rgb.as<float>(), c->vals_out.as<uint32_t>(),
-                              c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), out_rgba, out_dist, out_hits);
+        if (c->fcfg.k_buffer_size > 0)  // sorted 3DGUT (gut_render_kbuffer.cu)
+            launch_render_forward_kbuffer(s, c->cam, c->fcfg, c->fcfg.k_buffer_size, rays_o, rays_d, particles, c->rgb.as<float>(),
+                                          c->vals_out.as<uint32_t>(), c->ranges.as<uint32_t>(), out_rgba, out_dist, out_hits);
+        else
+            launch_render_forward(s, c->cam, c->fcfg, rays_o, rays_d, particles, c->rgb.as<float>(), c->vals_out.as<uint32_t>(),
+                                  c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), out_rgba, out_dist, out_hits);
     }
     c->launches += 2;
     GUT_CUDA(c, cudaGetLastError());
@@ -506,9 +516,14 @@ static int backward_impl(gutb200_ctx* c, void* stream, const gutb200_camera* cam
     GUT_CUDA(c, c->grad_acc.reserve(nn * kGradRow * 4, s, /*zero=*/true));
     if (c->num_isect > 0) {
         StageTimer t(c, 6, s);
-        launch_render_backward(s, c->cam, c->fcfg, rays_o, rays_d, particles, c->rgb.as<float>(), c->vals_out.as<uint32_t>(),
-                               c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), out_rgba, d_rgba, out_dist, d_dist,
-                               c->grad_acc.as<float>());
+        if (c->fcfg.k_buffer_size > 0)
+            launch_render_backward_kbuffer(s, c->cam, c->fcfg, c->fcfg.k_buffer_size, rays_o, rays_d, particles, c->rgb.as<float>(),
+                                           c->vals_out.as<uint32_t>(), c->ranges.as<uint32_t>(), out_rgba, d_rgba, out_dist, d_dist,
+                                           c->grad_acc.as<float>());
+        else
+            launch_render_backward(s, c->cam, c->fcfg, rays_o, rays_d, particles, c->rgb.as<float>(), c->vals_out.as<uint32_t>(),
+                                   c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), out_rgba, d_rgba, out_dist, d_dist,
+                                   c->grad_acc.as<float>());
         c->launches++;
     }
     if (n > 0) {

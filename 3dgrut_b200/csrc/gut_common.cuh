@@ -40,6 +40,7 @@ struct FrameConfig {
     float w0_mean, wi, w0_cov;   // unscented-transform weights (gutProjector.cuh:150,163,201)
     int rect_bounding, tight_opacity_bounding, tile_culling, global_z_order;
     int subtile_culling;   // ours: conservative per-warp / per-pixel conic pre-test in the render kernels (gut_render.cu)
+    int k_buffer_size;     // GAUSSIAN_K_BUFFER_SIZE: 0 (default) or 1..16 = sorted 3DGUT (gut_render_kbuffer.cu)
 };
 
 // Projection result of one particle consumed by the expand kernel: centre, extent, conic, opacity (32 B).
@@ -69,6 +70,12 @@ void launch_render_backward(cudaStream_t s, const FrameCamera& cam, const FrameC
                             const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
                             const uint32_t* ranges, const uint32_t* tile_order, const float* out_rgba, const float* d_rgba,
                             const float* out_dist, const float* d_dist, float* grad_acc);
+void launch_render_forward_kbuffer(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int K, const float* rays_o, const float* rays_d,
+                                   const float* particles, const float* rgb, const uint32_t* sorted_values, const uint32_t* ranges,
+                                   float* out_rgba, float* out_dist, float* out_hits);
+void launch_render_backward_kbuffer(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int K, const float* rays_o, const float* rays_d,
+                                    const float* particles, const float* rgb, const uint32_t* sorted_values, const uint32_t* ranges,
+                                    const float* out_rgba, const float* d_rgba, const float* out_dist, const float* d_dist, float* grad_acc);
 void launch_project_backward(cudaStream_t s, const FrameCamera& cam, int64_t n, const float* particles, const float* sph,
                              int sph_degree, const float* rgb, const uint32_t* tiles_count, float* grad_acc,
                              float* d_particles, float* d_sph, bool compact = false);

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import enum
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -132,8 +133,12 @@ def _native_config(conf) -> native.Config:
     cfg.global_z_order = int(bool(_cfg_get(conf, "render.splat.global_z_order", True)))
     cfg.enable_timings = int(bool(_cfg_get(conf, "render.enable_kernel_timings", False)))
     cfg.n_rolling_shutter_iterations = int(_cfg_get(conf, "render.splat.n_rolling_shutter_iterations", 5))
-    if int(_cfg_get(conf, "render.splat.k_buffer_size", 0)) != 0:
-        raise NotImplementedError("k_buffer_size > 0 (sorted 3DGUT) is not built yet (SURVEY 8f row 4)")
+    cfg.k_buffer_size = int(_cfg_get(conf, "render.splat.k_buffer_size", 0))
+    if not (0 <= cfg.k_buffer_size <= 16):
+        raise NotImplementedError("k_buffer_size must be within 0..16 (configs/paper/3dgut/sorted_*.yaml use 16)")
+    if cfg.k_buffer_size > 0 and not os.environ.get("GUTB200_EXPERIMENTAL_KBUFFER"):
+        raise NotImplementedError("k_buffer_size > 0 (sorted 3DGUT) is experimental: its kernels are compiled but not verified on hardware yet "
+                                  "(set GUTB200_EXPERIMENTAL_KBUFFER=1 to run them)")
     if int(_cfg_get(conf, "render.particle_radiance_sph_degree", 3)) != 3:
         raise NotImplementedError("this build stores 16 SH coefficients per particle (particle_radiance_sph_degree=3)")
     return cfg

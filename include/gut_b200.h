@@ -70,6 +70,7 @@ typedef struct gutb200_config {
     int32_t global_z_order;
     int32_t enable_timings;   /* render.enable_kernel_timings (src/splatRaster.cpp:168-169); 2 = also per-stage events */
     int32_t n_rolling_shutter_iterations; /* GAUSSIAN_N_ROLLING_SHUTTER_ITERATIONS (configs/render/3dgut.yaml:18): 5 */
+    int32_t k_buffer_size;    /* GAUSSIAN_K_BUFFER_SIZE (render.splat.k_buffer_size): 0 = unsorted (default), 1..16 = sorted 3DGUT */
     int32_t subtile_culling;  /* ours (no reference twin): exact-conservative sub-tile culling in render/renderBackward; 0 = off.
                                * Results are bit-identical either way (forward) -- the switch exists for the A/B test. */
 } gutb200_config;

@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     import b200_native as nat
 
     assert ctypes.sizeof(nat.Camera) == 4 * (2 + 2 + 2 + 6 + 2 + 4 + 7 + 7 + 2 + 1 + 6 + 6 + 3 + 1)
-    assert ctypes.sizeof(nat.Config) == 4 * 17
+    assert ctypes.sizeof(nat.Config) == 4 * 18
     cfg = nat.default_config()
     assert cfg.kernel_degree == 2 and abs(cfg.min_alpha - 1 / 255) < 1e-9 and abs(cfg.ut_delta - 3 ** 0.5) < 1e-6
     assert abs(cfg.min_transmittance - 1e-4) < 1e-10 and cfg.tile_culling == 1 and cfg.global_z_order == 1

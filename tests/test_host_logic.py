@@ -17,8 +17,10 @@ def test_native_config_from_reference_yaml_keys():
     cfg = _native_config(conf)
     assert cfg.kernel_degree == 2 and cfg.enable_timings == 1
     assert abs(cfg.ut_delta - math.sqrt(3.0)) < 1e-6
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):  # sorted 3DGUT: experimental, gated behind GUTB200_EXPERIMENTAL_KBUFFER
         _native_config({"render": {"splat": {"k_buffer_size": 16}}})
+    with pytest.raises(NotImplementedError):
+        _native_config({"render": {"splat": {"k_buffer_size": 64}}})
 
     class Obj:  # attribute-style (OmegaConf-like) access works too
         class render:
