@@ -16,6 +16,7 @@
 // [N,16] accumulator that G8 consumes and re-zeroes.
 #include "gut_common.cuh"
 #include "hit_math.cuh"
+#include "subtile_cull.cuh"
 #include "tma.cuh"
 
 namespace gutb200 {
@@ -89,12 +90,6 @@ __device__ __forceinline__ float kernel_response_grad(float gray, float gres, fl
 // ballot bit is set (48 % of the warp iterations on C2).  Pairs dropped could never be accepted: outputs are bit-identical with
 // the switch on and off (tests/test_gut_parity_gpu.py::test_subtile_culling_is_bit_identical).
 
-struct WarpFrame {
-    float e1x, e1y, e1z, e2x, e2y, e2z, e3x, e3y, e3z;   // frame around the direction of the block's first live pixel
-    float ulo, uhi, vlo, vhi, umax;                      // the block's rectangle in that frame
-    bool on;
-};
-
 __device__ __forceinline__ WarpFrame make_warp_frame(const FrameCamera& cam, const Ray& ray, bool alive, bool enabled, int lane) {
     WarpFrame wf;
     wf.on = false;
@@ -102,29 +97,10 @@ __device__ __forceinline__ WarpFrame make_warp_frame(const FrameCamera& cam, con
     if (!enabled || live == 0u) return wf;
     const int src = __ffs(live) - 1;
     float dx = __shfl_sync(kFull, ray.dx, src), dy = __shfl_sync(kFull, ray.dy, src), dz = __shfl_sync(kFull, ray.dz, src);
-    const float n2 = dx * dx + dy * dy + dz * dz;
-    if (!(n2 > 1e-20f) || !(n2 < 1e20f)) return wf;
-    const float in = rsqrtf(n2);
-    dx *= in; dy *= in; dz *= in;
-    const float* m = cam.s2w;  // complement: the camera axis least aligned with the direction
-    const float cxa = fabsf(m[0] * dx + m[1] * dy + m[2] * dz), cya = fabsf(m[3] * dx + m[4] * dy + m[5] * dz);
-    const float ax = cxa <= cya ? m[0] : m[3], ay = cxa <= cya ? m[1] : m[4], az = cxa <= cya ? m[2] : m[5];
-    const float k = ax * dx + ay * dy + az * dz;
-    float e1x = ax - k * dx, e1y = ay - k * dy, e1z = az - k * dz;
-    const float l1 = e1x * e1x + e1y * e1y + e1z * e1z;
-    if (!(l1 > 1e-6f)) return wf;
-    const float i1 = rsqrtf(l1);
-    e1x *= i1; e1y *= i1; e1z *= i1;
-    wf.e1x = e1x; wf.e1y = e1y; wf.e1z = e1z;
-    wf.e2x = dy * e1z - dz * e1y; wf.e2y = dz * e1x - dx * e1z; wf.e2z = dx * e1y - dy * e1x;
-    wf.e3x = dx; wf.e3y = dy; wf.e3z = dz;
+    if (!frame_axes(cam.s2w, dx, dy, dz, wf)) return wf;
     // this lane's ray in the frame; every live ray must point within 60 degrees of e3
-    const float w = ray.dx * dx + ray.dy * dy + ray.dz * dz;
-    const float r2 = ray.dx * ray.dx + ray.dy * ray.dy + ray.dz * ray.dz;
-    const bool fine = !alive || ((w > 0.f) && (w * w > 0.25f * r2));
-    const float iw = (alive && fine) ? 1.0f / w : 0.f;
-    const float u = (ray.dx * e1x + ray.dy * e1y + ray.dz * e1z) * iw;
-    const float v = (ray.dx * wf.e2x + ray.dy * wf.e2y + ray.dz * wf.e2z) * iw;
+    float u = 0.f, v = 0.f;
+    const bool fine = !alive || ray_uv(wf, ray.dx, ray.dy, ray.dz, u, v);
     float ulo = alive ? u : 3.0e38f, uhi = alive ? u : -3.0e38f, vlo = alive ? v : 3.0e38f, vhi = alive ? v : -3.0e38f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -138,61 +114,6 @@ __device__ __forceinline__ WarpFrame make_warp_frame(const FrameCamera& cam, con
     wf.umax = fmaxf(fmaxf(fabsf(ulo), fabsf(uhi)), fmaxf(fabsf(vlo), fabsf(vhi)));
     wf.on = __all_sync(kFull, fine);
     return wf;
-}
-
-// Can any ray of the warp's block be accepted by the particle with canonical transform rows (m0, m1, m2), canonical ray origin g
-// and density dns?  Conservative (see the section comment).
-template <int DEG>
-__device__ __forceinline__ bool block_candidate(const FrameConfig& cfg, const WarpFrame& wf, float m0x, float m0y, float m0z, float m1x,
-                                                float m1y, float m1z, float m2x, float m2y, float m2z, float gx, float gy, float gz,
-                                                float dns) {
-    const float tau = fmaxf(cfg.min_kernel_density, dns > 0.f ? cfg.min_alpha / dns : 2.f);
-    if (!(tau < 1.f)) return false;  // response <= 1: never accepted
-    const float ln = -logf(tau);
-    float r2 = DEG == 4 ? sqrtf(18.f * ln) : 2.f * ln;   // exp(-gray^2/18) > tau  |  exp(-gray/2) > tau
-    r2 = r2 * 1.002f + 1e-6f;
-    const float a1x = m0x * wf.e1x + m0y * wf.e1y + m0z * wf.e1z, a1y = m1x * wf.e1x + m1y * wf.e1y + m1z * wf.e1z,
-                a1z = m2x * wf.e1x + m2y * wf.e1y + m2z * wf.e1z;
-    const float a2x = m0x * wf.e2x + m0y * wf.e2y + m0z * wf.e2z, a2y = m1x * wf.e2x + m1y * wf.e2y + m1z * wf.e2z,
-                a2z = m2x * wf.e2x + m2y * wf.e2y + m2z * wf.e2z;
-    const float a3x = m0x * wf.e3x + m0y * wf.e3y + m0z * wf.e3z, a3y = m1x * wf.e3x + m1y * wf.e3y + m1z * wf.e3z,
-                a3z = m2x * wf.e3x + m2y * wf.e3y + m2z * wf.e3z;
-    const float c1x = a1y * gz - a1z * gy, c1y = a1z * gx - a1x * gz, c1z = a1x * gy - a1y * gx;
-    const float c2x = a2y * gz - a2z * gy, c2y = a2z * gx - a2x * gz, c2z = a2x * gy - a2y * gx;
-    const float c3x = a3y * gz - a3z * gy, c3y = a3z * gx - a3x * gz, c3z = a3x * gy - a3y * gx;
-    const float a33 = a3x * a3x + a3y * a3y + a3z * a3z, c33 = c3x * c3x + c3y * c3y + c3z * c3z;
-    const float A00 = (c1x * c1x + c1y * c1y + c1z * c1z) - r2 * (a1x * a1x + a1y * a1y + a1z * a1z);
-    const float A01 = (c1x * c2x + c1y * c2y + c1z * c2z) - r2 * (a1x * a2x + a1y * a2y + a1z * a2z);
-    const float A11 = (c2x * c2x + c2y * c2y + c2z * c2z) - r2 * (a2x * a2x + a2y * a2y + a2z * a2z);
-    const float B0 = (c1x * c3x + c1y * c3y + c1z * c3z) - r2 * (a1x * a3x + a1y * a3y + a1z * a3z);
-    const float B1 = (c2x * c3x + c2y * c3y + c2z * c3z) - r2 * (a2x * a3x + a2y * a3y + a2z * a3z);
-    const float K = c33 - r2 * a33;
-    // f is convex iff A > 0; otherwise {f < 0} is unbounded (particle around / behind the origin): keep the entry
-    if (!(A00 > 0.f) || !(A11 > 0.f) || !(A00 * A11 > A01 * A01)) return true;
-    // bound of the fp32 error of f over the block and of the exact test's own rounding near the boundary
-    const float U = wf.umax;
-    const float g2 = gx * gx + gy * gy + gz * gz;
-    const float err = 1e-5f * ((A00 + 2.f * fabsf(A01) + A11) * U * U + 2.f * (fabsf(B0) + fabsf(B1)) * U + c33 + r2 * a33) +
-                      4e-6f * sqrtf(fmaxf(c33, r2 * a33) * a33 * g2);
-    const float Kp = K - err;
-    // minimum of f(u,v) = A00 u^2 + 2 A01 u v + A11 v^2 + 2 B0 u + 2 B1 v + Kp over the rectangle: the unconstrained minimiser
-    // if it lies inside, else the smallest of the four edge minima (1-D convex quadratics, clamped)
-    const float u0 = wf.ulo, u1 = wf.uhi, v0 = wf.vlo, v1 = wf.vhi;
-    const float iA00 = 1.0f / A00, iA11 = 1.0f / A11;
-    const float qa = fmaf(A01, u0, B1), qb = fmaf(A01, u1, B1), pa = fmaf(A01, v0, B0), pb = fmaf(A01, v1, B0);
-    const float va = fminf(fmaxf(-qa * iA11, v0), v1), vb = fminf(fmaxf(-qb * iA11, v0), v1);
-    const float ua = fminf(fmaxf(-pa * iA00, u0), u1), ub = fminf(fmaxf(-pb * iA00, u0), u1);
-    const float fa = fmaf(va, fmaf(A11, va, 2.f * qa), fmaf(u0, fmaf(A00, u0, 2.f * B0), Kp));
-    const float fb = fmaf(vb, fmaf(A11, vb, 2.f * qb), fmaf(u1, fmaf(A00, u1, 2.f * B0), Kp));
-    const float fc = fmaf(ua, fmaf(A00, ua, 2.f * pa), fmaf(v0, fmaf(A11, v0, 2.f * B1), Kp));
-    const float fd = fmaf(ub, fmaf(A00, ub, 2.f * pb), fmaf(v1, fmaf(A11, v1, 2.f * B1), Kp));
-    const float edge_min = fminf(fminf(fa, fb), fminf(fc, fd));
-    // centre inside the rectangle: the interior minimum is below every edge value; keep the entry unless even f(centre) > 0,
-    // which the edge values cannot tell -- so test the centre explicitly
-    const float det = A00 * A11 - A01 * A01;
-    const float cu = (A01 * B1 - A11 * B0), cv = (A01 * B0 - A00 * B1);  // times det
-    const bool inside = (cu >= u0 * det) && (cu <= u1 * det) && (cv >= v0 * det) && (cv <= v1 * det);
-    return inside || (edge_min < 0.f);
 }
 
 // ----------------------------------------------------------------------------------------------------------
