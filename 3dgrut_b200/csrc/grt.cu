@@ -486,6 +486,11 @@ template <int DEG, bool BWD, bool PACKET>
 __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int64_t ray, float ox, float oy, float oz, float dx, float dy,
                                            float dz) {
     const float idx_ = 1.0f / dx, idy_ = 1.0f / dy, idz_ = 1.0f / dz;
+    // inverse direction for the node slab tests: a zero component (axis-parallel ray) would make the FMA form plane * inf + (-o * inf) a
+    // NaN and cull everything; 1e-20 keeps both products finite (|plane|, |o| << 1e18) and the slab interval (-huge, +huge) as it should be
+    const float tix = 1.0f / (fabsf(dx) > 1e-20f ? dx : copysignf(1e-20f, dx));
+    const float tiy = 1.0f / (fabsf(dy) > 1e-20f ? dy : copysignf(1e-20f, dy));
+    const float tiz = 1.0f / (fabsf(dz) > 1e-20f ? dz : copysignf(1e-20f, dz));
 
     float t0, t1;
     scene_clip(P.scene, ox, oy, oz, idx_, idy_, idz_, t0, t1);
@@ -502,7 +507,7 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
         while (true) {
             want = want && (last <= t1) && (T > P.min_transmittance);
             if (PACKET ? !__any_sync(0xFFFFFFFFu, want) : !want) break;
-            knn_query<PACKET>(P, want, ox, oy, oz, dx, dy, dz, idx_, idy_, idz_, last + kEpsT, t1 + kEpsT, kt, kid);
+            knn_query<PACKET>(P, want, ox, oy, oz, dx, dy, dz, tix, tiy, tiz, last + kEpsT, t1 + kEpsT, kt, kid);
             if (kid[0] == kNone) want = false;
             if (!want) continue;
             float lt[kK];
@@ -568,7 +573,7 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
         while (true) {
             want = want && (start < end);
             if (PACKET ? !__any_sync(0xFFFFFFFFu, want) : !want) break;
-            knn_query<PACKET>(P, want, ox, oy, oz, dx, dy, dz, idx_, idy_, idz_, start + kEpsT, end, kt, kid);
+            knn_query<PACKET>(P, want, ox, oy, oz, dx, dy, dz, tix, tiy, tiz, start + kEpsT, end, kt, kid);
             if (kid[0] == kNone) want = false;
             if (!want) continue;
             float lt[kK];

@@ -195,3 +195,36 @@ def test_traversal_variants_give_the_same_image(switch, off, monkeypatch):
         err = rel_l2(a, b)
         print(f"[variants] {switch}: d_{name} rel-L2 {err:.3e}")
         assert err <= 1e-3
+
+
+def test_axis_parallel_rays_reach_the_geometry():
+    """Rays with exactly zero direction components (orthographic bundles, the centre row / column of an axis-aligned camera): the inverse
+    direction is infinite there, which the one-FMA slab test of the node boxes must survive (it used to produce NaN and cull everything)."""
+    import b200_native as nat
+
+    dev = torch.device("cuda", 0)
+    sc = scenes.scene_c1()
+    H = W = 48
+    ys, xs = np.meshgrid(np.linspace(-1.4, 1.4, H, dtype=np.float32), np.linspace(-1.4, 1.4, W, dtype=np.float32), indexing="ij")
+    ro = np.stack([xs, ys, np.full_like(xs, -4.0)], -1).astype(np.float32)       # orthographic: origins on a plane,
+    rd = np.broadcast_to(np.array([0, 0, 1], np.float32), ro.shape).copy()        # all directions exactly +z
+    r2w = np.ascontiguousarray(np.eye(4, dtype=np.float32)[:3, :4])
+    cfg = go.grt_config()
+    rgb_ref, alpha_ref, dist_ref, hits_ref, vis_ref = go.grt_trace(cfg, sc.particles, sc.sph, 3, ro, rd, np.eye(4, dtype=np.float32))
+    assert hits_ref.sum() > 100
+    ctx = nat.GrtContext(nat.grt_default_config(), 0)
+    s = torch.cuda.current_stream(dev).cuda_stream
+    P = torch.from_numpy(sc.particles).to(dev)
+    S = torch.from_numpy(sc.sph).to(dev)
+    ctx.build_bvh(s, sc.n, P[:, 0:3].contiguous().data_ptr(), P[:, 4:8].contiguous().data_ptr(), P[:, 8:11].contiguous().data_ptr(),
+                  P[:, 3:4].contiguous().data_ptr())
+    R = H * W
+    tro, trd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    rgb, alpha, dist, hits, vis = (torch.zeros((R, 3), device=dev), torch.zeros(R, device=dev), torch.zeros((R, 2), device=dev),
+                                   torch.zeros(R, device=dev), torch.zeros(sc.n, device=dev))
+    ctx.trace(s, sc.n, P.data_ptr(), S.data_ptr(), 3, 1e-3, 1, H, W, tro.data_ptr(), trd.data_ptr(), r2w.ctypes.data, rgb.data_ptr(),
+              alpha.data_ptr(), dist.data_ptr(), hits.data_ptr(), vis.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(hits.cpu().numpy().reshape(hits_ref.shape), hits_ref)
+    assert np.abs(rgb.cpu().numpy().reshape(rgb_ref.shape) - rgb_ref).max() <= 1e-4
+    ctx.close()
