@@ -691,7 +691,7 @@ struct grtb200_ctx {
     size_t hit_list_bytes = 0, hit_count_bytes = 0;
     int hit_cap = 96, hit_cap_used = 0;
     uint64_t build_generation = 0;
-    struct { const float* rays_o; const float* rays_d; const float* particles; const float* out_rgb; const float* out_dist; int64_t rays; int64_t n; uint64_t generation; float r2w[12]; bool valid; } fwd_key = {};
+    struct { const float* rays_o; const float* rays_d; const float* particles; const float* out_rgb; const float* out_dist; int64_t rays; int64_t n; uint64_t generation; float r2w[12]; bool valid; int sph_degree; float min_transmittance; } fwd_key = {};
     float scene_host[6] = {0, 0, 0, 0, 0, 0};
     bool scene_valid = false;
 };
@@ -971,6 +971,8 @@ int grtb200_trace(grtb200_ctx* c, void* stream, int64_t n, const float* particle
         P.rays = rays;
         c->fwd_key = {rays_o, rays_d, particles, out_rgb, out_dist, rays, n, c->build_generation, {}, true};
         memcpy(c->fwd_key.r2w, P.r2w, sizeof(P.r2w));
+        c->fwd_key.sph_degree = sph_degree;
+        c->fwd_key.min_transmittance = min_transmittance;
         c->hit_cap_used = cap;
     }
     launch_trace<false>(c->cfg, P, s);
@@ -998,7 +1000,8 @@ int grtb200_trace_bwd(grtb200_ctx* c, void* stream, int64_t n, const float* part
     const int64_t rays = static_cast<int64_t>(batch) * height * width;
     const bool replay = c->fwd_key.valid && c->fwd_key.rays_o == rays_o && c->fwd_key.rays_d == rays_d && c->fwd_key.particles == particles &&
                         c->fwd_key.out_rgb == out_rgb && c->fwd_key.out_dist == out_dist && memcmp(c->fwd_key.r2w, P.r2w, sizeof(P.r2w)) == 0 &&
-                        c->fwd_key.rays == rays && c->fwd_key.n == n && c->fwd_key.generation == c->build_generation && n > 0;
+                        c->fwd_key.rays == rays && c->fwd_key.n == n && c->fwd_key.generation == c->build_generation && n > 0 &&
+                        c->fwd_key.sph_degree == sph_degree && c->fwd_key.min_transmittance == min_transmittance;
     if (replay) {  // the lists of the forward these outputs came from: replay them, re-trace only the rays that overflowed
         P.hit_list = static_cast<uint32_t*>(c->hit_list);
         P.hit_count = static_cast<uint32_t*>(c->hit_count);
