@@ -51,20 +51,38 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile into a private temp directory under an exclusive file lock and publish the library with one atomic rename: with one
+    process per GPU under torchrun every rank may call this at once, and none may ever dlopen a half-written file."""
+    import fcntl
+    import tempfile
+
     if not force and not needs_build():
         return OUT
     nvcc = _nvcc()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    objs = []
-    for unit, extra in UNITS.items():
-        obj = os.path.join(objdir, unit.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *COMMON, *extra, "-Xptxas", "-v" if verbose else "-warn-spills", "-c", os.path.join(CSRC, unit), "-o", obj]
-        if verbose:
-            print(" ".join(cmd), file=sys.stderr)
-        subprocess.check_call(cmd)
-        objs.append(obj)
-    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", OUT, *objs])
+    with open(os.path.join(objdir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():  # another rank built it while we waited
+                return OUT
+            with tempfile.TemporaryDirectory(dir=objdir, prefix="tmp_") as tmp:
+                procs, objs = [], []
+                for unit, extra in UNITS.items():
+                    obj = os.path.join(tmp, unit.replace(".cu", ".o"))
+                    cmd = [nvcc, *ARCH, *COMMON, *extra, "-Xptxas", "-v" if verbose else "-warn-spills", "-c", os.path.join(CSRC, unit), "-o", obj]
+                    if verbose:
+                        print(" ".join(cmd), file=sys.stderr)
+                    procs.append((cmd, subprocess.Popen(cmd)))  # translation units compile in parallel
+                    objs.append(obj)
+                for cmd, pr in procs:
+                    if pr.wait() != 0:
+                        raise subprocess.CalledProcessError(pr.returncode, cmd)
+                staged = os.path.join(tmp, "libgut_b200.so")
+                subprocess.check_call([nvcc, *ARCH, "-shared", "-o", staged, *objs])
+                os.replace(staged, OUT)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return OUT
 
 

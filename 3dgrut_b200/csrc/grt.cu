@@ -371,7 +371,10 @@ __device__ __forceinline__ void knn_query(const TraceParams& P, bool want, float
     // slab planes as one FMA each: t = plane * (1/d) + (-o/d); `slack` covers the rounding difference to (plane - o) / d, so the
     // box test stays a superset of the exact proxy test of the leaves
     const float nox = -ox * idx_, noy = -oy * idy_, noz = -oz * idz_;
-    const float slack = 4e-7f * (fabsf(nox) + fabsf(noy) + fabsf(noz)) + 1e-30f;
+    // degenerate axes (|1/d| clamped to 1e20 for axis-parallel rays, trace_rays) are left out: their slab interval is (-huge, +huge) or
+    // empty with the right sign, and |-o/d| ~ 1e20 there would inflate the slack until the other axes' tests never reject
+    const float slack = 4e-7f * ((fabsf(idx_) < 1e19f ? fabsf(nox) : 0.f) + (fabsf(idy_) < 1e19f ? fabsf(noy) : 0.f) +
+                                 (fabsf(idz_) < 1e19f ? fabsf(noz) : 0.f)) + 1e-30f;
     int stack[kStack];
     int sp = 0;
     stack[sp++] = 0;
