@@ -276,9 +276,6 @@ int check_args(gutb200_ctx* c, const gutb200_camera* cam, int64_t n, const void*
     if (n < 0 || n > 0x7FFFFFFF) return fail(c, "particle count %lld out of range", static_cast<long long>(n));
     if (reinterpret_cast<uintptr_t>(particles) & 15) return fail(c, "particle buffer must be 16-byte aligned");
     if (c->cfg.k_buffer_size < 0 || c->cfg.k_buffer_size > 16) return fail(c, "k_buffer_size %d out of range (0..16)", c->cfg.k_buffer_size);
-    if (c->cfg.k_buffer_size > 0 && !std::getenv("GUTB200_EXPERIMENTAL_KBUFFER"))
-        return fail(c, "k_buffer_size > 0 (sorted 3DGUT, gut_render_kbuffer.cu) is experimental: the kernels have not been verified on hardware "
-                       "yet; set GUTB200_EXPERIMENTAL_KBUFFER=1 to run them");
     if (c->cfg.kernel_degree != 2 && c->cfg.kernel_degree != 4) return fail(c, "kernel_degree %d not built (2 or 4)", c->cfg.kernel_degree);
     return 0;
 }

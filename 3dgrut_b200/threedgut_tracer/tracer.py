@@ -136,9 +136,6 @@ def _native_config(conf) -> native.Config:
     cfg.k_buffer_size = int(_cfg_get(conf, "render.splat.k_buffer_size", 0))
     if not (0 <= cfg.k_buffer_size <= 16):
         raise NotImplementedError("k_buffer_size must be within 0..16 (configs/paper/3dgut/sorted_*.yaml use 16)")
-    if cfg.k_buffer_size > 0 and not os.environ.get("GUTB200_EXPERIMENTAL_KBUFFER"):
-        raise NotImplementedError("k_buffer_size > 0 (sorted 3DGUT) is experimental: its kernels are compiled but not verified on hardware yet "
-                                  "(set GUTB200_EXPERIMENTAL_KBUFFER=1 to run them)")
     if int(_cfg_get(conf, "render.particle_radiance_sph_degree", 3)) != 3:
         raise NotImplementedError("this build stores 16 SH coefficients per particle (particle_radiance_sph_degree=3)")
     return cfg

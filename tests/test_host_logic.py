@@ -17,8 +17,7 @@ def test_native_config_from_reference_yaml_keys():
     cfg = _native_config(conf)
     assert cfg.kernel_degree == 2 and cfg.enable_timings == 1
     assert abs(cfg.ut_delta - math.sqrt(3.0)) < 1e-6
-    with pytest.raises(NotImplementedError):  # sorted 3DGUT: experimental, gated behind GUTB200_EXPERIMENTAL_KBUFFER
-        _native_config({"render": {"splat": {"k_buffer_size": 16}}})
+    assert _native_config({"render": {"splat": {"k_buffer_size": 16}}}).k_buffer_size == 16  # sorted 3DGUT (configs/paper/3dgut/sorted_*.yaml)
     with pytest.raises(NotImplementedError):
         _native_config({"render": {"splat": {"k_buffer_size": 64}}})
 

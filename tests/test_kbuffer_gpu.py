@@ -7,12 +7,7 @@ import scenes
 from helpers import image_error_report, oracle_camera, rel_l2, tracer_pose
 from oracle import gut_oracle as go
 
-import os
-
-# EXPERIMENTAL: the kernels were written after round 1's GPU budget was spent.  The one run they had exercised the K = 0 path by mistake
-# (the config field was not forwarded to the frame configuration -- fixed since), so they are still unverified: opt in explicitly.
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("GUTB200_EXPERIMENTAL_KBUFFER"),
-                                                  reason="sorted 3DGUT kernels not verified on hardware yet; set GUTB200_EXPERIMENTAL_KBUFFER=1")]
+pytestmark = pytest.mark.gpu  # first hardware run: round 2 (profiles/r02_a_gate_pytest.log), K = 4 / 16, kernel degrees 2 / 4
 torch = pytest.importorskip("torch")
 
 
