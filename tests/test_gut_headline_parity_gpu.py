@@ -6,7 +6,16 @@ heaviest-tile-first ordering and sub-tile culling are all compared with the orac
 
 Bars (same policy as test_gut_parity_gpu.py / DESIGN.md section 5): tile counts, depth bits, the sorted (key, value) stream and tile ranges
 BIT-EXACT; RGBA / distance: mean |diff| <= 1e-5, |diff| <= 1e-4 on all but max(3, 2e-4 P) pixels, max <= 2e-2; hit counts equal on
->= 99.9 % of the pixels; the five gradient tensors rel-L2 <= 1e-3 each.  The full-frame oracle costs ~5 s per view on the box."""
+>= 99.9 % of the pixels; the five gradient tensors rel-L2 <= 1e-3 each -- see below.  The full-frame oracle costs ~5 s per view on the box.
+
+Gradient bar, as first run and as it stands (profiles/r02_b_headline_first_run_1_failed.log): with a flat 1e-3 on every tensor, 1 of the 2 C2
+cameras FAILED -- cam41, d_quat rel-L2 2.22e-3 (the other four tensors 1.3e-4 .. 6.5e-4; cam3: all <= 4.5e-4).  The same frame evaluated by the
+oracle in fp32 and in fp64 ON THE SAME LISTS (no CUDA involved) differs by 2.24e-3 in d_quat, 93.6 % of the squared error in ONE anisotropic
+particle (scale ratio 18), 99.2 % in ten: a borderline accept flip (response > 0.0113 / alpha > 1/255 are discontinuous) on an elongated
+Gaussian, whose rotation gradient is large, dominates the norm.  A flat 1e-3 is below the fp32 noise floor of that frame for that tensor.
+Both cameras stay in the test.  The check is therefore, per tensor:  (1) err <= max(1e-3, 1.5 x yardstick), yardstick = oracle f32 vs
+oracle f64 of THIS frame, printed;  (2) with the ten particles that carry the largest yardstick error removed -- picked from the oracle
+pair, never from our output -- err <= 1e-3 flat.  (2) cannot be met by a systematic error; (1) keeps 1e-3 wherever the frame allows it."""
 import dataclasses
 
 import numpy as np
@@ -37,7 +46,7 @@ def _check_frame(label, sc, cam_index, n_cams, seed):
 
     c2w = sc.camera(cam_index, n_cams)
     pose = tracer_pose(c2w)
-    ref = oracle_frame(sc, c2w, seed=seed, pose=pose)
+    ref = oracle_frame(sc, c2w, seed=seed, pose=pose, with_f64=True)
     lens = ref["bn"].ranges[:, 1].astype(np.int64) - ref["bn"].ranges[:, 0]
     print(f"[headline] {label} cam{cam_index}: N={sc.n} I={len(ref['bn'].sorted_keys)} longest tile list {int(lens.max())} "
           f"(batches of 256: {int(np.ceil(lens.max() / 256))}), hits {int(ref['hits'].sum())}")
@@ -73,11 +82,29 @@ def _check_frame(label, sc, cam_index, n_cams, seed):
     dp, ds = np.zeros((n, 12), np.float32), np.zeros((n, 48), np.float32)
     ctx.backward_host(cam, n, p(sc.particles), p(sc.sph), sc.sph_degree, p(ro), p(rd), p(rgba), p(ref["d_rgba"]), p(dist), p(ref["d_dist"]),
                       p(dp), p(ds))
-    rdp = ref["dp"]
-    errs = dict(pos=rel_l2(dp[:, 0:3], rdp[:, 0:3]), dns=rel_l2(dp[:, 3:4], rdp[:, 3:4]), quat=rel_l2(dp[:, 4:8], rdp[:, 4:8]),
-                scl=rel_l2(dp[:, 8:11], rdp[:, 8:11]), sph=rel_l2(ds, ref["ds"]))
-    print(f"[headline] {label} cam{cam_index} gradient rel-L2:", {k: f"{v:.2e}" for k, v in errs.items()})
-    assert max(errs.values()) <= 1e-3
+    rdp, rdp64 = ref["dp"], ref["dp_64"]
+    cols = dict(pos=slice(0, 3), dns=slice(3, 4), quat=slice(4, 8), scl=slice(8, 11))
+    errs = {k: rel_l2(dp[:, v], rdp[:, v]) for k, v in cols.items()}
+    errs["sph"] = rel_l2(ds, ref["ds"])
+    yard = {k: rel_l2(rdp[:, v], rdp64[:, v]) for k, v in cols.items()}
+    yard["sph"] = rel_l2(ref["ds"], ref["ds_64"])
+    # the ten particles with the largest f32-vs-f64 disagreement OF THE ORACLE (all gradient columns): borderline accept flips
+    e2 = ((rdp.astype(np.float64) - rdp64) ** 2).sum(1) / max(float((rdp64 ** 2).sum()), 1e-300) \
+        + ((ref["ds"].astype(np.float64) - ref["ds_64"]) ** 2).sum(1) / max(float((ref["ds_64"] ** 2).sum()), 1e-300)
+    keep = np.ones(n, bool)
+    keep[np.argsort(-e2)[:10]] = False
+    robust = {k: rel_l2(dp[keep][:, v], rdp[keep][:, v]) for k, v in cols.items()}
+    robust["sph"] = rel_l2(ds[keep], ref["ds"][keep])
+    fmt = lambda d: {k: f"{v:.2e}" for k, v in d.items()}  # noqa: E731
+    print(f"[headline] {label} cam{cam_index} gradient rel-L2 vs oracle:", fmt(errs))
+    print(f"[headline] {label} cam{cam_index} yardstick (oracle f32 vs f64, same lists):", fmt(yard))
+    print(f"[headline] {label} cam{cam_index} gradient rel-L2 without the oracle's 10 flip particles:", fmt(robust))
+    over = {k: v for k, v in errs.items() if v > 1e-3}
+    if over:
+        print(f"[headline] {label} cam{cam_index}: ABOVE the flat 1e-3 bar: {fmt(over)} -- allowed only up to 1.5 x this frame's yardstick")
+    for k in errs:
+        assert errs[k] <= max(1e-3, 1.5 * yard[k]), (k, errs[k], yard[k])
+        assert robust[k] <= 1e-3, (k, robust[k])
     assert np.all(dp[:, 11] == 0)
     ctx.close()
 
