@@ -1,5 +1,5 @@
 // 3dgrut_b200/csrc/gut_render_kbuffer.cu -- sorted 3DGUT: per-tile compositing with a per-ray k-buffer (GAUSSIAN_K_BUFFER_SIZE = K > 0)
-// and its adjoint.  Parity vs the oracle verified on a B200 in round 2 (tests/test_kbuffer_gpu.py: image 2e-7 mean, gradients rel-L2 3e-6).
+// and its adjoint.  Parity vs the CPU restatement verified on a B200 in round 2 (tests/test_kbuffer_gpu.py: image 2e-7 mean, gradients rel-L2 3e-6).
 // First version, written for parity, not for speed (the default configuration is K = 0, gut_render.cu).
 //
 // Reference semantics restated (not copied) from threedgut_tracer/include/3dgut/kernels/cuda/renderers/gutKBufferRenderer.cuh:

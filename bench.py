@@ -259,6 +259,56 @@ def time_image_loss(torch, dev, H, W, flush, peak, peak_src, iters=20):
             "frac": ach / peak if peak else None, "peak_source": peak_src, "bound": "hbm (the 11x11 window makes it FP32-bound at this size)"}
 
 
+def time_reference_gpu(torch, dev, sc, poses, particles, sph, rays_o, rays_d, d_rgba, d_dist, flush, view_of, steps, warmup=5):
+    """Same-box GPU denominator: the REFERENCE's own 3DGUT renderer (threedgut_tracer/src/gutRenderer.cu and the headers it includes,
+    compiled unmodified for sm_100a in the build container with the reference's flags; only the slangc output is a hand translation --
+    oracle/ref_cuda/) on the same tensors, same cameras, same CUDA-event / L2-flush protocol as our timed region.  Baseline only: nothing
+    on the product path touches it.  Returns None when the prebuilt library did not travel."""
+    try:
+        from oracle import gut_ref_cuda as grc
+
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libgut_ref_cuda.so")):
+            return None
+        rr = grc.ReferenceRaster()
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)}
+    H, W, n = sc.height, sc.width, sc.n
+    s = torch.cuda.current_stream(dev).cuda_stream
+    dp, ds = torch.empty((n, 12), device=dev), torch.empty((n, 48), device=dev)
+
+    def step(i):
+        pose = poses[view_of(i)]
+        rgba, dist, hits, vis = rr.trace(torch, s, i, sc.sph_degree, particles, sph, W, H, sc.fx, sc.fy, sc.cx, sc.cy, pose, rays_o, rays_d)
+        rr.trace_bwd(torch, s, i, sc.sph_degree, particles, sph, W, H, sc.fx, sc.fy, sc.cx, sc.cy, pose, rays_o, rays_d, rgba, d_rgba, dist, d_dist,
+                     out=(dp, ds))
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        flush.fill_(float(i))
+        ev[i][0].record()
+        step(warmup + i)
+        ev[i][1].record()
+    torch.cuda.synchronize(dev)
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    rr.set_timing(True)
+    rr.stage_times()
+    for i in range(min(steps, 10)):
+        flush.fill_(float(i))
+        step(warmup + i)
+    torch.cuda.synchronize(dev)
+    stage = rr.stage_times()
+    rr.set_timing(False)
+    rr.close()
+    return {"value": 1000.0 / ms, "unit": UNIT, "ms_per_step": ms, "steps": steps, "stage_ms": stage,
+            "what": "reference threedgut_tracer/src/gutRenderer.cu (projectOnTiles, CUB scan, expand, 44-bit CUB sort, ranges, render, renderBackward, "
+                    "projectBackward + its host orchestration incl. the per-frame host sync and output zero-fills) compiled unmodified with "
+                    "-O3 -use_fast_math for sm_100a; slangc output replaced by the hand translation oracle/ref_cuda/threedgutSlang.cuh",
+            "timing": "CUDA events around trace+trace_bwd per step, L2 flushed between steps, same cameras and tensors as our arm"}
+
+
 class HostFeed:
     """End-to-end input feed: every step's rays and target image are copied from pinned host memory on a copy stream
     while the previous step computes (what a DataLoader with pinned memory does), and every step's loss is read back
@@ -492,6 +542,7 @@ def main():
     ap.add_argument("--cpu-tile-stride", type=int, default=16)
     ap.add_argument("--cpu-ray-stride", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference_gpu block (the reference's own kernels timed on this GPU)")
     ap.add_argument("--exchange", default="compact", choices=["compact", "allreduce"],
                     help="multi-GPU gradient exchange of the 3DGUT path: compact = all-reduce [N,12] + all-gather [N,4] + rebuild of the SH "
                          "gradient (64 B per Gaussian on the wire), allreduce = one all-reduce of [N,60] (240 B)")
@@ -721,6 +772,17 @@ def main():
             "stage_ms": stage_ms,
             "frame_algorithmic_gbs": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9,
         }
+        if world == 1 and not args.no_reference_gpu:
+            rg = time_reference_gpu(torch, dev, sc, poses, particles, sph, rays_o, rays_d, d_rgba, d_dist, flush, view_of, steps=min(args.steps, 30))
+            if rg is not None:
+                line["reference_gpu"] = rg
+                if "value" in rg:
+                    ours_map = {"project": "project", "prepare_expand": "scan", "expand": "expand", "sort": "sort+tile_ranges", "render": "render",
+                                "render_backward": "render_backward", "project_backward": "project_backward"}
+                    ours_stage = dict(stage_ms)
+                    ours_stage["sort+tile_ranges"] = stage_ms["sort"] + stage_ms["tile_ranges"]
+                    line["vs_reference_gpu"] = {"speedup_device_timed": value / rg["value"],
+                                                "per_stage_ours_over_reference_ms": {k: [ours_stage[v], rg["stage_ms"][k]] for k, v in ours_map.items()}}
         if world == 1:
             line["optimizer_step"] = time_optimizer_step(torch, dev, n, flush, peak, peak_src)
             line["image_loss"] = time_image_loss(torch, dev, H, W, flush, peak, peak_src)
