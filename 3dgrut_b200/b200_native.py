@@ -43,6 +43,7 @@ EXPORTS = [
     "gutb200_forward", "gutb200_backward", "gutb200_forward_host", "gutb200_backward_host", "gutb200_last_stats",
     "gutb200_debug_copy", "gutb200_collect_times", "gutb200_collect_stage_times", "gutb200_set_timings", "gutb200_launch_count",
     "gutb200_backward_compact", "gutb200_sph_grad_from_views", "gutb200_camera_position",
+    "gutb200_debug_work_counters", "gutb200_debug_fma_peak",
     "gutb200_selective_adam_update", "gutb200_gaussian_adam_step",  # bound in optimizers/__init__.py
     "gutb200_image_loss_scratch_bytes", "gutb200_image_loss",  # bound in losses.py
 ]
@@ -97,6 +98,8 @@ def load():
     lib.gutb200_collect_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.gutb200_collect_stage_times.argtypes = [vp, C.POINTER(C.c_float)]
     lib.gutb200_set_timings.argtypes = [vp, C.c_int]
+    lib.gutb200_debug_work_counters.argtypes = [vp, vp, vp, vp, vp]
+    lib.gutb200_debug_fma_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     _LIB = lib
     return lib
 
@@ -200,6 +203,19 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._lib.gutb200_launch_count(self._h))
+
+    COUNTERS = ("tests_ref", "tests_exec", "hits", "fwd_iters", "hit_iters", "screens", "bwd_lanes")
+
+    def work_counters(self, particles, rays_o, rays_d):
+        """Work counters of the last forward (device pointers as passed to it): dict of ints (gutb200_debug_work_counters)."""
+        arr = (C.c_uint64 * 8)()
+        self._check(self._lib.gutb200_debug_work_counters(self._h, particles, rays_o, rays_d, arr), "gutb200_debug_work_counters")
+        return dict(zip(self.COUNTERS, [int(v) for v in arr]))
+
+    def fma_peak_tflops(self, repeats: int = 5) -> float:
+        v = C.c_float()
+        self._check(self._lib.gutb200_debug_fma_peak(self._h, int(repeats), C.byref(v)), "gutb200_debug_fma_peak")
+        return float(v.value)
 
 
 # ---------------------------------------------------------------------------------------------------------------

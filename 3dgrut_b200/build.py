@@ -28,6 +28,7 @@ UNITS = {
     # optimizer step: plain IEEE arithmetic (the reference plugin is built without fast-math, setup_optimizers.py)
     "gut_optim.cu": [],
     "gut_loss.cu": [],
+    "gut_debug.cu": [],
 }
 
 

@@ -162,7 +162,8 @@ struct gutb200_ctx {
     // per intersection
     DeviceBuffer keys_in, keys_out, vals_in, vals_out, sort_temp;
     // per tile
-    DeviceBuffer ranges, tile_order;
+    DeviceBuffer ranges, tile_order, chunk_base, hit_words;
+    gutb200_camera fwd_camera{};   // the camera of the forward whose context the backward replays
     // host staging for the *_host entry points
     DeviceBuffer h_particles, h_sph, h_rays_o, h_rays_d, h_rgba, h_dist, h_hits, h_vis, h_drgba, h_ddist, h_dpart, h_dsph;
     uint32_t* pinned_total = nullptr;
@@ -346,7 +347,7 @@ void gutb200_default_config(gutb200_config* c) {  // configs/render/3dgut.yaml, 
     c->tile_culling = 1;
     c->global_z_order = 1;
     c->enable_timings = 0;
-    c->subtile_culling = 3;  // bit 0: renderBackward, bit 1: render
+    c->subtile_culling = 7;  // bit 1: sub-tile screens in render; bit 2: renderBackward walks the forward's hit words (bit 0: unused since round 2)
     c->n_rolling_shutter_iterations = 5;  // configs/render/3dgut.yaml:18
     c->k_buffer_size = 0;                 // configs/render/3dgut.yaml: k_buffer_size 0 (unsorted)
     if (const char* e = std::getenv("GUTB200_SUBTILE_CULLING")) c->subtile_culling = std::atoi(e);  // A/B switch for profiling
@@ -377,7 +378,7 @@ void gutb200_destroy(gutb200_ctx* c) {
     cudaDeviceSynchronize();
     DeviceBuffer* bufs[] = {&c->tiles_count, &c->offsets, &c->proj, &c->depth, &c->rgb, &c->grad_acc, &c->scan_temp, &c->ids, &c->perm,
                             &c->depth_sorted, &c->cnt_perm, &c->dsort_temp, &c->keys_in,
-                            &c->keys_out, &c->vals_in, &c->vals_out, &c->sort_temp, &c->ranges, &c->tile_order, &c->h_particles, &c->h_sph,
+                            &c->keys_out, &c->vals_in, &c->vals_out, &c->sort_temp, &c->ranges, &c->tile_order, &c->chunk_base, &c->hit_words, &c->h_particles, &c->h_sph,
                             &c->h_rays_o, &c->h_rays_d, &c->h_rgba, &c->h_dist, &c->h_hits, &c->h_vis, &c->h_drgba, &c->h_ddist,
                             &c->h_dpart, &c->h_dsph};
     for (DeviceBuffer* b : bufs) b->release();
@@ -418,6 +419,7 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     GUT_CUDA(c, c->rgb.reserve(nn * 12, s));
     GUT_CUDA(c, c->ranges.reserve(static_cast<size_t>(tiles) * 8, s));
     GUT_CUDA(c, c->tile_order.reserve(static_cast<size_t>(tiles) * 4, s));
+    GUT_CUDA(c, c->chunk_base.reserve(static_cast<size_t>(tiles) * 4, s));
     GUT_CUDA(c, c->scan_temp.reserve(scan_temp_bytes(n) + 16, s));
     GUT_CUDA(c, c->ids.reserve(nn * 4, s));
     GUT_CUDA(c, c->perm.reserve(nn * 4, s));
@@ -473,15 +475,20 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     } else {
         GUT_CUDA(c, c->vals_out.reserve(16, s));
     }
+    const size_t words = hit_words_capacity(total, tiles);
+    GUT_CUDA(c, c->hit_words.reserve(words * 4, s));
     {
         StageTimer t(c, 5, s);
-        launch_tile_order(s, c->cam, c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>());
+        launch_tile_order(s, c->cam, c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), c->chunk_base.as<uint32_t>());
+        if (c->fcfg.k_buffer_size == 0)  // chunks a forward warp never reaches must read as "no hit" in the backward
+            GUT_CUDA(c, cudaMemsetAsync(c->hit_words.ptr, 0, words * 4, s));
         if (c->fcfg.k_buffer_size > 0)  // sorted 3DGUT (gut_render_kbuffer.cu)
             launch_render_forward_kbuffer(s, c->cam, c->fcfg, c->fcfg.k_buffer_size, rays_o, rays_d, particles, c->rgb.as<float>(),
                                           c->vals_out.as<uint32_t>(), c->ranges.as<uint32_t>(), out_rgba, out_dist, out_hits);
         else
             launch_render_forward(s, c->cam, c->fcfg, rays_o, rays_d, particles, c->rgb.as<float>(), c->vals_out.as<uint32_t>(),
-                                  c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), out_rgba, out_dist, out_hits);
+                                  c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), c->chunk_base.as<uint32_t>(),
+                                  c->hit_words.as<uint32_t>(), out_rgba, out_dist, out_hits);
     }
     c->launches += 2;
     GUT_CUDA(c, cudaGetLastError());
@@ -493,6 +500,7 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     c->num_isect = total;
     c->num_tiles = tiles;
     c->fwd_stream = s;
+    c->fwd_camera = *cam;
     c->have_forward = true;
     return 0;
 }
@@ -505,6 +513,9 @@ static int backward_impl(gutb200_ctx* c, void* stream, const gutb200_camera* cam
     // the backward replays the sorted lists of the immediately preceding forward (gutRenderer.cu:436-440)
     if (!c->have_forward || c->fwd_stream != s || c->n != n || c->cam.width != cam->width || c->cam.height != cam->height)
         return fail(c, "backward needs the forward context of the same stream / particle count / resolution");
+    // the lists, the projection and the hit words are those of the forward's camera: a different view in between is an error, not a silent mix
+    if (memcmp(&c->fwd_camera, cam, sizeof(gutb200_camera)) != 0)
+        return fail(c, "backward was called with a camera that differs from the immediately preceding forward's (poses / intrinsics)");
     GUT_CUDA(c, cudaSetDevice(c->device));
     if (c->cfg.enable_timings) {
         GUT_CUDA(c, cudaEventRecord(c->ev[2], s));
@@ -519,14 +530,14 @@ static int backward_impl(gutb200_ctx* c, void* stream, const gutb200_camera* cam
                                            c->grad_acc.as<float>());
         else
             launch_render_backward(s, c->cam, c->fcfg, rays_o, rays_d, particles, c->rgb.as<float>(), c->vals_out.as<uint32_t>(),
-                                   c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), out_rgba, d_rgba, out_dist, d_dist,
-                                   c->grad_acc.as<float>());
+                                   c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), c->chunk_base.as<uint32_t>(),
+                                   c->hit_words.as<uint32_t>(), out_rgba, d_rgba, out_dist, d_dist, c->grad_acc.as<float>());
         c->launches++;
     }
     if (n > 0) {
         StageTimer t(c, 7, s);
-        launch_project_backward(s, c->cam, n, particles, sph, sph_degree, c->rgb.as<float>(), c->tiles_count.as<uint32_t>(),
-                                c->grad_acc.as<float>(), d_particles, d_sph, compact);
+        launch_project_backward(s, c->cam, n, particles, sph, sph_degree, c->rgb.as<float>(), c->tiles_count.as<uint32_t>(), rays_o,
+                                c->grad_acc.as<float>(), d_particles, d_sph, compact, /*canon=*/c->fcfg.k_buffer_size == 0);
         c->launches++;
     }
     GUT_CUDA(c, cudaGetLastError());
@@ -689,6 +700,58 @@ int gutb200_debug_copy(gutb200_ctx* c, int what, void* dst, size_t bytes) {
     }
     if (bytes != have) return fail(c, "debug buffer %d holds %zu bytes, caller asked for %zu", what, have, bytes);
     if (have) GUT_CUDA(c, cudaMemcpy(dst, src, have, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// Work counters of the last forward (debug): re-walks its lists with the counting instantiation of the forward kernel.
+// counters8: tests_ref, tests_exec, hits, fwd_iters, hit_iters, screens, bwd_lanes, 0 (see WorkCounters in gut_render.cu)
+int gutb200_debug_work_counters(gutb200_ctx* c, const float* particles, const float* rays_o, const float* rays_d, uint64_t* counters8) {
+    if (!c || !c->have_forward) return fail(c, "no forward context");
+    if (c->fcfg.k_buffer_size != 0) return fail(c, "work counters exist for the unsorted path (k_buffer_size 0) only");
+    GUT_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->fwd_stream;
+    unsigned long long* dctr = nullptr;
+    GUT_CUDA(c, cudaMalloc(&dctr, 64));
+    cudaMemsetAsync(dctr, 0, 64, s);
+    for (int i = 0; i < 8; ++i) counters8[i] = 0;
+    if (c->num_isect > 0)
+        launch_count_work(s, c->cam, c->fcfg, rays_o, rays_d, particles, c->rgb.as<float>(), c->vals_out.as<uint32_t>(), c->ranges.as<uint32_t>(),
+                          c->tile_order.as<uint32_t>(), c->chunk_base.as<uint32_t>(), c->hit_words.as<uint32_t>(), dctr);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaMemcpy(counters8, dctr, 64, cudaMemcpyDeviceToHost);
+    cudaFree(dctr);
+    GUT_CUDA(c, e);
+    return 0;
+}
+
+// FP32 FMA throughput of this GPU (debug): best of `repeats` launches of the micro-benchmark in gut_debug.cu, in TFLOP/s
+int gutb200_debug_fma_peak(gutb200_ctx* c, int repeats, float* tflops) {
+    if (!c || !tflops) return 1;
+    GUT_CUDA(c, cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    GUT_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 2048;
+    float* sink = nullptr;
+    GUT_CUDA(c, cudaMalloc(&sink, 4));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 0.f;
+    for (int r = 0; r < repeats + 1; ++r) {  // first launch is a warm-up
+        cudaEventRecord(a, c->own_stream);
+        launch_fma_peak(c->own_stream, blocks, iters, sink);
+        cudaEventRecord(b, c->own_stream);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        const double flops = static_cast<double>(blocks) * 256.0 * iters * 16.0 * 8.0 * 2.0;
+        if (r > 0 && ms > 0.f) best = fmaxf(best, static_cast<float>(flops / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(sink);
+    *tflops = best;
+    GUT_CUDA(c, cudaGetLastError());
     return 0;
 }
 

@@ -62,14 +62,21 @@ void launch_expand(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cf
 void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint32_t* sorted_keys, uint32_t* ranges);
 void launch_synth_keys(cudaStream_t s, int64_t num, const uint32_t* tiles, const uint32_t* vals, const float* depth, uint64_t* out);
 
-void launch_tile_order(cudaStream_t s, const FrameCamera& cam, const uint32_t* ranges, uint32_t* tile_order);
+// hit words: one 32-bit word per (32-entry chunk of a tile list, warp of the tile's CTA); tile t's slice starts at chunk_base[t] * 8 words
+inline size_t hit_words_capacity(int64_t num_isect, int64_t tiles) { return (static_cast<size_t>(num_isect) / 32 + static_cast<size_t>(tiles) + 1) * 8; }
+void launch_tile_order(cudaStream_t s, const FrameCamera& cam, const uint32_t* ranges, uint32_t* tile_order, uint32_t* chunk_base);
 void launch_render_forward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
                            const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
-                           const uint32_t* ranges, const uint32_t* tile_order, float* out_rgba, float* out_dist, float* out_hits);
+                           const uint32_t* ranges, const uint32_t* tile_order, const uint32_t* chunk_base, uint32_t* hit_words, float* out_rgba,
+                           float* out_dist, float* out_hits);
+void launch_count_work(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o, const float* rays_d,
+                       const float* particles, const float* rgb, const uint32_t* sorted_values, const uint32_t* ranges,
+                       const uint32_t* tile_order, const uint32_t* chunk_base, uint32_t* hit_words, unsigned long long* counters8);
 void launch_render_backward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
                             const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
-                            const uint32_t* ranges, const uint32_t* tile_order, const float* out_rgba, const float* d_rgba,
-                            const float* out_dist, const float* d_dist, float* grad_acc);
+                            const uint32_t* ranges, const uint32_t* tile_order, const uint32_t* chunk_base, const uint32_t* hit_words,
+                            const float* out_rgba, const float* d_rgba, const float* out_dist, const float* d_dist, float* grad_acc);
+void launch_fma_peak(cudaStream_t s, int blocks, int iters, float* sink);
 void launch_render_forward_kbuffer(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int K, const float* rays_o, const float* rays_d,
                                    const float* particles, const float* rgb, const uint32_t* sorted_values, const uint32_t* ranges,
                                    float* out_rgba, float* out_dist, float* out_hits);
@@ -77,8 +84,8 @@ void launch_render_backward_kbuffer(cudaStream_t s, const FrameCamera& cam, cons
                                     const float* particles, const float* rgb, const uint32_t* sorted_values, const uint32_t* ranges,
                                     const float* out_rgba, const float* d_rgba, const float* out_dist, const float* d_dist, float* grad_acc);
 void launch_project_backward(cudaStream_t s, const FrameCamera& cam, int64_t n, const float* particles, const float* sph,
-                             int sph_degree, const float* rgb, const uint32_t* tiles_count, float* grad_acc,
-                             float* d_particles, float* d_sph, bool compact = false);
+                             int sph_degree, const float* rgb, const uint32_t* tiles_count, const float* rays_o, float* grad_acc,
+                             float* d_particles, float* d_sph, bool compact, bool canon);
 void launch_sph_from_views(cudaStream_t s, int64_t n, const float* particles, int sph_degree, int views, const float* view_positions,
                            const float* d_radiance_all, float* d_sph);
 

@@ -149,9 +149,10 @@ __device__ __forceinline__ bool tile_common_origin(const FrameCamera& cam, const
     return __syncthreads_and(same);
 }
 
-// exact test + compositing of one (pixel, staged entry j) pair
+// exact test + compositing of one (pixel, staged entry j) pair; returns whether the accept test passed (before the t-range test:
+// the reference's backward does not re-apply the range test)
 template <int DEG, bool UNIFORM>
-__device__ __forceinline__ void forward_pair(const FrameConfig& cfg, const FwdSmem& sm, int j, const Ray& ray, bool& alive, float& T, float& cr,
+__device__ __forceinline__ bool forward_pair(const FrameConfig& cfg, const FwdSmem& sm, int j, const Ray& ray, bool& alive, float& T, float& cr,
                                              float& cg, float& cb, float& dist, uint32_t& hits) {
     const float4 m0 = sm.m0[j], m1 = sm.m1[j], m2 = sm.m2[j];
     float gox, goy, goz;
@@ -174,7 +175,8 @@ __device__ __forceinline__ void forward_pair(const FrameConfig& cfg, const FwdSm
     const float gres = kernel_response<DEG>(gray);
     const float4 sd = sm.sd[j];
     const float alpha = fminf(cfg.max_alpha, gres * sd.w);
-    if ((gres > cfg.min_kernel_density) && (alpha > cfg.min_alpha)) {
+    const bool accept = (gres > cfg.min_kernel_density) && (alpha > cfg.min_alpha);
+    if (accept) {
         const float pd = -(gdx * gox + gdy * goy + gdz * goz);
         const float hx = sd.x * gdx * pd, hy = sd.y * gdy * pd, hz = sd.z * gdz * pd;
         const float t = sqrtf(hx * hx + hy * hy + hz * hz);
@@ -192,14 +194,27 @@ __device__ __forceinline__ void forward_pair(const FrameConfig& cfg, const FwdSm
             if (T < cfg.min_transmittance) alive = false;
         }
     }
+    return accept;
 }
 
-template <int DEG, bool UNIFORM>
+// Work counters (debug entry point gutb200_debug_work_counters; COUNT instantiations never run on the product path).
+//   0 tests_ref   (pixel, entry) pairs the reference's loop evaluates: every live pixel tests every entry of its tile list
+//   1 tests_exec  lane-level exact tests our forward executes after sub-tile culling
+//   2 hits        accepted pairs (the set the backward's adjoint runs on)
+//   3 fwd_iters   warp iterations of the forward's exact test     4 hit_iters  warp iterations with >= 1 accepting lane (= backward's iterations)
+//   5 screens     lane-level sub-tile culling screens             6 bwd_lanes  live lanes summed over hit_iters (lane-level tests of the backward)
+struct WorkCounters {
+    unsigned long long v[8];
+};
+
+template <int DEG, bool UNIFORM, bool COUNT>
 __device__ __forceinline__ void forward_tile(const FrameConfig& cfg, FwdSmem& sm, const WarpFrame& wf, const Ray& ray, float o0x, float o0y,
                                              float o0z, int tid, uint32_t begin, uint32_t end, const float* __restrict__ particles,
-                                             const float* __restrict__ rgb, const uint32_t* __restrict__ sorted_values, bool& alive,
-                                             float& T, float& cr, float& cg, float& cb, float& dist, uint32_t& hits) {
+                                             const float* __restrict__ rgb, const uint32_t* __restrict__ sorted_values,
+                                             uint32_t* __restrict__ hit_words, bool& alive, float& T, float& cr, float& cg, float& cb,
+                                             float& dist, uint32_t& hits, WorkCounters* __restrict__ ctr) {
     const int lane = tid & 31;
+    unsigned long long c_ref = 0, c_exec = 0, c_hits = 0, c_iters = 0, c_hit_iters = 0, c_screens = 0, c_bwd_lanes = 0;
     for (uint32_t base = begin; base < end; base += kBatch) {
         if (__syncthreads_and(!alive)) break;
         const uint32_t k = base + tid;
@@ -228,6 +243,9 @@ __device__ __forceinline__ void forward_tile(const FrameConfig& cfg, FwdSmem& sm
         }
         __syncthreads();
         const int count = min(kBatch, static_cast<int>(end - base));
+        // this warp's hit words of the batch: bit e of word c/32 = "some pixel of the warp's 8x4 block accepted entry c + e" -- the backward
+        // walks only those entries (a necessary condition of its own exact test, so it drops nothing it would have accepted)
+        uint32_t* words = hit_words + (static_cast<size_t>(base - begin) >> 5) * (kTilePixels / 32) + (tid >> 5);
         if (UNIFORM) {
             // chunks of 32 entries: lane k screens entry k against the warp's pixel block, the warp walks the survivors
             for (int c = 0; c < count; c += 32) {
@@ -237,21 +255,75 @@ __device__ __forceinline__ void forward_tile(const FrameConfig& cfg, FwdSmem& sm
                 if (wf.on && cand) {
                     const float4 m0 = sm.m0[e], m1 = sm.m1[e], m2 = sm.m2[e];
                     cand = block_candidate<DEG>(cfg, wf, m0.x, m0.y, m0.z, m1.x, m1.y, m1.z, m2.x, m2.y, m2.z, m0.w, m1.w, m2.w, sm.sd[e].w);
+                    if (COUNT) c_screens++;
                 }
                 unsigned todo = __ballot_sync(kFull, cand);
+                uint32_t word = 0;
+                int prev = c;
                 while (todo) {
-                    const int j = c + __ffs(todo) - 1;
+                    const int b = __ffs(todo) - 1;
+                    const int j = c + b;
                     todo &= todo - 1;
-                    if (alive) forward_pair<DEG, true>(cfg, sm, j, ray, alive, T, cr, cg, cb, dist, hits);
+                    int live_n = 0;
+                    if (COUNT) {
+                        live_n = __popc(__ballot_sync(kFull, alive));
+                        c_ref += static_cast<unsigned long long>(live_n) * (j - prev + 1);
+                        prev = j + 1;
+                        c_iters++;
+                        if (alive) c_exec++;
+                    }
+                    bool acc = false;
+                    if (alive) acc = forward_pair<DEG, true>(cfg, sm, j, ray, alive, T, cr, cg, cb, dist, hits);
+                    const unsigned accs = __ballot_sync(kFull, acc);
+                    if (accs) word |= 1u << b;
+                    if (COUNT && accs) {
+                        c_hit_iters++;
+                        c_bwd_lanes += live_n;
+                        c_hits += acc ? 1 : 0;
+                    }
                 }
+                if (COUNT) {
+                    const unsigned live = __ballot_sync(kFull, alive);
+                    c_ref += static_cast<unsigned long long>(__popc(live)) * (min(c + 32, count) - prev);
+                }
+                if (lane == 0) words[(c >> 5) * (kTilePixels / 32)] = word;
             }
         } else {
-            for (int j = 0; alive && j < count; ++j) forward_pair<DEG, false>(cfg, sm, j, ray, alive, T, cr, cg, cb, dist, hits);
+            // per-pixel origins: no warp-level screening; the backward gets all-ones words for these tiles
+            if (lane == 0)
+                for (int c = 0; c < count; c += 32) words[(c >> 5) * (kTilePixels / 32)] = 0xFFFFFFFFu;
+            for (int j = 0; alive && j < count; ++j) {
+                const bool acc = forward_pair<DEG, false>(cfg, sm, j, ray, alive, T, cr, cg, cb, dist, hits);
+                if (COUNT) {
+                    c_exec++;
+                    c_hits += acc ? 1 : 0;
+                }
+            }
+        }
+    }
+    if (COUNT) {
+        // c_ref, c_iters, c_hit_iters are warp-uniform (lane 0 reports); the others are per lane
+        if (!UNIFORM) c_ref = 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c_exec += __shfl_xor_sync(kFull, c_exec, o);
+            c_hits += __shfl_xor_sync(kFull, c_hits, o);
+            c_screens += __shfl_xor_sync(kFull, c_screens, o);
+        }
+        if (lane == 0) {
+            if (!UNIFORM) c_ref = c_exec;
+            atomicAdd(&ctr->v[0], c_ref);
+            atomicAdd(&ctr->v[1], c_exec);
+            atomicAdd(&ctr->v[2], c_hits);
+            atomicAdd(&ctr->v[3], c_iters);
+            atomicAdd(&ctr->v[4], c_hit_iters);
+            atomicAdd(&ctr->v[5], c_screens);
+            atomicAdd(&ctr->v[6], c_bwd_lanes);
         }
     }
 }
 
-template <int DEG>
+template <int DEG, bool COUNT>
 __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera cam, FrameConfig cfg,
                                                                      const float* __restrict__ rays_o,
                                                                      const float* __restrict__ rays_d,
@@ -259,8 +331,10 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
                                                                      const float* __restrict__ rgb,
                                                                      const uint32_t* __restrict__ sorted_values,
                                                                      const uint32_t* __restrict__ ranges,
-                                                                     const uint32_t* __restrict__ tile_order, float* __restrict__ out_rgba,
-                                                                     float* __restrict__ out_dist, float* __restrict__ out_hits) {
+                                                                     const uint32_t* __restrict__ tile_order,
+                                                                     const uint32_t* __restrict__ chunk_base, uint32_t* __restrict__ hit_words,
+                                                                     float* __restrict__ out_rgba, float* __restrict__ out_dist,
+                                                                     float* __restrict__ out_hits, WorkCounters* __restrict__ ctr) {
     __shared__ FwdSmem sm;
     const int tile = tile_order[blockIdx.x];  // heaviest tiles first (tile_order_kernel): shortens the tail of the grid
     const int tid = threadIdx.x;
@@ -281,10 +355,12 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
     uint32_t hits = 0;
     bool alive = valid;
     const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
+    uint32_t* words = hit_words + static_cast<size_t>(chunk_base[tile]) * (kTilePixels / 32);
     if (uniform)
-        forward_tile<DEG, true>(cfg, sm, wf, ray, o0x, o0y, o0z, tid, begin, end, particles, rgb, sorted_values, alive, T, cr, cg, cb, dist, hits);
+        forward_tile<DEG, true, COUNT>(cfg, sm, wf, ray, o0x, o0y, o0z, tid, begin, end, particles, rgb, sorted_values, words, alive, T, cr, cg, cb, dist, hits, ctr);
     else
-        forward_tile<DEG, false>(cfg, sm, wf, ray, o0x, o0y, o0z, tid, begin, end, particles, rgb, sorted_values, alive, T, cr, cg, cb, dist, hits);
+        forward_tile<DEG, false, COUNT>(cfg, sm, wf, ray, o0x, o0y, o0z, tid, begin, end, particles, rgb, sorted_values, words, alive, T, cr, cg, cb, dist, hits, ctr);
+    if (COUNT) return;  // the counting pass leaves the frame's outputs alone
 
     if (valid) {  // finalizeRay (rayPayload.cuh:160-193); invalid rays keep the initial buffer values
         reinterpret_cast<float4*>(out_rgba)[pix] = make_float4(cr, cg, cb, 1.0f - T);
@@ -297,15 +373,31 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
     }
 }
 
-// Order tiles by decreasing list length (bucketed by log2): one small single-CTA kernel per frame.
-__global__ void __launch_bounds__(1024) tile_order_kernel(int num_tiles, const uint32_t* __restrict__ ranges, uint32_t* __restrict__ order) {
+// Order tiles by decreasing list length (bucketed by log2) and lay out the per-tile slices of the hit-word buffer
+// (chunk_base[t] = exclusive prefix sum of ceil(list length / 32)): one small single-CTA kernel per frame.
+__global__ void __launch_bounds__(1024) tile_order_kernel(int num_tiles, const uint32_t* __restrict__ ranges, uint32_t* __restrict__ order,
+                                                          uint32_t* __restrict__ chunk_base) {
     __shared__ uint32_t hist[34];
+    __shared__ uint32_t warp_sums[32];
     if (threadIdx.x < 34) hist[threadIdx.x] = 0;
     __syncthreads();
     for (int t = threadIdx.x; t < num_tiles; t += blockDim.x) {
         const uint32_t c = ranges[t * 2 + 1] - ranges[t * 2];
         atomicAdd(&hist[__clz(c) + 1], 1u);  // __clz(0) = 32 -> last bucket; long lists -> small bucket index
     }
+    // chunk_base: every thread owns a contiguous strip of tiles
+    const int strip = (num_tiles + static_cast<int>(blockDim.x) - 1) / static_cast<int>(blockDim.x);
+    const int t0 = min(static_cast<int>(threadIdx.x) * strip, num_tiles), t1 = min(t0 + strip, num_tiles);
+    uint32_t mine = 0;
+    for (int t = t0; t < t1; ++t) mine += (ranges[t * 2 + 1] - ranges[t * 2] + 31u) >> 5;
+    uint32_t incl = mine;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t run = 0;
@@ -314,8 +406,19 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(int num_tiles, const u
             hist[b] = run;
             run += h;
         }
+        run = 0;
+        for (int w = 0; w < 32; ++w) {
+            const uint32_t v = warp_sums[w];
+            warp_sums[w] = run;
+            run += v;
+        }
     }
     __syncthreads();
+    uint32_t run = warp_sums[warp] + incl - mine;
+    for (int t = t0; t < t1; ++t) {
+        chunk_base[t] = run;
+        run += (ranges[t * 2 + 1] - ranges[t * 2] + 31u) >> 5;
+    }
     for (int t = threadIdx.x; t < num_tiles; t += blockDim.x) {
         const uint32_t c = ranges[t * 2 + 1] - ranges[t * 2];
         order[atomicAdd(&hist[__clz(c) + 1], 1u)] = static_cast<uint32_t>(t);
@@ -324,13 +427,24 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(int num_tiles, const u
 
 // ----------------------------------------------------------------------------------------------------------
 // G7 backward
+//
+// What is summed per particle, and where: with gro = S^-1 R (o - mu) and grdu = S^-1 R d the hand adjoint
+// (gaussianParticles.cuh:684-747) ends in terms that are LINEAR in per-particle constants once the ray origin is fixed:
+//     d pos   = -R^T (S^-1 groGrd)                      d scale_i = <per-pair part>_i - gro_i (S^-1 groGrd)_i
+//     d quat  = J(q)^T vec( (S^-1 groGrd) (o - mu)^T + (S^-1 grduGrd) d^T )
+// The kernel therefore accumulates, per particle, the canonical sums  G = sum groGrd (slots 0..2),  the per-pair scale part
+// (slots 8..10) and the quaternion contraction of the d-dependent outer product only (slots 4..7), all relative to the FRAME origin
+// o_f = origin of the frame's first ray; G8 (project_backward_kernel<.., CANON = true>) applies the three linear maps once per
+// particle instead of once per (pixel, particle).  Pixels whose origin differs from o_f (GENERAL tiles: per-pixel origins) add the
+// exact correction terms, so the result is the reference's gradient for any ray bundle.
+//
 // staged record, 7 x float4:
-//   r0 = rot row0, pos.x   r1 = rot row1, pos.y   r2 = rot row2, pos.z   (rows of quaternionWXYZToMatrix = columns of R)
+//   r0, r1, r2 = rows of quaternionWXYZToMatrix (columns of R); .w = canonical frame origin S^-1 R (o_f - mu) (FAST) | position (GENERAL)
 //   sc = scale.xyz, density     is = 1/scale.xyz, _     qt = quat wxyz     cl = clamped rgb, particle index bits
 
 struct BwdSmem {
     float4 r0[kBatch], r1[kBatch], r2[kBatch], sc[kBatch], is[kBatch], qt[kBatch], cl[kBatch];
-    float4 go[kBatch];  // canonical origin of the tile's common ray origin (UNIFORM path)
+    uint32_t hw[(kBatch / 32) * (kTilePixels / 32)];  // the forward's hit words of this batch, [chunk][warp]
 };
 
 // sum 16 per-lane values over the warp; lane L returns the total of component (L >> 1). 16 SHFL in all.
@@ -366,16 +480,135 @@ __device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lan
     return v[0];
 }
 
-template <int DEG, bool UNIFORM>
-__device__ __forceinline__ void backward_tile(const FrameConfig& cfg, BwdSmem& sm, const WarpFrame& wf, const Ray& ray, float o0x, float o0y,
-                                              float o0z, int tid, int lane, uint32_t begin, uint32_t end, const float* __restrict__ particles,
-                                              const float* __restrict__ rgb, const uint32_t* __restrict__ sorted_values, bool alive,
-                                              float Cix, float Ciy, float Ciz, float Cgx, float Cgy, float Cgz, float Tint, float Tgrad,
-                                              float Dint, float Dgrad, float* __restrict__ grad_acc) {
-    float T = 1.f, Cx = 0.f, Cy = 0.f, Cz = 0.f, D = 0.f;
+// per-pixel backward state (initializeBackwardRay, kernels/cuda/common/rayPayloadBackward.cuh:31-73)
+struct BwdRay {
+    float Cix, Ciy, Ciz, Cgx, Cgy, Cgz, Tint, Tgrad, Dint, Dgrad;
+    float T, Cx, Cy, Cz, D;
+};
+
+// exact test + adjoint of one (pixel, staged entry j) pair (processHitBwd, gaussianParticles.cuh:484-751); fills g[] and returns true on a hit
+template <int DEG, bool FAST>
+__device__ __forceinline__ bool backward_pair(const FrameConfig& cfg, const BwdSmem& sm, int j, const Ray& ray, float dox, float doy, float doz,
+                                              bool depth_grads, BwdRay& st, bool& alive, float (&g)[16]) {
+    const float4 r0 = sm.r0[j], r1 = sm.r1[j], r2 = sm.r2[j], sc = sm.sc[j], is = sm.is[j];
+    float gox, goy, goz;                                                                          // gro
+    float pcx = 0.f, pcy = 0.f, pcz = 0.f;
+    if (FAST) {
+        gox = r0.w; goy = r1.w; goz = r2.w;
+    } else {
+        pcx = ray.ox - r0.w; pcy = ray.oy - r1.w; pcz = ray.oz - r2.w;                              // gposc
+        gox = is.x * (r0.x * pcx + r0.y * pcy + r0.z * pcz);
+        goy = is.y * (r1.x * pcx + r1.y * pcy + r1.z * pcz);
+        goz = is.z * (r2.x * pcx + r2.y * pcy + r2.z * pcz);
+    }
+    const float drx = r0.x * ray.dx + r0.y * ray.dy + r0.z * ray.dz;                                // rayDirR
+    const float dry = r1.x * ray.dx + r1.y * ray.dy + r1.z * ray.dz;
+    const float drz = r2.x * ray.dx + r2.y * ray.dy + r2.z * ray.dz;
+    const float ux = is.x * drx, uy = is.y * dry, uz = is.z * drz;                                  // grdu
+    const float l = ux * ux + uy * uy + uz * uz;
+    const float il = l > 0.f ? rsqrtf(l) : 1.f;
+    const float gdx = ux * il, gdy = uy * il, gdz = uz * il;                                        // grd
+    const float ccx = gdy * goz - gdz * goy, ccy = gdz * gox - gdx * goz, ccz = gdx * goy - gdy * gox;  // gcrod
+    const float gray = ccx * ccx + ccy * ccy + ccz * ccz;
+    const float gres = kernel_response<DEG>(gray);
+    const float dns = sc.w;
+    const float alpha = fminf(cfg.max_alpha, gres * dns);
+    if (!((gres > cfg.min_kernel_density) && (alpha > cfg.min_alpha))) return false;
+
+    const float4 cl = sm.cl[j];
+    const float T = st.T;
+    const float weight = alpha * T;
+    const float nextT = (1.f - alpha) * T;
+    const bool last = nextT <= cfg.min_transmittance;
+    const float inv_next = last ? 0.f : 1.0f / nextT;
+    const float pd = -(gdx * gox + gdy * goy + gdz * goz);
+
+    // depth branch (:545-580); skipped by warps whose pixels carry no distance gradient (an RGB-only loss)
+    float a_hit = 0.f, sd = 0.f, hgx = 0.f, hgy = 0.f, hgz = 0.f, ddx = 0.f, ddy = 0.f, ddz = 0.f;
+    if (depth_grads) {
+        ddx = gdx * pd; ddy = gdy * pd; ddz = gdz * pd;                                             // grdd
+        const float hx = sc.x * ddx, hy = sc.y * ddy, hz = sc.z * ddz;                              // grds
+        const float gsq = hx * hx + hy * hy + hz * hz;
+        const float gdist = sqrtf(gsq);
+        st.D += weight * gdist;
+        const float resD = fmaxf((st.Dint - st.D) * inv_next, 0.f);
+        a_hit = (gdist - resD) * T * st.Dgrad;
+        const float hs = gsq > 0.f ? (weight / gdist) * st.Dgrad : 0.f;
+        hgx = hx * hs; hgy = hy * hs; hgz = hz * hs;                                                // grdsRayHitGrd
+        sd = hgx * sc.x * gdx + hgy * sc.y * gdy + hgz * sc.z * gdz;                                // grdScaledDot
+    }
+    // opacity branch (:586-587)
+    const float resT = alpha < 0.999999f ? st.Tint / (1.f - alpha) : T;
+    const float a_dns = resT * -st.Tgrad;
+    // radiance branch (:602-612)
+    g[12] = st.Cgx * weight; g[13] = st.Cgy * weight; g[14] = st.Cgz * weight;
+    st.Cx += weight * cl.x; st.Cy += weight * cl.y; st.Cz += weight * cl.z;
+    const float rcx = fmaxf((st.Cix - st.Cx) * inv_next, 0.f);
+    const float rcy = fmaxf((st.Ciy - st.Cy) * inv_next, 0.f);
+    const float rcz = fmaxf((st.Ciz - st.Cz) * inv_next, 0.f);
+    const float common = a_hit + a_dns + T * ((cl.x - rcx) * st.Cgx + (cl.y - rcy) * st.Cgy + (cl.z - rcz) * st.Cgz);
+    g[3] = gres * common;                                                                           // d density (:624-627)
+    const float gray_g = kernel_response_grad<DEG>(gray, gres, dns * common);                       // (:639-648)
+    // gray = |grd x gro|^2  (:684-702)
+    const float kx = 2.f * ccx * gray_g, ky = 2.f * ccy * gray_g, kz = 2.f * ccz * gray_g;          // gcrodGrd
+    float gd_gx = kz * goy - ky * goz, gd_gy = kx * goz - kz * gox, gd_gz = ky * gox - kx * goy;    // grdGrd
+    float go_gx = ky * gdz - kz * gdy, go_gy = kz * gdx - kx * gdz, go_gz = kx * gdy - ky * gdx;    // groGrd
+    if (depth_grads) {                                                                              // + grdRayHitGrd, groRayHitGrd
+        gd_gx += sc.x * hgx * pd - gox * sd; gd_gy += sc.y * hgy * pd - goy * sd; gd_gz += sc.z * hgz * pd - goz * sd;
+        go_gx -= gdx * sd; go_gy -= gdy * sd; go_gz -= gdz * sd;
+    }
+    g[0] = go_gx; g[1] = go_gy; g[2] = go_gz;          // canonical: G8 turns the sums into d pos, the gro part of d scale and of d quat
+    // grd = normalize(grdu)  (:729-731, safe_normalize_bw mathUtils.cuh:410-420)
+    const float il3 = il * il * il;
+    const float du = gd_gx * ux + gd_gy * uy + gd_gz * uz;
+    const float ug_x = l > 0.f ? il * gd_gx - il3 * ux * du : 0.f;                                  // grduGrd
+    const float ug_y = l > 0.f ? il * gd_gy - il3 * uy * du : 0.f;
+    const float ug_z = l > 0.f ? il * gd_gz - il3 * uz * du : 0.f;
+    // grdu = (1/s) rayDirR  (:733-738)
+    const float rdg_x = is.x * ug_x, rdg_y = is.y * ug_y, rdg_z = is.z * ug_z;                      // rayDirRGrd
+    float sgx = ddx * hgx - ux * rdg_x, sgy = ddy * hgy - uy * rdg_y, sgz = ddz * hgz - uz * rdg_z; // gsclRayHitGrd, rayDirR/s^2 = grdu/s
+    // rotation rows receive dM_i = rdg_i * d  (+ prg_i * (o - o_f) for pixels off the frame origin; the o_f - mu part is G8's)
+    float m00 = rdg_x * ray.dx, m01 = rdg_x * ray.dy, m02 = rdg_x * ray.dz;
+    float m10 = rdg_y * ray.dx, m11 = rdg_y * ray.dy, m12 = rdg_y * ray.dz;
+    float m20 = rdg_z * ray.dx, m21 = rdg_z * ray.dy, m22 = rdg_z * ray.dz;
+    if (!FAST) {
+        const float prg_x = is.x * go_gx, prg_y = is.y * go_gy, prg_z = is.z * go_gz;               // gposcrGrd
+        // gro(pixel) - gro(frame) = S^-1 R (o - o_f)
+        sgx -= is.x * (r0.x * dox + r0.y * doy + r0.z * doz) * prg_x;
+        sgy -= is.y * (r1.x * dox + r1.y * doy + r1.z * doz) * prg_y;
+        sgz -= is.z * (r2.x * dox + r2.y * doy + r2.z * doz) * prg_z;
+        m00 += prg_x * dox; m01 += prg_x * doy; m02 += prg_x * doz;
+        m10 += prg_y * dox; m11 += prg_y * doy; m12 += prg_y * doz;
+        m20 += prg_z * dox; m21 += prg_z * doy; m22 += prg_z * doz;
+    }
+    g[8] = sgx; g[9] = sgy; g[10] = sgz;
+    const float4 q = sm.qt[j];                                                                      // matmul_bw_quat (:719-747)
+    const float qr = q.x, qx = q.y, qy = q.z, qz = q.w;
+    g[4] = 2.f * (qz * (m01 - m10) + qy * (m20 - m02) + qx * (m12 - m21));
+    g[5] = 2.f * (qy * (m01 + m10) + qz * (m02 + m20) + qr * (m12 - m21)) - 4.f * qx * (m11 + m22);
+    g[6] = 2.f * (qx * (m01 + m10) + qr * (m20 - m02) + qz * (m12 + m21)) - 4.f * qy * (m00 + m22);
+    g[7] = 2.f * (qr * (m01 - m10) + qx * (m02 + m20) + qy * (m12 + m21)) - 4.f * qz * (m00 + m11);
+    st.T = nextT;
+    if (nextT < cfg.min_transmittance) alive = false;
+    return true;
+}
+
+template <int DEG, bool FAST>
+__device__ __forceinline__ void backward_tile(const FrameConfig& cfg, BwdSmem& sm, const Ray& ray, float ofx, float ofy, float ofz, int tid,
+                                              int lane, uint32_t begin, uint32_t end, const float* __restrict__ particles,
+                                              const float* __restrict__ rgb, const uint32_t* __restrict__ sorted_values,
+                                              const uint32_t* __restrict__ hit_words, bool use_words, bool alive, BwdRay& st,
+                                              float* __restrict__ grad_acc) {
+    const float dox = ray.ox - ofx, doy = ray.oy - ofy, doz = ray.oz - ofz;   // zero in FAST tiles
+    const bool depth_grads = __any_sync(kFull, alive && (st.Dgrad != 0.f));
     for (uint32_t base = begin; base < end; base += kBatch) {
         if (__syncthreads_and(!alive)) break;
         const uint32_t k = base + tid;
+        if (tid < (kBatch / 32) * (kTilePixels / 32)) {
+            const uint32_t chunk = (base - begin) / 32 + (tid >> 3);
+            const bool in_list = base + (tid >> 3) * 32 < end;
+            sm.hw[tid] = (use_words && in_list) ? hit_words[static_cast<size_t>(chunk) * (kTilePixels / 32) + (tid & 7)] : 0xFFFFFFFFu;
+        }
         if (k < end) {
             const uint32_t idx = sorted_values[k];
             const float4* p4 = reinterpret_cast<const float4*>(particles) + static_cast<size_t>(idx) * 3;
@@ -383,152 +616,63 @@ __device__ __forceinline__ void backward_tile(const FrameConfig& cfg, BwdSmem& s
             const float r = q.x, x = q.y, y = q.z, z = q.w;
             const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
             const float rx = r * x, ry = r * y, rz = r * z;
-            sm.r0[tid] = make_float4(1.f - 2.f * (yy + zz), 2.f * (xy + rz), 2.f * (xz - ry), a.x);
-            sm.r1[tid] = make_float4(2.f * (xy - rz), 1.f - 2.f * (xx + zz), 2.f * (yz + rx), a.y);
-            sm.r2[tid] = make_float4(2.f * (xz + ry), 2.f * (yz - rx), 1.f - 2.f * (xx + yy), a.z);
+            float4 t0 = make_float4(1.f - 2.f * (yy + zz), 2.f * (xy + rz), 2.f * (xz - ry), a.x);
+            float4 t1 = make_float4(2.f * (xy - rz), 1.f - 2.f * (xx + zz), 2.f * (yz + rx), a.y);
+            float4 t2 = make_float4(2.f * (xz + ry), 2.f * (yz - rx), 1.f - 2.f * (xx + yy), a.z);
+            if (FAST) {  // .w carries the canonical frame origin instead of the particle position
+                const float vx = ofx - a.x, vy = ofy - a.y, vz = ofz - a.z;
+                t0.w = (t0.x * vx + t0.y * vy + t0.z * vz) / s.x;
+                t1.w = (t1.x * vx + t1.y * vy + t1.z * vz) / s.y;
+                t2.w = (t2.x * vx + t2.y * vy + t2.z * vz) / s.z;
+            }
+            sm.r0[tid] = t0;
+            sm.r1[tid] = t1;
+            sm.r2[tid] = t2;
             sm.sc[tid] = make_float4(s.x, s.y, s.z, a.w);
             sm.is[tid] = make_float4(1.0f / s.x, 1.0f / s.y, 1.0f / s.z, 0.f);
             sm.qt[tid] = q;
             sm.cl[tid] = make_float4(fmaxf(rgb[idx * 3 + 0], 0.f), fmaxf(rgb[idx * 3 + 1], 0.f), fmaxf(rgb[idx * 3 + 2], 0.f),
                                      __uint_as_float(idx));
-            if (UNIFORM) {
-                const float vx = o0x - a.x, vy = o0y - a.y, vz = o0z - a.z;
-                const float4 t0 = sm.r0[tid], t1 = sm.r1[tid], t2 = sm.r2[tid];
-                sm.go[tid] = make_float4((t0.x * vx + t0.y * vy + t0.z * vz) / s.x, (t1.x * vx + t1.y * vy + t1.z * vz) / s.y,
-                                         (t2.x * vx + t2.y * vy + t2.z * vz) / s.z, 0.f);
-            }
         }
         __syncthreads();
         const int count = min(kBatch, static_cast<int>(end - base));
-        // chunks of 32 entries: lane k screens entry k against the warp's pixel block (UNIFORM tiles), the warp walks the survivors
+        // chunks of 32 entries; the warp walks the entries some pixel of its block accepted in the forward (hit words)
         for (int c = 0; c < count; c += 32) {
             if (__all_sync(kFull, !alive)) break;
-            const int e = c + lane;
-            bool cand = e < count;
-            if (UNIFORM && wf.on && cand) {
-                const float4 r0 = sm.r0[e], r1 = sm.r1[e], r2 = sm.r2[e], is = sm.is[e], g0 = sm.go[e];
-                cand = block_candidate<DEG>(cfg, wf, is.x * r0.x, is.x * r0.y, is.x * r0.z, is.y * r1.x, is.y * r1.y, is.y * r1.z, is.z * r2.x,
-                                            is.z * r2.y, is.z * r2.z, g0.x, g0.y, g0.z, sm.sc[e].w);
-            }
-            unsigned todo = __ballot_sync(kFull, cand);
+            unsigned todo = sm.hw[(c >> 5) * (kTilePixels / 32) + (tid >> 5)];
+            if (count - c < 32) todo &= (1u << (count - c)) - 1u;
             while (todo) {
-            const int j = c + __ffs(todo) - 1;
-            todo &= todo - 1;
-            float g[16];
+                const int j = c + __ffs(todo) - 1;
+                todo &= todo - 1;
+                float g[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) g[i] = 0.f;
-            bool hit = false;
-            if (alive) {
-                const float4 r0 = sm.r0[j], r1 = sm.r1[j], r2 = sm.r2[j], sc = sm.sc[j], is = sm.is[j];
-                // canonical ray (processHitBwd, gaussianParticles.cuh:520-532)
-                const float pcx = ray.ox - r0.w, pcy = ray.oy - r1.w, pcz = ray.oz - r2.w;              // gposc
-                float gox, goy, goz;                                                                      // gro
-                if (UNIFORM) {
-                    const float4 g0 = sm.go[j];
-                    gox = g0.x; goy = g0.y; goz = g0.z;
-                } else {
-                    gox = is.x * (r0.x * pcx + r0.y * pcy + r0.z * pcz);
-                    goy = is.y * (r1.x * pcx + r1.y * pcy + r1.z * pcz);
-                    goz = is.z * (r2.x * pcx + r2.y * pcy + r2.z * pcz);
+                for (int i = 0; i < 16; ++i) g[i] = 0.f;
+                bool hit = false;
+                if (alive) hit = backward_pair<DEG, FAST>(cfg, sm, j, ray, dox, doy, doz, depth_grads, st, alive, g);
+                if (__any_sync(kFull, hit)) {
+                    const float total = warp_transpose_reduce16(g, lane);
+                    if ((lane & 1) == 0) {
+                        const uint32_t idx = __float_as_uint(sm.cl[j].w);
+                        atomicAdd(grad_acc + static_cast<size_t>(idx) * kGradRow + (lane >> 1), total);
+                    }
+                    if (__all_sync(kFull, !alive)) break;
                 }
-                const float drx = r0.x * ray.dx + r0.y * ray.dy + r0.z * ray.dz;                          // rayDirR
-                const float dry = r1.x * ray.dx + r1.y * ray.dy + r1.z * ray.dz;
-                const float drz = r2.x * ray.dx + r2.y * ray.dy + r2.z * ray.dz;
-                const float ux = is.x * drx, uy = is.y * dry, uz = is.z * drz;                            // grdu
-                const float l = ux * ux + uy * uy + uz * uz;
-                const float il = l > 0.f ? rsqrtf(l) : 1.f;
-                const float gdx = ux * il, gdy = uy * il, gdz = uz * il;                                  // grd
-                const float ccx = gdy * goz - gdz * goy, ccy = gdz * gox - gdx * goz, ccz = gdx * goy - gdy * gox;  // gcrod
-                const float gray = ccx * ccx + ccy * ccy + ccz * ccz;
-                const float gres = kernel_response<DEG>(gray);
-                const float dns = sc.w;
-                const float alpha = fminf(cfg.max_alpha, gres * dns);
-                if ((gres > cfg.min_kernel_density) && (alpha > cfg.min_alpha)) {
-                    hit = true;
-                    const float4 cl = sm.cl[j];
-                    const float pd = -(gdx * gox + gdy * goy + gdz * goz);
-                    const float ddx = gdx * pd, ddy = gdy * pd, ddz = gdz * pd;                            // grdd
-                    const float hx = sc.x * ddx, hy = sc.y * ddy, hz = sc.z * ddz;                         // grds
-                    const float gsq = hx * hx + hy * hy + hz * hz;
-                    const float gdist = sqrtf(gsq);
-                    const float weight = alpha * T;
-                    const float nextT = (1.f - alpha) * T;
-                    const bool last = nextT <= cfg.min_transmittance;
-                    const float inv_next = last ? 0.f : 1.0f / nextT;
-
-                    // depth branch (:545-580)
-                    D += weight * gdist;
-                    const float resD = fmaxf((Dint - D) * inv_next, 0.f);
-                    const float a_hit = (gdist - resD) * T * Dgrad;
-                    const float hs = gsq > 0.f ? (weight / gdist) * Dgrad : 0.f;
-                    const float hgx = hx * hs, hgy = hy * hs, hgz = hz * hs;                               // grdsRayHitGrd
-                    const float sd = hgx * sc.x * gdx + hgy * sc.y * gdy + hgz * sc.z * gdz;               // grdScaledDot
-                    // opacity branch (:586-587)
-                    const float resT = alpha < 0.999999f ? Tint / (1.f - alpha) : T;
-                    const float a_dns = resT * -Tgrad;
-                    // radiance branch (:602-612)
-                    g[12] = Cgx * weight; g[13] = Cgy * weight; g[14] = Cgz * weight;
-                    Cx += weight * cl.x; Cy += weight * cl.y; Cz += weight * cl.z;
-                    const float rcx = fmaxf((Cix - Cx) * inv_next, 0.f);
-                    const float rcy = fmaxf((Ciy - Cy) * inv_next, 0.f);
-                    const float rcz = fmaxf((Ciz - Cz) * inv_next, 0.f);
-                    const float common = a_hit + a_dns + T * (cl.x - rcx) * Cgx + T * (cl.y - rcy) * Cgy + T * (cl.z - rcz) * Cgz;
-                    g[3] = gres * common;                                                                 // d density (:624-627)
-                    const float gray_g = kernel_response_grad<DEG>(gray, gres, dns * common);             // (:639-648)
-                    // gray = |grd x gro|^2  (:684-702)
-                    const float kx = 2.f * ccx * gray_g, ky = 2.f * ccy * gray_g, kz = 2.f * ccz * gray_g;  // gcrodGrd
-                    const float gd_gx = kz * goy - ky * goz + (sc.x * hgx * pd - gox * sd);                 // grdGrd + grdRayHitGrd
-                    const float gd_gy = kx * goz - kz * gox + (sc.y * hgy * pd - goy * sd);
-                    const float gd_gz = ky * gox - kx * goy + (sc.z * hgz * pd - goz * sd);
-                    const float go_gx = ky * gdz - kz * gdy - gdx * sd;                                     // groGrd + groRayHitGrd
-                    const float go_gy = kz * gdx - kx * gdz - gdy * sd;
-                    const float go_gz = kx * gdy - ky * gdx - gdz * sd;
-                    // gro = (1/s) gposcr  (:705-713)
-                    const float prg_x = is.x * go_gx, prg_y = is.y * go_gy, prg_z = is.z * go_gz;          // gposcrGrd
-                    float sgx = ddx * hgx - gox * prg_x;               // gsclRayHitGrd + gsclGrdGro (gposcr/s^2 = gro/s)
-                    float sgy = ddy * hgy - goy * prg_y;
-                    float sgz = ddz * hgz - goz * prg_z;
-                    // gposcr = R^T gposc  (:715-726)
-                    g[0] = -(prg_x * r0.x + prg_y * r1.x + prg_z * r2.x);
-                    g[1] = -(prg_x * r0.y + prg_y * r1.y + prg_z * r2.y);
-                    g[2] = -(prg_x * r0.z + prg_y * r1.z + prg_z * r2.z);
-                    // grd = normalize(grdu)  (:729-731, safe_normalize_bw mathUtils.cuh:410-420)
-                    const float il3 = il * il * il;
-                    const float du = gd_gx * ux + gd_gy * uy + gd_gz * uz;
-                    const float ug_x = l > 0.f ? il * gd_gx - il3 * ux * du : 0.f;                          // grduGrd
-                    const float ug_y = l > 0.f ? il * gd_gy - il3 * uy * du : 0.f;
-                    const float ug_z = l > 0.f ? il * gd_gz - il3 * uz * du : 0.f;
-                    // grdu = (1/s) rayDirR  (:733-738)
-                    const float rdg_x = is.x * ug_x, rdg_y = is.y * ug_y, rdg_z = is.z * ug_z;             // rayDirRGrd
-                    sgx -= ux * rdg_x;                                  // rayDirR/s^2 = grdu/s
-                    sgy -= uy * rdg_y;
-                    sgz -= uz * rdg_z;
-                    g[8] = sgx; g[9] = sgy; g[10] = sgz;
-                    // rotation rows m_i receive dM_i = prg_i * gposc + rdg_i * d   (matmul_bw_quat twice, :719-747)
-                    const float m00 = prg_x * pcx + rdg_x * ray.dx, m01 = prg_x * pcy + rdg_x * ray.dy, m02 = prg_x * pcz + rdg_x * ray.dz;
-                    const float m10 = prg_y * pcx + rdg_y * ray.dx, m11 = prg_y * pcy + rdg_y * ray.dy, m12 = prg_y * pcz + rdg_y * ray.dz;
-                    const float m20 = prg_z * pcx + rdg_z * ray.dx, m21 = prg_z * pcy + rdg_z * ray.dy, m22 = prg_z * pcz + rdg_z * ray.dz;
-                    const float4 q = sm.qt[j];
-                    const float qr = q.x, qx = q.y, qy = q.z, qz = q.w;
-                    g[4] = 2.f * (qz * (m01 - m10) + qy * (m20 - m02) + qx * (m12 - m21));
-                    g[5] = 2.f * (qy * (m01 + m10) + qz * (m02 + m20) + qr * (m12 - m21)) - 4.f * qx * (m11 + m22);
-                    g[6] = 2.f * (qx * (m01 + m10) + qr * (m20 - m02) + qz * (m12 + m21)) - 4.f * qy * (m00 + m22);
-                    g[7] = 2.f * (qr * (m01 - m10) + qx * (m02 + m20) + qy * (m12 + m21)) - 4.f * qz * (m00 + m11);
-                    T = nextT;
-                    if (T < cfg.min_transmittance) alive = false;
-                }
-            }
-            if (__any_sync(kFull, hit)) {
-                const float total = warp_transpose_reduce16(g, lane);
-                if ((lane & 1) == 0) {
-                    const uint32_t idx = __float_as_uint(sm.cl[j].w);
-                    atomicAdd(grad_acc + static_cast<size_t>(idx) * kGradRow + (lane >> 1), total);
-                }
-                if (__all_sync(kFull, !alive)) break;
-            }
             }
         }
     }
+}
+
+// world-space origin of the frame's first ray; a tile is FAST when every one of its rays starts there (always the case for camera rays)
+__device__ __forceinline__ bool frame_common_origin(const FrameCamera& cam, const float* __restrict__ rays_o, bool inside, int64_t pix,
+                                                    float& ox, float& oy, float& oz) {
+    const float ax = rays_o[0], ay = rays_o[1], az = rays_o[2];
+    bool same = true;
+    if (inside) same = (rays_o[pix * 3 + 0] == ax) && (rays_o[pix * 3 + 1] == ay) && (rays_o[pix * 3 + 2] == az);
+    const float* m = cam.s2w;
+    ox = m[0] * ax + m[3] * ay + m[6] * az + m[9];
+    oy = m[1] * ax + m[4] * ay + m[7] * az + m[10];
+    oz = m[2] * ax + m[5] * ay + m[8] * az + m[11];
+    return __syncthreads_and(same);
 }
 
 template <int DEG>
@@ -540,6 +684,8 @@ __global__ void __launch_bounds__(kTilePixels, 3) render_backward_kernel(FrameCa
                                                                       const uint32_t* __restrict__ sorted_values,
                                                                       const uint32_t* __restrict__ ranges,
                                                                       const uint32_t* __restrict__ tile_order,
+                                                                      const uint32_t* __restrict__ chunk_base,
+                                                                      const uint32_t* __restrict__ hit_words,
                                                                       const float* __restrict__ out_rgba, const float* __restrict__ d_rgba,
                                                                       const float* __restrict__ out_dist, const float* __restrict__ d_dist,
                                                                       float* __restrict__ grad_acc) {
@@ -555,38 +701,32 @@ __global__ void __launch_bounds__(kTilePixels, 3) render_backward_kernel(FrameCa
     Ray ray;
     ray.alive = false;
     if (inside) ray = make_ray(cam, rays_o, rays_d, pix);
-    bool alive = inside && ray.alive;
+    const bool alive = inside && ray.alive;
 
-    // initializeBackwardRay (kernels/cuda/common/rayPayloadBackward.cuh:31-73)
-    float Cix = 0.f, Ciy = 0.f, Ciz = 0.f, Cgx = 0.f, Cgy = 0.f, Cgz = 0.f, Tint = 1.f, Tgrad = 0.f, Dint = 0.f, Dgrad = 0.f;
+    BwdRay st;
+    st.Cix = st.Ciy = st.Ciz = st.Cgx = st.Cgy = st.Cgz = 0.f;
+    st.Tint = 1.f; st.Tgrad = 0.f; st.Dint = 0.f; st.Dgrad = 0.f;
+    st.T = 1.f; st.Cx = st.Cy = st.Cz = st.D = 0.f;
     if (alive) {
         const float4 o = reinterpret_cast<const float4*>(out_rgba)[pix];
         const float4 g = reinterpret_cast<const float4*>(d_rgba)[pix];
-        Cix = o.x; Ciy = o.y; Ciz = o.z;
-        Cgx = g.x; Cgy = g.y; Cgz = g.z;
-        Tint = 1.f - o.w;
-        Tgrad = -1.f * g.w;
-        Dint = out_dist[pix];
-        Dgrad = d_dist[pix];
+        st.Cix = o.x; st.Ciy = o.y; st.Ciz = o.z;
+        st.Cgx = g.x; st.Cgy = g.y; st.Cgz = g.z;
+        st.Tint = 1.f - o.w;
+        st.Tgrad = -1.f * g.w;
+        st.Dint = out_dist[pix];
+        st.Dgrad = d_dist[pix];
     }
 
-    float o0x, o0y, o0z;
-    const bool uniform = tile_common_origin(cam, rays_o, tile, inside, pix, o0x, o0y, o0z);
-    // the warp-uniform frame lives in shared memory: 15 fewer live registers in the adjoint loop
-    __shared__ WarpFrame wfs[kTilePixels / 32];
-    WarpFrame& wf = wfs[tid >> 5];
-    {
-        const WarpFrame tmp = make_warp_frame(cam, ray, alive, uniform && (cfg.subtile_culling & 1), lane);
-        if (lane == 0) wf = tmp;
-        __syncwarp();
-    }
+    float ofx, ofy, ofz;
+    const bool fast = frame_common_origin(cam, rays_o, inside, pix, ofx, ofy, ofz);
     const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
-    if (uniform)
-        backward_tile<DEG, true>(cfg, sm, wf, ray, o0x, o0y, o0z, tid, lane, begin, end, particles, rgb, sorted_values, alive, Cix, Ciy, Ciz,
-                                 Cgx, Cgy, Cgz, Tint, Tgrad, Dint, Dgrad, grad_acc);
+    const uint32_t* words = hit_words + static_cast<size_t>(chunk_base[tile]) * (kTilePixels / 32);
+    const bool use_words = (cfg.subtile_culling & 4) != 0;
+    if (fast)
+        backward_tile<DEG, true>(cfg, sm, ray, ofx, ofy, ofz, tid, lane, begin, end, particles, rgb, sorted_values, words, use_words, alive, st, grad_acc);
     else
-        backward_tile<DEG, false>(cfg, sm, wf, ray, o0x, o0y, o0z, tid, lane, begin, end, particles, rgb, sorted_values, alive, Cix, Ciy, Ciz,
-                                  Cgx, Cgy, Cgz, Tint, Tgrad, Dint, Dgrad, grad_acc);
+        backward_tile<DEG, false>(cfg, sm, ray, ofx, ofy, ofz, tid, lane, begin, end, particles, rgb, sorted_values, words, use_words, alive, st, grad_acc);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -608,11 +748,15 @@ constexpr int kPbThreads = 128;
 // COMPACT (view-parallel training): instead of the [N,48] SH gradient row the kernel emits the masked radiance gradient (3 floats) the
 // row is the outer product of -- d_sph[j][c] = basis_j(direction) * g[c] -- so ranks exchange 16 instead of 192 bytes per particle and
 // rebuild the summed rows with sph_from_views_kernel.
-template <bool COMPACT>
+// CANON: the accumulator rows hold G7's canonical sums (see the G7 section comment): slots 0..2 = sum groGrd, 8..10 = per-pair part of
+// d scale, 4..7 = quaternion contraction of the direction-dependent outer products; the three per-particle linear maps are applied here.
+// (The sorted k-buffer kernels still accumulate final gradients: CANON = false.)
+template <bool COMPACT, bool CANON>
 __global__ void __launch_bounds__(kPbThreads) project_backward_kernel(FrameCamera cam, int64_t n, const float* __restrict__ particles,
                                                                       const float* __restrict__ sph, int deg, const float* __restrict__ rgb,
-                                                                      const uint32_t* __restrict__ tiles_count, float* __restrict__ grad_acc,
-                                                                      float* __restrict__ d_particles, float* __restrict__ d_sph) {
+                                                                      const uint32_t* __restrict__ tiles_count, const float* __restrict__ rays_o,
+                                                                      float* __restrict__ grad_acc, float* __restrict__ d_particles,
+                                                                      float* __restrict__ d_sph) {
     __shared__ __align__(128) float4 s_acc[kPbThreads * 4];   // in: accumulator rows, out: zeros
     __shared__ __align__(128) float4 s_sh[kPbThreads * 12];   // in: SH coefficients, out: d_sph rows
     __shared__ __align__(128) float4 s_dp[kPbThreads * 3];    // out: d_particles rows
@@ -633,18 +777,56 @@ __global__ void __launch_bounds__(kPbThreads) project_backward_kernel(FrameCamer
     if (tid == 0) tma_bulk_g2s(s_acc, grad_acc + base * kGradRow, static_cast<uint32_t>(cnt) * 64u, &s_bar);
     if (want_sh) tma_bulk_g2s(s_sh + tid * 12, sph + i * 48, 192u, &s_bar);
     // overlap the remaining scalar loads with the bulk copies
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), pq = p, ps = p;
     float c0 = 0.f, c1 = 0.f, c2 = 0.f;
     if (vis) {
         p = __ldg(reinterpret_cast<const float4*>(particles + i * 12));
+        if (CANON) {
+            pq = __ldg(reinterpret_cast<const float4*>(particles + i * 12) + 1);
+            ps = __ldg(reinterpret_cast<const float4*>(particles + i * 12) + 2);
+        }
         c0 = rgb[i * 3 + 0]; c1 = rgb[i * 3 + 1]; c2 = rgb[i * 3 + 2];
+    }
+    float ofx = 0.f, ofy = 0.f, ofz = 0.f;
+    if (CANON) {  // world-space origin of the frame's first ray, as G7 computes it (frame_common_origin)
+        const float ax = rays_o[0], ay = rays_o[1], az = rays_o[2];
+        const float* m = cam.s2w;
+        ofx = m[0] * ax + m[3] * ay + m[6] * az + m[9];
+        ofy = m[1] * ax + m[4] * ay + m[7] * az + m[10];
+        ofz = m[2] * ax + m[5] * ay + m[8] * az + m[11];
     }
     mbar_wait(&s_bar, 0);
 
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     if (in_range) {
-        const float4 a0 = s_acc[tid * 4 + 0], a1 = s_acc[tid * 4 + 1], a2 = s_acc[tid * 4 + 2], a3 = s_acc[tid * 4 + 3];
+        float4 a0 = s_acc[tid * 4 + 0], a1 = s_acc[tid * 4 + 1], a2 = s_acc[tid * 4 + 2];
+        const float4 a3 = s_acc[tid * 4 + 3];
         s_acc[tid * 4 + 0] = zero; s_acc[tid * 4 + 1] = zero; s_acc[tid * 4 + 2] = zero; s_acc[tid * 4 + 3] = zero;
+        if (CANON && vis) {
+            const float r = pq.x, x = pq.y, y = pq.z, z = pq.w;
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+            const float rx = r * x, ry = r * y, rz = r * z;
+            const float r0x = 1.f - 2.f * (yy + zz), r0y = 2.f * (xy + rz), r0z = 2.f * (xz - ry);
+            const float r1x = 2.f * (xy - rz), r1y = 1.f - 2.f * (xx + zz), r1z = 2.f * (yz + rx);
+            const float r2x = 2.f * (xz + ry), r2y = 2.f * (yz - rx), r2z = 1.f - 2.f * (xx + yy);
+            const float isx = 1.0f / ps.x, isy = 1.0f / ps.y, isz = 1.0f / ps.z;
+            const float pcx = ofx - p.x, pcy = ofy - p.y, pcz = ofz - p.z;                      // gposc of the frame origin
+            const float gox = isx * (r0x * pcx + r0y * pcy + r0z * pcz);                        // gro of the frame origin
+            const float goy = isy * (r1x * pcx + r1y * pcy + r1z * pcz);
+            const float goz = isz * (r2x * pcx + r2y * pcy + r2z * pcz);
+            const float prx = isx * a0.x, pry = isy * a0.y, prz = isz * a0.z;                   // gposcrGrd = S^-1 sum groGrd
+            a0.x = -(prx * r0x + pry * r1x + prz * r2x);                                        // gposcr = R gposc  (gaussianParticles.cuh:715-726)
+            a0.y = -(prx * r0y + pry * r1y + prz * r2y);
+            a0.z = -(prx * r0z + pry * r1z + prz * r2z);
+            a2.x -= gox * prx; a2.y -= goy * pry; a2.z -= goz * prz;                            // gposcr/s^2 = gro/s  (:705-713)
+            const float m00 = prx * pcx, m01 = prx * pcy, m02 = prx * pcz;                      // matmul_bw_quat (:719-726)
+            const float m10 = pry * pcx, m11 = pry * pcy, m12 = pry * pcz;
+            const float m20 = prz * pcx, m21 = prz * pcy, m22 = prz * pcz;
+            a1.x += 2.f * (z * (m01 - m10) + y * (m20 - m02) + x * (m12 - m21));
+            a1.y += 2.f * (y * (m01 + m10) + z * (m02 + m20) + r * (m12 - m21)) - 4.f * x * (m11 + m22);
+            a1.z += 2.f * (x * (m01 + m10) + r * (m20 - m02) + z * (m12 + m21)) - 4.f * y * (m00 + m22);
+            a1.w += 2.f * (r * (m01 - m10) + x * (m02 + m20) + y * (m12 + m21)) - 4.f * z * (m00 + m11);
+        }
         float dpx = a0.x, dpy = a0.y, dpz = a0.z;
         float4* row = s_sh + tid * 12;
         if (!vis) {
@@ -767,40 +949,57 @@ __global__ void __launch_bounds__(128) sph_from_views_kernel(int64_t n, const fl
 
 }  // namespace
 
-void launch_tile_order(cudaStream_t s, const FrameCamera& cam, const uint32_t* ranges, uint32_t* tile_order) {
-    tile_order_kernel<<<1, 1024, 0, s>>>(cam.grid_x * cam.grid_y, ranges, tile_order);
+void launch_tile_order(cudaStream_t s, const FrameCamera& cam, const uint32_t* ranges, uint32_t* tile_order, uint32_t* chunk_base) {
+    tile_order_kernel<<<1, 1024, 0, s>>>(cam.grid_x * cam.grid_y, ranges, tile_order, chunk_base);
 }
 
 void launch_render_forward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
                            const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
-                           const uint32_t* ranges, const uint32_t* tile_order, float* out_rgba, float* out_dist, float* out_hits) {
+                           const uint32_t* ranges, const uint32_t* tile_order, const uint32_t* chunk_base, uint32_t* hit_words, float* out_rgba,
+                           float* out_dist, float* out_hits) {
     const unsigned grid = cam.grid_x * cam.grid_y;
     if (cfg.kernel_degree == 4)
-        render_forward_kernel<4><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, out_rgba, out_dist, out_hits);
+        render_forward_kernel<4, false><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, chunk_base, hit_words, out_rgba, out_dist, out_hits, nullptr);
     else
-        render_forward_kernel<2><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, out_rgba, out_dist, out_hits);
+        render_forward_kernel<2, false><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, chunk_base, hit_words, out_rgba, out_dist, out_hits, nullptr);
+}
+
+// debug: the forward's list walk with work counters (see WorkCounters); writes no image, rewrites the same hit words
+void launch_count_work(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o, const float* rays_d,
+                       const float* particles, const float* rgb, const uint32_t* sorted_values, const uint32_t* ranges,
+                       const uint32_t* tile_order, const uint32_t* chunk_base, uint32_t* hit_words, unsigned long long* counters8) {
+    const unsigned grid = cam.grid_x * cam.grid_y;
+    WorkCounters* ctr = reinterpret_cast<WorkCounters*>(counters8);
+    if (cfg.kernel_degree == 4)
+        render_forward_kernel<4, true><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, chunk_base, hit_words, nullptr, nullptr, nullptr, ctr);
+    else
+        render_forward_kernel<2, true><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, chunk_base, hit_words, nullptr, nullptr, nullptr, ctr);
 }
 
 void launch_render_backward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
                             const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
-                            const uint32_t* ranges, const uint32_t* tile_order, const float* out_rgba, const float* d_rgba,
-                            const float* out_dist, const float* d_dist, float* grad_acc) {
+                            const uint32_t* ranges, const uint32_t* tile_order, const uint32_t* chunk_base, const uint32_t* hit_words,
+                            const float* out_rgba, const float* d_rgba, const float* out_dist, const float* d_dist, float* grad_acc) {
     const unsigned grid = cam.grid_x * cam.grid_y;
     if (cfg.kernel_degree == 4)
-        render_backward_kernel<4><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, out_rgba, d_rgba, out_dist, d_dist, grad_acc);
+        render_backward_kernel<4><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, chunk_base, hit_words, out_rgba, d_rgba, out_dist, d_dist, grad_acc);
     else
-        render_backward_kernel<2><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, out_rgba, d_rgba, out_dist, d_dist, grad_acc);
+        render_backward_kernel<2><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, chunk_base, hit_words, out_rgba, d_rgba, out_dist, d_dist, grad_acc);
 }
 
 void launch_project_backward(cudaStream_t s, const FrameCamera& cam, int64_t n, const float* particles, const float* sph,
-                             int sph_degree, const float* rgb, const uint32_t* tiles_count, float* grad_acc, float* d_particles,
-                             float* d_sph, bool compact) {
+                             int sph_degree, const float* rgb, const uint32_t* tiles_count, const float* rays_o, float* grad_acc,
+                             float* d_particles, float* d_sph, bool compact, bool canon) {
     if (n <= 0) return;
     const unsigned blocks = static_cast<unsigned>((n + kPbThreads - 1) / kPbThreads);
-    if (compact)
-        project_backward_kernel<true><<<blocks, kPbThreads, 0, s>>>(cam, n, particles, sph, sph_degree, rgb, tiles_count, grad_acc, d_particles, d_sph);
+    if (compact && canon)
+        project_backward_kernel<true, true><<<blocks, kPbThreads, 0, s>>>(cam, n, particles, sph, sph_degree, rgb, tiles_count, rays_o, grad_acc, d_particles, d_sph);
+    else if (compact)
+        project_backward_kernel<true, false><<<blocks, kPbThreads, 0, s>>>(cam, n, particles, sph, sph_degree, rgb, tiles_count, rays_o, grad_acc, d_particles, d_sph);
+    else if (canon)
+        project_backward_kernel<false, true><<<blocks, kPbThreads, 0, s>>>(cam, n, particles, sph, sph_degree, rgb, tiles_count, rays_o, grad_acc, d_particles, d_sph);
     else
-        project_backward_kernel<false><<<blocks, kPbThreads, 0, s>>>(cam, n, particles, sph, sph_degree, rgb, tiles_count, grad_acc, d_particles, d_sph);
+        project_backward_kernel<false, false><<<blocks, kPbThreads, 0, s>>>(cam, n, particles, sph, sph_degree, rgb, tiles_count, rays_o, grad_acc, d_particles, d_sph);
 }
 
 void launch_sph_from_views(cudaStream_t s, int64_t n, const float* particles, int sph_degree, int views, const float* view_positions /*host [views,3]*/,

@@ -662,6 +662,13 @@ def main():
     stage_ms = ctx.collect_stage_times()
     ctx.set_timings(0)
     value = world * args.steps / (total_ms / 1000.0)
+    work, fma_peak = None, None
+    if rank == 0:
+        try:  # debug entry points, outside every timed region: work counters of the last frame + FP32 FMA peak of this GPU
+            work = ctx.work_counters(particles.data_ptr(), rays_o.data_ptr(), rays_d.data_ptr())
+            fma_peak = ctx.fma_peak_tflops()
+        except RuntimeError as e:
+            print(f"bench.py: work counters unavailable: {e}", file=sys.stderr)
 
     # ---- end to end through the public API: Tracer.render + loss.backward, camera batch from pinned host memory
     class _G:
@@ -741,14 +748,28 @@ def main():
         dom = max(stage_ms, key=lambda k: stage_ms[k])
         dom_ms = stage_ms[dom]
         traffic = None  # dram__bytes_read+write of that kernel from the committed ncu --set full capture of this workload
-        issue_pct = None  # smsp__issue_active of that kernel from the same capture (the render kernels are issue-bound, not HBM-bound)
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if tj.get("workload") == sc.name:
                 traffic = tj["dram_bytes_per_launch"].get({"render": "render_forward"}.get(dom, dom))
-                issue_pct = tj.get("issue_active_pct", {}).get({"render": "render_forward"}.get(dom, dom))
         achieved = stage_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        # SURVEY 8d "Algorithmic FLOPs for G6/G7": 65 per pair test + 30 per accepted hit (forward) / 400 per accepted hit (adjoint), with the
+        # pair tests of the REFERENCE's loop (every live pixel tests every list entry) counted on the device for this frame, over the live
+        # kernel times; the denominator is the FMA micro-benchmark run in this process
+        fp32 = None
+        if work is not None:
+            f_fwd = 65.0 * work["tests_ref"] + 30.0 * work["hits"]
+            f_bwd = 65.0 * work["tests_ref"] + 400.0 * work["hits"]
+            t_fwd, t_bwd = stage_ms["render"] * 1e-3, stage_ms["render_backward"] * 1e-3
+            fp32 = {"unit": "TFLOP/s", "peak": fma_peak, "peak_source": "FMA micro-benchmark in this run (gutb200_debug_fma_peak: 8 chains/thread, 2 flops/FMA)",
+                    "formula": "(65*tests_ref + 30*hits) / t_render ; (65*tests_ref + 400*hits) / t_render_backward (SURVEY 8d)",
+                    "render": {"achieved": f_fwd / t_fwd / 1e12, "frac": f_fwd / t_fwd / 1e12 / fma_peak if fma_peak else None},
+                    "render_backward": {"achieved": f_bwd / t_bwd / 1e12, "frac": f_bwd / t_bwd / 1e12 / fma_peak if fma_peak else None},
+                    "work": work,
+                    "executed": {"forward_lane_tests": work["tests_exec"], "backward_lane_tests": work["bwd_lanes"],
+                                 "forward_warp_iterations": work["fwd_iters"], "backward_warp_iterations": work["hit_iters"],
+                                 "hit_lanes_per_backward_iteration": work["hits"] / max(work["hit_iters"], 1)}}
         frame_bytes = 356 * N_ + 796 * V_ + (156 + 24 * 6) * I_ + 24 * T_ + 136 * P_
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -766,9 +787,9 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(stage_bytes[dom]),
                          "kernel_ms": dom_ms,
-                         "issue_active_pct_ncu": issue_pct,
-                         "note": "render/render_backward are FP32-issue bound (SURVEY 8d): the HBM fraction is reported as required, "
-                                 "issue_active_pct_ncu is the committed ncu smsp__issue_active of this kernel on this workload"},
+                         "note": "render/render_backward are FP32-issue bound (SURVEY 8d): the HBM fraction is reported as required; "
+                                 "roofline_fp32 (work counters and FMA peak both measured in this run) is the figure that bounds them"},
+            "roofline_fp32": fp32,
             "stage_ms": stage_ms,
             "frame_algorithmic_gbs": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9,
         }

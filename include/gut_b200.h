@@ -71,8 +71,9 @@ typedef struct gutb200_config {
     int32_t enable_timings;   /* render.enable_kernel_timings (src/splatRaster.cpp:168-169); 2 = also per-stage events */
     int32_t n_rolling_shutter_iterations; /* GAUSSIAN_N_ROLLING_SHUTTER_ITERATIONS (configs/render/3dgut.yaml:18): 5 */
     int32_t k_buffer_size;    /* GAUSSIAN_K_BUFFER_SIZE (render.splat.k_buffer_size): 0 = unsorted (default), 1..16 = sorted 3DGUT */
-    int32_t subtile_culling;  /* ours (no reference twin): exact-conservative sub-tile culling in render/renderBackward; 0 = off.
-                               * Results are bit-identical either way (forward) -- the switch exists for the A/B test. */
+    int32_t subtile_culling;  /* ours (no reference twin), bit mask, default 7: bit 1 = exact-conservative sub-tile screens in render,
+                               * bit 2 = renderBackward walks only the list entries some pixel of the warp's 8x4 block accepted in the
+                               * forward ("hit words"); bit 0 unused.  Forward results are bit-identical with bit 1 on or off. */
 } gutb200_config;
 
 typedef struct gutb200_ctx gutb200_ctx;
@@ -162,6 +163,15 @@ int gutb200_set_timings(gutb200_ctx* ctx, int level);
 /* Mean device time (ms) per stage since the last collect (needs enable_timings >= 2); order:
  * project, scan, expand, sort, tile_ranges, render, render_backward, project_backward. */
 int gutb200_collect_stage_times(gutb200_ctx* ctx, float* mean_ms /*[8]*/);
+
+/* Measurement helpers (debug, synchronise; never on the render path).
+ * work counters of the last forward (unsorted path): counters8 = { tests_ref: (pixel, entry) pairs the reference's per-pixel loop
+ * evaluates, tests_exec: lane-level exact tests our forward ran after sub-tile screening, hits: accepted pairs (the adjoint's work),
+ * fwd_iters / hit_iters: warp iterations of the forward / of the backward, screens: lane-level sub-tile screens, bwd_lanes: live lanes
+ * summed over the backward's iterations, 0 }.  particles / rays_* are the device pointers the forward was called with. */
+int gutb200_debug_work_counters(gutb200_ctx* ctx, const float* particles, const float* rays_o, const float* rays_d, uint64_t* counters8);
+/* FP32 FMA throughput of the device in TFLOP/s (micro-benchmark, best of `repeats` launches): the roofline_fp32 denominator. */
+int gutb200_debug_fma_peak(gutb200_ctx* ctx, int repeats, float* tflops);
 
 /* Number of kernels this library launched since the context was created (bench.py's gpu_launches). */
 int64_t gutb200_launch_count(const gutb200_ctx* ctx);
