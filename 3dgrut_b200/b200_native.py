@@ -204,11 +204,11 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.gutb200_launch_count(self._h))
 
-    COUNTERS = ("tests_ref", "tests_exec", "hits", "fwd_iters", "hit_iters", "screens", "bwd_lanes")
+    COUNTERS = ("tests_ref", "tests_exec", "hits", "fwd_iters", "hit_iters", "screens", "bwd_lanes", "iters16", "iters8", "sub16_hits", "sub8_hits")
 
     def work_counters(self, particles, rays_o, rays_d):
         """Work counters of the last forward (device pointers as passed to it): dict of ints (gutb200_debug_work_counters)."""
-        arr = (C.c_uint64 * 8)()
+        arr = (C.c_uint64 * 16)()
         self._check(self._lib.gutb200_debug_work_counters(self._h, particles, rays_o, rays_d, arr), "gutb200_debug_work_counters")
         return dict(zip(self.COUNTERS, [int(v) for v in arr]))
 

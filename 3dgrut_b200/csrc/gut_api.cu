@@ -704,21 +704,21 @@ int gutb200_debug_copy(gutb200_ctx* c, int what, void* dst, size_t bytes) {
 }
 
 // Work counters of the last forward (debug): re-walks its lists with the counting instantiation of the forward kernel.
-// counters8: tests_ref, tests_exec, hits, fwd_iters, hit_iters, screens, bwd_lanes, 0 (see WorkCounters in gut_render.cu)
-int gutb200_debug_work_counters(gutb200_ctx* c, const float* particles, const float* rays_o, const float* rays_d, uint64_t* counters8) {
+// counters16: tests_ref, tests_exec, hits, fwd_iters, hit_iters, screens, bwd_lanes, iters16, iters8, sub16_hits, sub8_hits, 0.. (WorkCounters, gut_render.cu)
+int gutb200_debug_work_counters(gutb200_ctx* c, const float* particles, const float* rays_o, const float* rays_d, uint64_t* counters16) {
     if (!c || !c->have_forward) return fail(c, "no forward context");
     if (c->fcfg.k_buffer_size != 0) return fail(c, "work counters exist for the unsorted path (k_buffer_size 0) only");
     GUT_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t s = c->fwd_stream;
     unsigned long long* dctr = nullptr;
-    GUT_CUDA(c, cudaMalloc(&dctr, 64));
-    cudaMemsetAsync(dctr, 0, 64, s);
-    for (int i = 0; i < 8; ++i) counters8[i] = 0;
+    GUT_CUDA(c, cudaMalloc(&dctr, 128));
+    cudaMemsetAsync(dctr, 0, 128, s);
+    for (int i = 0; i < 16; ++i) counters16[i] = 0;
     if (c->num_isect > 0)
         launch_count_work(s, c->cam, c->fcfg, rays_o, rays_d, particles, c->rgb.as<float>(), c->vals_out.as<uint32_t>(), c->ranges.as<uint32_t>(),
                           c->tile_order.as<uint32_t>(), c->chunk_base.as<uint32_t>(), c->hit_words.as<uint32_t>(), dctr);
     cudaError_t e = cudaStreamSynchronize(s);
-    if (e == cudaSuccess) e = cudaMemcpy(counters8, dctr, 64, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(counters16, dctr, 128, cudaMemcpyDeviceToHost);
     cudaFree(dctr);
     GUT_CUDA(c, e);
     return 0;

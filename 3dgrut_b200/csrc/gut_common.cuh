@@ -62,8 +62,9 @@ void launch_expand(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cf
 void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint32_t* sorted_keys, uint32_t* ranges);
 void launch_synth_keys(cudaStream_t s, int64_t num, const uint32_t* tiles, const uint32_t* vals, const float* depth, uint64_t* out);
 
-// hit words: one 32-bit word per (32-entry chunk of a tile list, warp of the tile's CTA); tile t's slice starts at chunk_base[t] * 8 words
-inline size_t hit_words_capacity(int64_t num_isect, int64_t tiles) { return (static_cast<size_t>(num_isect) / 32 + static_cast<size_t>(tiles) + 1) * 8; }
+// hit words: one 32-bit word per (32-entry chunk of a tile list, warp of the tile's CTA, quarter of the warp's 8x4 pixel block);
+// tile t's slice starts at chunk_base[t] * 32 words
+inline size_t hit_words_capacity(int64_t num_isect, int64_t tiles) { return (static_cast<size_t>(num_isect) / 32 + static_cast<size_t>(tiles) + 1) * 32; }
 void launch_tile_order(cudaStream_t s, const FrameCamera& cam, const uint32_t* ranges, uint32_t* tile_order, uint32_t* chunk_base);
 void launch_render_forward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
                            const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,

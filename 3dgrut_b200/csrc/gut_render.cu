@@ -203,9 +203,17 @@ __device__ __forceinline__ bool forward_pair(const FrameConfig& cfg, const FwdSm
 //   2 hits        accepted pairs (the set the backward's adjoint runs on)
 //   3 fwd_iters   warp iterations of the forward's exact test     4 hit_iters  warp iterations with >= 1 accepting lane (= backward's iterations)
 //   5 screens     lane-level sub-tile culling screens             6 bwd_lanes  live lanes summed over hit_iters (lane-level tests of the backward)
+//   7 iters16 / 8 iters8   backward iterations when half-warps (4x4 pixels) / quarter-warps (4x2) walk their own entries in lockstep
+//   9 sub16_hits / 10 sub8_hits   (half-warp, entry) / (quarter-warp, entry) pairs with >= 1 accepting lane (= gradient rows flushed)
 struct WorkCounters {
-    unsigned long long v[8];
+    unsigned long long v[16];
 };
+
+// Lane bits of a warp's 8x4 pixel block: b0..b2 = x, b3..b4 = y (tile_pixel).  Quarter q = b2 | b4 << 1 is a 4x2-pixel block; the
+// forward records one hit word per (32-entry chunk, warp, quarter); halves (4x4 pixels, split by b2) and the whole warp OR them.
+__device__ __forceinline__ int lane_quarter(int lane) { return ((lane >> 2) & 1) | ((lane >> 3) & 2); }
+__device__ __forceinline__ unsigned quarter_lanes(int q) { return (0x0F0Fu << ((q & 1) * 4)) << ((q >> 1) * 16); }
+constexpr int kWordsPerChunk = (kTilePixels / 32) * 4;  // 8 warps x 4 quarters
 
 template <int DEG, bool UNIFORM, bool COUNT>
 __device__ __forceinline__ void forward_tile(const FrameConfig& cfg, FwdSmem& sm, const WarpFrame& wf, const Ray& ray, float o0x, float o0y,
@@ -215,6 +223,7 @@ __device__ __forceinline__ void forward_tile(const FrameConfig& cfg, FwdSmem& sm
                                              float& dist, uint32_t& hits, WorkCounters* __restrict__ ctr) {
     const int lane = tid & 31;
     unsigned long long c_ref = 0, c_exec = 0, c_hits = 0, c_iters = 0, c_hit_iters = 0, c_screens = 0, c_bwd_lanes = 0;
+    unsigned long long c_iters16 = 0, c_iters8 = 0, c_sub16 = 0, c_sub8 = 0;
     for (uint32_t base = begin; base < end; base += kBatch) {
         if (__syncthreads_and(!alive)) break;
         const uint32_t k = base + tid;
@@ -245,7 +254,10 @@ __device__ __forceinline__ void forward_tile(const FrameConfig& cfg, FwdSmem& sm
         const int count = min(kBatch, static_cast<int>(end - base));
         // this warp's hit words of the batch: bit e of word c/32 = "some pixel of the warp's 8x4 block accepted entry c + e" -- the backward
         // walks only those entries (a necessary condition of its own exact test, so it drops nothing it would have accepted)
-        uint32_t* words = hit_words + (static_cast<size_t>(base - begin) >> 5) * (kTilePixels / 32) + (tid >> 5);
+        uint32_t* words = hit_words + (static_cast<size_t>(base - begin) >> 5) * kWordsPerChunk + (tid >> 5) * 4;
+        const int quarter = lane_quarter(lane);
+        const unsigned my_quarter = quarter_lanes(quarter);
+        const bool writer = (lane & 0x0B) == 0;  // lanes 0, 4, 16, 20: one per quarter
         if (UNIFORM) {
             // chunks of 32 entries: lane k screens entry k against the warp's pixel block, the warp walks the survivors
             for (int c = 0; c < count; c += 32) {
@@ -275,7 +287,7 @@ __device__ __forceinline__ void forward_tile(const FrameConfig& cfg, FwdSmem& sm
                     bool acc = false;
                     if (alive) acc = forward_pair<DEG, true>(cfg, sm, j, ray, alive, T, cr, cg, cb, dist, hits);
                     const unsigned accs = __ballot_sync(kFull, acc);
-                    if (accs) word |= 1u << b;
+                    if (accs & my_quarter) word |= 1u << b;  // this lane's quarter (4x2 pixels) accepted entry j
                     if (COUNT && accs) {
                         c_hit_iters++;
                         c_bwd_lanes += live_n;
@@ -285,13 +297,25 @@ __device__ __forceinline__ void forward_tile(const FrameConfig& cfg, FwdSmem& sm
                 if (COUNT) {
                     const unsigned live = __ballot_sync(kFull, alive);
                     c_ref += static_cast<unsigned long long>(__popc(live)) * (min(c + 32, count) - prev);
+                    // lockstep iteration counts of the sub-block walks: halves split by b2, quarters by (b2, b4)
+                    const uint32_t wq = word, wh = word | __shfl_xor_sync(kFull, word, 16);
+                    const int p16 = __popc(wh), p8 = __popc(wq);
+                    const int m16 = max(p16, __shfl_xor_sync(kFull, p16, 4));
+                    int m8 = max(p8, __shfl_xor_sync(kFull, p8, 4));
+                    m8 = max(m8, __shfl_xor_sync(kFull, m8, 16));
+                    c_iters16 += m16;
+                    c_iters8 += m8;
+                    c_sub16 += p16 + __shfl_xor_sync(kFull, p16, 4);
+                    int s8 = p8 + __shfl_xor_sync(kFull, p8, 4);
+                    s8 += __shfl_xor_sync(kFull, s8, 16);
+                    c_sub8 += s8;
                 }
-                if (lane == 0) words[(c >> 5) * (kTilePixels / 32)] = word;
+                if (writer) words[(c >> 5) * kWordsPerChunk + quarter] = word;
             }
         } else {
             // per-pixel origins: no warp-level screening; the backward gets all-ones words for these tiles
-            if (lane == 0)
-                for (int c = 0; c < count; c += 32) words[(c >> 5) * (kTilePixels / 32)] = 0xFFFFFFFFu;
+            if (writer)
+                for (int c = 0; c < count; c += 32) words[(c >> 5) * kWordsPerChunk + quarter] = 0xFFFFFFFFu;
             for (int j = 0; alive && j < count; ++j) {
                 const bool acc = forward_pair<DEG, false>(cfg, sm, j, ray, alive, T, cr, cg, cb, dist, hits);
                 if (COUNT) {
@@ -319,6 +343,10 @@ __device__ __forceinline__ void forward_tile(const FrameConfig& cfg, FwdSmem& sm
             atomicAdd(&ctr->v[4], c_hit_iters);
             atomicAdd(&ctr->v[5], c_screens);
             atomicAdd(&ctr->v[6], c_bwd_lanes);
+            atomicAdd(&ctr->v[7], c_iters16);
+            atomicAdd(&ctr->v[8], c_iters8);
+            atomicAdd(&ctr->v[9], c_sub16);
+            atomicAdd(&ctr->v[10], c_sub8);
         }
     }
 }
@@ -355,7 +383,7 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
     uint32_t hits = 0;
     bool alive = valid;
     const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
-    uint32_t* words = hit_words + static_cast<size_t>(chunk_base[tile]) * (kTilePixels / 32);
+    uint32_t* words = hit_words + static_cast<size_t>(chunk_base[tile]) * kWordsPerChunk;
     if (uniform)
         forward_tile<DEG, true, COUNT>(cfg, sm, wf, ray, o0x, o0y, o0z, tid, begin, end, particles, rgb, sorted_values, words, alive, T, cr, cg, cb, dist, hits, ctr);
     else
@@ -444,40 +472,49 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(int num_tiles, const u
 
 struct BwdSmem {
     float4 r0[kBatch], r1[kBatch], r2[kBatch], sc[kBatch], is[kBatch], qt[kBatch], cl[kBatch];
-    uint32_t hw[(kBatch / 32) * (kTilePixels / 32)];  // the forward's hit words of this batch, [chunk][warp]
+    uint32_t hw[(kBatch / 32) * kWordsPerChunk];  // the forward's hit words of this batch, [chunk][warp][quarter]
 };
 
-// sum 16 per-lane values over the warp; lane L returns the total of component (L >> 1). 16 SHFL in all.
-__device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lane) {
+// Transposing butterfly over the SUBL lanes of a sub-block (SUBL = 32: the warp, 16: half = 4x4 pixels, 8: quarter = 4x2 pixels; the
+// sub-block id uses lane bits b2 (and b4), the exchanges use the others).  Each level halves the number of values a lane carries:
+//   SUBL 32: 16 values -> 1 (both lanes of a pair hold it), component = lane >> 1                         16 SHFL
+//   SUBL 16: 16 values -> 1, component = 8 [lane & 16] + 4 [lane & 8] + 2 [lane & 2] + [lane & 1]          15 SHFL
+//   SUBL  8: 16 values -> 2 (v[0], v[1]), components 8 [lane & 8] + 4 [lane & 2] + 2 [lane & 1] + {0, 1}   14 SHFL
+template <int H>
+__device__ __forceinline__ void butterfly_level(float (&v)[16], bool up, int mask) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const bool up = lane & 16;
-        const float send = up ? v[i] : v[i + 8];
-        const float keep = up ? v[i + 8] : v[i];
-        v[i] = keep + __shfl_xor_sync(kFull, send, 16);
+    for (int i = 0; i < H; ++i) {
+        const float send = up ? v[i] : v[i + H];
+        const float keep = up ? v[i + H] : v[i];
+        v[i] = keep + __shfl_xor_sync(kFull, send, mask);
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool up = lane & 8;
-        const float send = up ? v[i] : v[i + 4];
-        const float keep = up ? v[i + 4] : v[i];
-        v[i] = keep + __shfl_xor_sync(kFull, send, 8);
+}
+
+template <int SUBL>
+__device__ __forceinline__ void sub_reduce16(float (&v)[16], int lane) {
+    if (SUBL == 32) {
+        butterfly_level<8>(v, lane & 16, 16);
+        butterfly_level<4>(v, lane & 8, 8);
+        butterfly_level<2>(v, lane & 4, 4);
+        butterfly_level<1>(v, lane & 2, 2);
+        v[0] += __shfl_xor_sync(kFull, v[0], 1);
+    } else if (SUBL == 16) {
+        butterfly_level<8>(v, lane & 16, 16);
+        butterfly_level<4>(v, lane & 8, 8);
+        butterfly_level<2>(v, lane & 2, 2);
+        butterfly_level<1>(v, lane & 1, 1);
+    } else {
+        butterfly_level<8>(v, lane & 8, 8);
+        butterfly_level<4>(v, lane & 2, 2);
+        butterfly_level<2>(v, lane & 1, 1);
     }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const bool up = lane & 4;
-        const float send = up ? v[i] : v[i + 2];
-        const float keep = up ? v[i + 2] : v[i];
-        v[i] = keep + __shfl_xor_sync(kFull, send, 4);
-    }
-    {
-        const bool up = lane & 2;
-        const float send = up ? v[0] : v[1];
-        const float keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(kFull, send, 2);
-    }
-    v[0] += __shfl_xor_sync(kFull, v[0], 1);
-    return v[0];
+}
+
+template <int SUBL>
+__device__ __forceinline__ int sub_component(int lane) {
+    if (SUBL == 32) return lane >> 1;
+    if (SUBL == 16) return ((lane & 16) >> 1) | ((lane & 8) >> 1) | (lane & 3);
+    return (lane & 8) | ((lane & 2) << 1) | ((lane & 1) << 1);
 }
 
 // per-pixel backward state (initializeBackwardRay, kernels/cuda/common/rayPayloadBackward.cuh:31-73)
@@ -593,7 +630,7 @@ __device__ __forceinline__ bool backward_pair(const FrameConfig& cfg, const BwdS
     return true;
 }
 
-template <int DEG, bool FAST>
+template <int DEG, bool FAST, int SUBL>
 __device__ __forceinline__ void backward_tile(const FrameConfig& cfg, BwdSmem& sm, const Ray& ray, float ofx, float ofy, float ofz, int tid,
                                               int lane, uint32_t begin, uint32_t end, const float* __restrict__ particles,
                                               const float* __restrict__ rgb, const uint32_t* __restrict__ sorted_values,
@@ -601,13 +638,17 @@ __device__ __forceinline__ void backward_tile(const FrameConfig& cfg, BwdSmem& s
                                               float* __restrict__ grad_acc) {
     const float dox = ray.ox - ofx, doy = ray.oy - ofy, doz = ray.oz - ofz;   // zero in FAST tiles
     const bool depth_grads = __any_sync(kFull, alive && (st.Dgrad != 0.f));
+    const int quarter = lane_quarter(lane);
+    // lanes of this lane's sub-block, and where its gradient components land after the reduction
+    const unsigned sub_lanes = SUBL == 32 ? kFull : SUBL == 16 ? (quarter_lanes(quarter & 1) | quarter_lanes((quarter & 1) | 2)) : quarter_lanes(quarter);
+    const int comp = sub_component<SUBL>(lane);
     for (uint32_t base = begin; base < end; base += kBatch) {
         if (__syncthreads_and(!alive)) break;
         const uint32_t k = base + tid;
-        if (tid < (kBatch / 32) * (kTilePixels / 32)) {
-            const uint32_t chunk = (base - begin) / 32 + (tid >> 3);
-            const bool in_list = base + (tid >> 3) * 32 < end;
-            sm.hw[tid] = (use_words && in_list) ? hit_words[static_cast<size_t>(chunk) * (kTilePixels / 32) + (tid & 7)] : 0xFFFFFFFFu;
+        {   // 8 chunks x 8 warps x 4 quarters = one word per thread
+            const uint32_t chunk = (base - begin) / 32 + (tid >> 5);
+            const bool in_list = base + (tid >> 5) * 32 < end;
+            sm.hw[tid] = (use_words && in_list) ? hit_words[static_cast<size_t>(chunk) * kWordsPerChunk + (tid & 31)] : 0xFFFFFFFFu;
         }
         if (k < end) {
             const uint32_t idx = sorted_values[k];
@@ -636,24 +677,38 @@ __device__ __forceinline__ void backward_tile(const FrameConfig& cfg, BwdSmem& s
         }
         __syncthreads();
         const int count = min(kBatch, static_cast<int>(end - base));
-        // chunks of 32 entries; the warp walks the entries some pixel of its block accepted in the forward (hit words)
+        // chunks of 32 entries.  Every sub-block of the warp walks ITS OWN entries -- those some pixel of the sub-block accepted in the
+        // forward (hit words) -- in lockstep with the other sub-blocks: one pass of the adjoint serves up to 32 / SUBL particles, and
+        // the reduction tree is log2(SUBL) levels deep.
         for (int c = 0; c < count; c += 32) {
             if (__all_sync(kFull, !alive)) break;
-            unsigned todo = sm.hw[(c >> 5) * (kTilePixels / 32) + (tid >> 5)];
+            const uint32_t* hw = sm.hw + (c >> 5) * kWordsPerChunk + (tid >> 5) * 4;
+            unsigned todo;
+            if (SUBL == 32) todo = hw[0] | hw[1] | hw[2] | hw[3];
+            else if (SUBL == 16) todo = hw[quarter & 1] | hw[(quarter & 1) | 2];
+            else todo = hw[quarter];
             if (count - c < 32) todo &= (1u << (count - c)) - 1u;
-            while (todo) {
-                const int j = c + __ffs(todo) - 1;
+            while (__any_sync(kFull, todo != 0u)) {
+                const bool act = todo != 0u;
+                const int j = act ? c + __ffs(todo) - 1 : c;
                 todo &= todo - 1;
                 float g[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) g[i] = 0.f;
                 bool hit = false;
-                if (alive) hit = backward_pair<DEG, FAST>(cfg, sm, j, ray, dox, doy, doz, depth_grads, st, alive, g);
-                if (__any_sync(kFull, hit)) {
-                    const float total = warp_transpose_reduce16(g, lane);
-                    if ((lane & 1) == 0) {
-                        const uint32_t idx = __float_as_uint(sm.cl[j].w);
-                        atomicAdd(grad_acc + static_cast<size_t>(idx) * kGradRow + (lane >> 1), total);
+                if (act && alive) hit = backward_pair<DEG, FAST>(cfg, sm, j, ray, dox, doy, doz, depth_grads, st, alive, g);
+                const unsigned hits = __ballot_sync(kFull, hit);
+                if (hits) {
+                    sub_reduce16<SUBL>(g, lane);
+                    if (hits & sub_lanes) {  // this sub-block's particle received something
+                        float* row = grad_acc + static_cast<size_t>(__float_as_uint(sm.cl[j].w)) * kGradRow + comp;
+                        if (SUBL == 32) {
+                            if ((lane & 1) == 0) atomicAdd(row, g[0]);
+                        } else if (SUBL == 16) {
+                            atomicAdd(row, g[0]);
+                        } else {
+                            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(row), "f"(g[0]), "f"(g[1]) : "memory");
+                        }
                     }
                     if (__all_sync(kFull, !alive)) break;
                 }
@@ -675,7 +730,7 @@ __device__ __forceinline__ bool frame_common_origin(const FrameCamera& cam, cons
     return __syncthreads_and(same);
 }
 
-template <int DEG>
+template <int DEG, int SUBL>
 __global__ void __launch_bounds__(kTilePixels, 3) render_backward_kernel(FrameCamera cam, FrameConfig cfg,
                                                                       const float* __restrict__ rays_o,
                                                                       const float* __restrict__ rays_d,
@@ -721,12 +776,12 @@ __global__ void __launch_bounds__(kTilePixels, 3) render_backward_kernel(FrameCa
     float ofx, ofy, ofz;
     const bool fast = frame_common_origin(cam, rays_o, inside, pix, ofx, ofy, ofz);
     const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
-    const uint32_t* words = hit_words + static_cast<size_t>(chunk_base[tile]) * (kTilePixels / 32);
+    const uint32_t* words = hit_words + static_cast<size_t>(chunk_base[tile]) * kWordsPerChunk;
     const bool use_words = (cfg.subtile_culling & 4) != 0;
     if (fast)
-        backward_tile<DEG, true>(cfg, sm, ray, ofx, ofy, ofz, tid, lane, begin, end, particles, rgb, sorted_values, words, use_words, alive, st, grad_acc);
+        backward_tile<DEG, true, SUBL>(cfg, sm, ray, ofx, ofy, ofz, tid, lane, begin, end, particles, rgb, sorted_values, words, use_words, alive, st, grad_acc);
     else
-        backward_tile<DEG, false>(cfg, sm, ray, ofx, ofy, ofz, tid, lane, begin, end, particles, rgb, sorted_values, words, use_words, alive, st, grad_acc);
+        backward_tile<DEG, false, SUBL>(cfg, sm, ray, ofx, ofy, ofz, tid, lane, begin, end, particles, rgb, sorted_values, words, use_words, alive, st, grad_acc);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -981,10 +1036,15 @@ void launch_render_backward(cudaStream_t s, const FrameCamera& cam, const FrameC
                             const uint32_t* ranges, const uint32_t* tile_order, const uint32_t* chunk_base, const uint32_t* hit_words,
                             const float* out_rgba, const float* d_rgba, const float* out_dist, const float* d_dist, float* grad_acc) {
     const unsigned grid = cam.grid_x * cam.grid_y;
-    if (cfg.kernel_degree == 4)
-        render_backward_kernel<4><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, chunk_base, hit_words, out_rgba, d_rgba, out_dist, d_dist, grad_acc);
-    else
-        render_backward_kernel<2><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, chunk_base, hit_words, out_rgba, d_rgba, out_dist, d_dist, grad_acc);
+    // sub-block width of the backward walk: bits 4..5 of the switch (0 = default quarter-warps, 1 = half-warps, 2 = whole warp)
+    const int sub = (cfg.subtile_culling >> 4) & 3;
+#define GUT_BWD(DEG_, SUB_) render_backward_kernel<DEG_, SUB_><<<grid, kTilePixels, 0, s>>>(cam, cfg, rays_o, rays_d, particles, rgb, sorted_values, ranges, tile_order, chunk_base, hit_words, out_rgba, d_rgba, out_dist, d_dist, grad_acc)
+    if (cfg.kernel_degree == 4) {
+        if (sub == 2) GUT_BWD(4, 32); else if (sub == 1) GUT_BWD(4, 16); else GUT_BWD(4, 8);
+    } else {
+        if (sub == 2) GUT_BWD(2, 32); else if (sub == 1) GUT_BWD(2, 16); else GUT_BWD(2, 8);
+    }
+#undef GUT_BWD
 }
 
 void launch_project_backward(cudaStream_t s, const FrameCamera& cam, int64_t n, const float* particles, const float* sph,

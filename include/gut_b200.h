@@ -72,8 +72,9 @@ typedef struct gutb200_config {
     int32_t n_rolling_shutter_iterations; /* GAUSSIAN_N_ROLLING_SHUTTER_ITERATIONS (configs/render/3dgut.yaml:18): 5 */
     int32_t k_buffer_size;    /* GAUSSIAN_K_BUFFER_SIZE (render.splat.k_buffer_size): 0 = unsorted (default), 1..16 = sorted 3DGUT */
     int32_t subtile_culling;  /* ours (no reference twin), bit mask, default 7: bit 1 = exact-conservative sub-tile screens in render,
-                               * bit 2 = renderBackward walks only the list entries some pixel of the warp's 8x4 block accepted in the
-                               * forward ("hit words"); bit 0 unused.  Forward results are bit-identical with bit 1 on or off. */
+                               * bit 2 = renderBackward walks only the list entries some pixel of a sub-block accepted in the forward
+                               * ("hit words"); bits 4..5 = sub-block of that walk: 0 quarter-warp (4x2 pixels), 1 half-warp (4x4),
+                               * 2 whole warp (8x4); bit 0 unused.  Forward results are bit-identical with bit 1 on or off. */
 } gutb200_config;
 
 typedef struct gutb200_ctx gutb200_ctx;
@@ -165,11 +166,13 @@ int gutb200_set_timings(gutb200_ctx* ctx, int level);
 int gutb200_collect_stage_times(gutb200_ctx* ctx, float* mean_ms /*[8]*/);
 
 /* Measurement helpers (debug, synchronise; never on the render path).
- * work counters of the last forward (unsorted path): counters8 = { tests_ref: (pixel, entry) pairs the reference's per-pixel loop
+ * work counters of the last forward (unsorted path): counters16 = { tests_ref: (pixel, entry) pairs the reference's per-pixel loop
  * evaluates, tests_exec: lane-level exact tests our forward ran after sub-tile screening, hits: accepted pairs (the adjoint's work),
  * fwd_iters / hit_iters: warp iterations of the forward / of the backward, screens: lane-level sub-tile screens, bwd_lanes: live lanes
- * summed over the backward's iterations, 0 }.  particles / rays_* are the device pointers the forward was called with. */
-int gutb200_debug_work_counters(gutb200_ctx* ctx, const float* particles, const float* rays_o, const float* rays_d, uint64_t* counters8);
+ * summed over those, iters16 / iters8: backward iterations when half- / quarter-warps walk their own entries in lockstep, sub16_hits /
+ * sub8_hits: (half- / quarter-warp, entry) pairs with a hit = gradient rows flushed, 0... }.  particles / rays_* are the device pointers
+ * the forward was called with. */
+int gutb200_debug_work_counters(gutb200_ctx* ctx, const float* particles, const float* rays_o, const float* rays_d, uint64_t* counters16);
 /* FP32 FMA throughput of the device in TFLOP/s (micro-benchmark, best of `repeats` launches): the roofline_fp32 denominator. */
 int gutb200_debug_fma_peak(gutb200_ctx* ctx, int repeats, float* tflops);
 

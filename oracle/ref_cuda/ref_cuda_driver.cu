@@ -232,6 +232,23 @@ int refcuda_stage_times(void* h, float* ms9) {
     return 0;
 }
 
+// host-side camera maths of the reference for one pose (debug): view matrix columns [12], sensor position [3], and the RenderParameters
+// fields as the kernels receive them [resolution 2, focal 2, principal 2, model type, shutter type]
+void refcuda_debug_camera(int width, int height, const float* focal, const float* pp, const float* pose0, const float* pose1, float* out20) {
+    const threedgut::RenderParameters rp = make_params(0, width, height, focal, pp, pose0, pose1);
+    const threedgut::TSensorPose pose = threedgut::interpolatedSensorPose(rp.sensorState.startPose, rp.sensorState.endPose, 0.5f);
+    const tcnn::mat4x3 view = threedgut::sensorPoseToMat(pose);
+    const threedgut::TSensorPose inv = threedgut::sensorPoseInverse(pose);
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 3; ++r) out20[c * 3 + r] = view[c][r];
+    for (int i = 0; i < 3; ++i) out20[12 + i] = inv[i];
+    out20[15] = static_cast<float>(rp.resolution.x);
+    out20[16] = static_cast<float>(rp.resolution.y);
+    out20[17] = rp.sensorModel.ocvPinholeParams.focalLength.x;
+    out20[18] = rp.sensorModel.ocvPinholeParams.principalPoint.y;
+    out20[19] = static_cast<float>(static_cast<int>(rp.sensorModel.modelType) * 10 + static_cast<int>(rp.sensorModel.shutterType));
+}
+
 // debug copies of the forward context for the parity tests: 0 tiles count [N] u32, 1 sorted keys [I] u64, 2 sorted values [I] u32,
 // 3 tile ranges [T,2] u32, 4 depth [N] f32, 5 precomputed features [N,3] f32.  Returns the byte size (dst may be null to query).
 int64_t refcuda_debug_copy(void* h, int what, void* dst, int64_t n, int64_t tiles) {

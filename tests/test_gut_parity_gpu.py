@@ -214,7 +214,7 @@ def test_subtile_culling_is_bit_identical(scene_name, degree):
     for cam_index in (1, 6):
         pose = tracer_pose(sc.camera(cam_index, 10))
         out = []
-        for mode in (7, 5, 0):  # default (screens + hit words) / hit words without the forward screens / neither
+        for mode in (7, 5, 0):  # default (screens + hit words, quarter-warp walk) / hit words without the forward screens / neither
             cfg = nat.default_config()
             cfg.kernel_degree = degree
             cfg.subtile_culling = mode
@@ -227,8 +227,9 @@ def test_subtile_culling_is_bit_identical(scene_name, degree):
             assert np.array_equal(hits1, hits_), f"hit counts differ on {(hits1 != hits_).sum()} pixels"
             assert np.array_equal(rgba1.view(np.uint32), rgba_.view(np.uint32))
             assert np.array_equal(dist1.view(np.uint32), dist_.view(np.uint32))
-        # the screens drop only pairs nobody accepts: same hit words, same gradients up to the order of the atomics
-        assert rel_l2(dp1, dp5) <= 1e-5 and rel_l2(ds1, ds5) <= 1e-5
+        # the screens drop only pairs nobody accepts: same hit words, same gradients up to the order of the atomics (canonical sums are
+        # mapped to pos / scale / quat after the reduction, so the order noise of the sums passes through three small linear maps)
+        assert rel_l2(dp1, dp5) <= 1e-4 and rel_l2(ds1, ds5) <= 1e-5
         # hit words on / off: the backward re-tests every pair either way; the words only skip entries no pixel of the warp accepted in
         # the forward, whose arithmetic differs from the backward's in the last bits (scale folded into the rotation rows) -- a borderline pair
         # accepted by one and not the other is the only possible difference
@@ -443,7 +444,7 @@ def test_compact_exchange_rebuilds_the_sh_gradient():
         full_ds.append(ds.clone())
         rgba, dst, hits, vis = raster.trace(0, 3, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose)
         dp2, g = raster.trace_bwd_compact(0, 3, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose, rgba, d_rgba, dst, d_dist)
-        assert rel_l2(dp2.cpu().numpy(), dp.cpu().numpy()) <= 1e-6  # atomics order only
+        assert rel_l2(dp2.cpu().numpy(), dp.cpu().numpy()) <= 2e-5  # atomics order only (through the per-particle maps of G8)
         gs.append(g.clone())
         pos.append(raster.sensor_position(sensor, pose, pose, W, H))
     assert np.allclose(pos[0], np.asarray(sc.camera(2, 10))[:3, 3], atol=1e-5)
