@@ -367,7 +367,7 @@ class HostFeed:
         self.torch.cuda.synchronize(self.dev)
 
 
-def run_grt(args, rank, local_rank, world, dev, dist):
+def run_grt(args, rank, local_rank, world, dev, dist, sub=False):
     """C4: the C2 scene through the 3DGRT path.  A step = build_bvh (the reference's default config rebuilds every
     step, configs/render/3dgrt.yaml:6 + base_gs.yaml:88) + trace + trace_bwd."""
     import torch
@@ -425,30 +425,35 @@ def run_grt(args, rank, local_rank, world, dev, dist):
         torch.cuda.synchronize(dev)
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not sub:
         sampler.start()
-    for s in range(args.warmup):
+    n_steps, n_warm = (min(args.steps, 10), min(args.warmup, 3)) if sub else (args.steps, args.warmup)
+    for s in range(n_warm):
         step_device(s)
     barrier()
     ctx = ot.native_context(dev)
     launches0 = ctx.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for s in range(args.steps):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+    for s in range(n_steps):
         flush.fill_(float(s))
         ev[s][0].record()
-        step_device(args.warmup + s)
+        step_device(n_warm + s)
         ev[s][1].record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and not sub) else None
     total_ms = torch.tensor([float(sum(a.elapsed_time(b) for a, b in ev))], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     launches = ctx.launch_count() - launches0
-    for s in range(min(args.steps, 10)):
+    for s in range(min(n_steps, 10)):
         flush.fill_(float(s))
-        step_device(args.warmup + s, timed=True)
-    value = world * args.steps / (total_ms / 1000.0)
+        step_device(n_warm + s, timed=True)
+    value = world * n_steps / (total_ms / 1000.0)
+    if sub:  # sub-record of the default c2 line: device-timed only
+        return {"workload": sc.name + " via 3dgrt", "value": value, "unit": UNIT, "n_gpus": world, "steps": n_steps, "ms_per_step": total_ms / n_steps,
+                "stage_ms": {k: float(np.mean(v)) for k, v in stage.items()}, "gaussians": n, "rays": H * W,
+                "note": "BASELINE configs[3]: the C2 scene through the 3DGRT path (software LBVH); step = build_bvh + trace + trace_bwd"}
 
     # e2e through Tracer.build_acc + Tracer.render + loss.backward with the camera batch from pinned host memory
     class _G:
@@ -532,6 +537,141 @@ def run_grt(args, rank, local_rank, world, dev, dist):
         dist.destroy_process_group()
 
 
+def gut_device_loop(torch, dist, args, rank, world, dev, workload, steps, warmup, stage_pass=True):
+    """Device-timed 3DGUT loop on one workload: `warmup` untimed + `steps` timed view-steps per rank (one view forward + backward each), L2
+    flushed between steps, per-step CUDA events, MAX over ranks.  With world > 1 every rank renders a different camera and the gradients are
+    summed every `--accumulate` view-steps (a step's batch = accumulate x world views): `compact` all-gathers each
+    view's [N,4] radiance gradient asynchronously (it overlaps the next view's render), all-reduces the accumulated [N,12] once and rebuilds
+    the [N,48] SH gradient; `allreduce` all-reduces [N,60] once per batch."""
+    import scenes
+    import threedgut_tracer
+    from threedgut_tracer.tracer import fromOpenCVPinholeCameraModelParameters, ShutterType
+
+    sc = make_scene(workload)
+    n, H, W = sc.n, sc.height, sc.width
+    tracer = threedgut_tracer.Tracer({"render": {"enable_kernel_timings": False}})
+    raster = tracer.tracer_wrapper
+    particles = torch.from_numpy(sc.particles).to(dev)
+    sph = torch.from_numpy(sc.sph).to(dev)
+    ro_np, rd_np = sc.rays()
+    rays_o, rays_d = torch.from_numpy(ro_np).to(dev), torch.from_numpy(rd_np).to(dev)
+    sensor = fromOpenCVPinholeCameraModelParameters(np.array([W, H]), ShutterType.GLOBAL, np.array([sc.cx, sc.cy], np.float32),
+                                                    np.array([sc.fx, sc.fy], np.float32), np.zeros(6, np.float32), np.zeros(2, np.float32),
+                                                    np.zeros(4, np.float32))
+    n_views = 100
+    poses = [scenes.pose7_from_c2w(sc.camera(i, n_views)) for i in range(n_views)]
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    d_rgba = torch.randn((H, W, 4), device=dev, generator=gen)
+    d_dist = 0.05 * torch.randn((H, W, 1), device=dev, generator=gen)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+    V = max(1, args.accumulate) if world > 1 else 1
+
+    def view_of(step, r=None):  # disjoint cameras per rank
+        return (step * world + (rank if r is None else r)) % n_views
+
+    grad_flat = torch.empty(n * 60, dtype=torch.float32, device=dev)  # [N,12] and [N,48] views of one bucket: one all-reduce
+    grad_views = (grad_flat[: n * 12].view(n, 12), grad_flat[n * 12:].view(n, 48))
+    grad_tmp = (torch.empty((n, 12), device=dev), torch.empty((n, 48), device=dev)) if (world > 1 and V > 1 and args.exchange == "allreduce") else None
+    compact = None
+    if world > 1 and args.exchange == "compact":
+        import view_parallel
+
+        compact = view_parallel.CompactGradientExchange(raster, n, dev, views_per_rank=V)
+        pos_table = np.stack([raster.sensor_position(sensor, p, p, W, H) for p in poses]).astype(np.float32)  # every rank knows every pose
+    xev = []  # (start, end) events around the exposed part of the exchange, filled only in the stage pass
+
+    def step_device(step, time_exchange=False):
+        pose = poses[view_of(step)]
+        slot = step % V
+        rgba, dst, hits, vis = raster.trace(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose)
+        if compact is not None:
+            # 64 B instead of 240 B per Gaussian on the wire: all-reduce d_particles, all-gather the radiance gradients, rebuild d_sph
+            raster.trace_bwd_compact(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose, rgba, d_rgba, dst,
+                                     d_dist, out=compact.out(slot))
+            compact.submit(slot)
+            if slot == V - 1:
+                first = step - (V - 1)
+                idx = [view_of(first + j, r) for j in range(V) for r in range(world)]  # slot-major, rank-minor
+                if time_exchange:
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                out = compact.finish(sc.sph_degree, particles, pos_table[idx])
+                if time_exchange:
+                    b.record()
+                    xev.append((a, b))
+                return out
+            return None
+        if world > 1 and slot > 0:
+            raster.trace_bwd(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose, rgba, d_rgba, dst, d_dist, out=grad_tmp)
+            grad_views[0].add_(grad_tmp[0])
+            grad_views[1].add_(grad_tmp[1])
+        else:
+            raster.trace_bwd(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose, rgba, d_rgba, dst, d_dist,
+                             out=grad_views)
+        if world > 1 and slot == V - 1:
+            if time_exchange:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            dist.all_reduce(grad_flat)
+            if time_exchange:
+                b.record()
+                xev.append((a, b))
+        return grad_views
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    ctx = raster.native_context(dev)
+    steps = max(V, (steps // V) * V)      # whole batches only
+    warmup = ((warmup + V - 1) // V) * V
+    for s_ in range(warmup):
+        step_device(s_)
+    barrier()
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for s_ in range(steps):
+        flush.fill_(float(s_))  # L2 flush between timed iterations, outside the per-step event pair
+        ev[s_][0].record()
+        step_device(warmup + s_)
+        ev[s_][1].record()
+    barrier()
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev], dtype=np.float64)
+    total_ms = torch.tensor([float(step_ms.sum())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    launches = ctx.launch_count() - launches0
+    stats = ctx.stats()
+    stage_ms, exchange = None, None
+    if stage_pass:
+        # separate short pass with per-stage CUDA events (they add host syncs, so never inside the timed region)
+        ctx.set_timings(2)
+        ctx.collect_stage_times()
+        k = max(V, (min(steps, 20) // V) * V)
+        for s_ in range(k):
+            flush.fill_(float(s_))
+            step_device(warmup + s_, time_exchange=True)
+        barrier()
+        stage_ms = ctx.collect_stage_times()
+        ctx.set_timings(0)
+        if world > 1 and xev:
+            xms = float(np.mean([a.elapsed_time(b) for a, b in xev]))
+            wire = compact.bytes_on_wire() if compact is not None else int(2 * (world - 1) / world * 240 * n)
+            exchange = {"kind": args.exchange, "views_per_rank_per_batch": V, "exposed_ms_per_batch": xms, "exposed_ms_per_view": xms / V,
+                        "bytes_on_wire_per_rank_per_batch": wire, "bus_gbs_over_exposed_time": wire / (xms * 1e-3) / 1e9 if xms > 0 else None,
+                        "note": "exposed = the step's all-reduce + waiting for the (already running) all-gathers + the SH rebuild kernel, "
+                                "CUDA events on the compute stream; the all-gathers of earlier views of the batch overlap the next view's render"}
+    value = world * steps / (total_ms / 1000.0)
+    return {"value": value, "total_ms": total_ms, "steps": steps, "warmup": warmup, "launches": launches, "stats": stats, "stage_ms": stage_ms,
+            "exchange": exchange, "accumulate": V,
+            "objs": dict(sc=sc, tracer=tracer, raster=raster, ctx=ctx, particles=particles, sph=sph, rays_o=rays_o, rays_d=rays_d, poses=poses,
+                         d_rgba=d_rgba, d_dist=d_dist, flush=flush, view_of=view_of, barrier=barrier, sensor=sensor)}
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -546,6 +686,9 @@ def main():
     ap.add_argument("--exchange", default="compact", choices=["compact", "allreduce"],
                     help="multi-GPU gradient exchange of the 3DGUT path: compact = all-reduce [N,12] + all-gather [N,4] + rebuild of the SH "
                          "gradient (64 B per Gaussian on the wire), allreduce = one all-reduce of [N,60] (240 B)")
+    ap.add_argument("--accumulate", type=int, default=2,
+                    help="multi-GPU: view-steps per rank between two gradient exchanges (a batch = accumulate x world views); ignored at N=1")
+    ap.add_argument("--no-sub-records", action="store_true", help="skip the c3 (6M Gaussians) and c4 (3DGRT) sub-records of the default c2 line")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -568,100 +711,26 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    import b200_native as nat
+    import b200_native as nat  # noqa: F401
     import scenes
-    import threedgut_tracer
-    from threedgut_tracer.tracer import SensorPose3D, fromOpenCVPinholeCameraModelParameters, ShutterType
+    import threedgut_tracer  # noqa: F401
 
     if args.workload.startswith("c4"):
         run_grt(args, rank, local_rank, world, dev, dist)
         return
-    sc = make_scene(args.workload)
-    n, H, W = sc.n, sc.height, sc.width
-    conf = {"render": {"enable_kernel_timings": False}}
-    tracer = threedgut_tracer.Tracer(conf)
-    raster = tracer.tracer_wrapper
-
-    particles = torch.from_numpy(sc.particles).to(dev)
-    sph = torch.from_numpy(sc.sph).to(dev)
-    ro_np, rd_np = sc.rays()
-    rays_o, rays_d = torch.from_numpy(ro_np).to(dev), torch.from_numpy(rd_np).to(dev)
-    sensor = fromOpenCVPinholeCameraModelParameters(np.array([W, H]), ShutterType.GLOBAL, np.array([sc.cx, sc.cy], np.float32),
-                                                    np.array([sc.fx, sc.fy], np.float32), np.zeros(6, np.float32), np.zeros(2, np.float32),
-                                                    np.zeros(4, np.float32))
-    n_views = 100
-    poses = [scenes.pose7_from_c2w(sc.camera(i, n_views)) for i in range(n_views)]
-    gen = torch.Generator(device=dev).manual_seed(1234)
-    d_rgba = torch.randn((H, W, 4), device=dev, generator=gen)
-    d_dist = 0.05 * torch.randn((H, W, 1), device=dev, generator=gen)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-
-    def view_of(step):  # disjoint cameras per rank
-        return (step * world + rank) % n_views
-
-    grad_flat = torch.empty(n * 60, dtype=torch.float32, device=dev)  # [N,12] and [N,48] views of one bucket: one all-reduce
-    grad_views = (grad_flat[: n * 12].view(n, 12), grad_flat[n * 12:].view(n, 48))
-    compact = None
-    if world > 1 and args.exchange == "compact":
-        import view_parallel
-
-        compact = view_parallel.CompactGradientExchange(raster, n, dev)
-        sensor_pos = [raster.sensor_position(sensor, p, p, W, H) for p in poses]  # every rank knows every view's pose
-
-    def step_device(step):
-        pose = poses[view_of(step)]
-        rgba, dst, hits, vis = raster.trace(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose)
-        if compact is not None:
-            # 64 B instead of 240 B per Gaussian on the wire: all-reduce d_particles, all-gather the radiance gradients, rebuild d_sph
-            raster.trace_bwd_compact(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose, rgba, d_rgba, dst,
-                                     d_dist, out=compact.out())
-            positions = np.stack([sensor_pos[(step * world + r) % n_views] for r in range(world)])
-            return compact.exchange(sc.sph_degree, particles, positions)
-        dp, ds = raster.trace_bwd(step, sc.sph_degree, particles, sph, rays_o, rays_d, None, sensor, 0, 1, pose, pose, rgba, d_rgba, dst, d_dist,
-                                  out=grad_views)
-        if world > 1:
-            dist.all_reduce(grad_flat)
-        return dp, ds
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    ctx = raster.native_context(dev)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()  # runs through warm-up and the timed region (both under load)
-    for s in range(args.warmup):
-        step_device(s)
-    barrier()
-    launches0 = ctx.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for s in range(args.steps):
-        flush.fill_(float(s))  # L2 flush between timed iterations, outside the per-step event pair
-        ev[s][0].record()
-        step_device(args.warmup + s)
-        ev[s][1].record()
-    barrier()
+    main_run = gut_device_loop(torch, dist, args, rank, world, dev, args.workload, args.steps, args.warmup, stage_pass=True)
     clocks = sampler.stop() if rank == 0 else None
-    step_ms = np.array([a.elapsed_time(b) for a, b in ev], dtype=np.float64)
-    total_ms = torch.tensor([float(step_ms.sum())], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    launches = ctx.launch_count() - launches0
-    stats = ctx.stats()
-    # separate short pass with per-stage CUDA events (they add host syncs, so never inside the timed region)
-    ctx.set_timings(2)
-    ctx.collect_stage_times()
-    for s in range(min(args.steps, 20)):
-        flush.fill_(float(s))
-        step_device(args.warmup + s)
-    barrier()
-    stage_ms = ctx.collect_stage_times()
-    ctx.set_timings(0)
-    value = world * args.steps / (total_ms / 1000.0)
+    o = main_run["objs"]
+    sc, tracer, raster, ctx, particles, sph, rays_o, rays_d, poses, d_rgba, d_dist, flush, view_of = (
+        o["sc"], o["tracer"], o["raster"], o["ctx"], o["particles"], o["sph"], o["rays_o"], o["rays_d"], o["poses"], o["d_rgba"], o["d_dist"],
+        o["flush"], o["view_of"])
+    n, H, W, n_views = sc.n, sc.height, sc.width, 100
+    ro_np, rd_np = sc.rays()
+    total_ms, launches, stats, stage_ms, value = main_run["total_ms"], main_run["launches"], main_run["stats"], main_run["stage_ms"], main_run["value"]
+    barrier = o["barrier"]
     work, fma_peak = None, None
     if rank == 0:
         try:  # debug entry points, outside every timed region: work counters of the last frame + FP32 FMA peak of this GPU
@@ -731,8 +800,43 @@ def main():
     e2e_value = world * e2e_steps / float(e2e_s.item())
     h2d = int(pin_o.numel() * 4 + pin_d.numel() * 4 + pin_gt.numel() * 4)
 
+    # ---- measurements beside the metric (rank 0, N = 1): the reference's own kernels on this GPU, optimizer step, image loss
+    extras = {}
+    peak, peak_src = load_peaks()
+    if rank == 0 and world == 1:
+        if not args.no_reference_gpu:
+            rg = time_reference_gpu(torch, dev, sc, poses, particles, sph, rays_o, rays_d, d_rgba, d_dist, flush, view_of, steps=min(args.steps, 30))
+            if rg is not None:
+                extras["reference_gpu"] = rg
+                if "value" in rg:
+                    ours_map = {"project": "project", "prepare_expand": "scan", "expand": "expand", "sort": "sort+tile_ranges", "render": "render",
+                                "render_backward": "render_backward", "project_backward": "project_backward"}
+                    ours_stage = dict(stage_ms)
+                    ours_stage["sort+tile_ranges"] = stage_ms["sort"] + stage_ms["tile_ranges"]
+                    extras["vs_reference_gpu"] = {"speedup_device_timed": value / rg["value"],
+                                                  "per_stage_ours_over_reference_ms": {k: [ours_stage[v], rg["stage_ms"][k]] for k, v in ours_map.items()}}
+        extras["optimizer_step"] = time_optimizer_step(torch, dev, n, flush, peak, peak_src)
+        extras["image_loss"] = time_image_loss(torch, dev, H, W, flush, peak, peak_src)
+
+    # ---- sub-records of the default line (same process, same ranks, short runs; never part of `value`): BASELINE configs[2] (C3: 6M
+    # Gaussians at 1237x822, the configuration the 1->8 GPU curve is named on) and, at N=1, configs[3] (C4: the C2 scene through 3DGRT)
+    sub_records = {}
+    run_info = {k: v for k, v in main_run.items() if k != "objs"}
+    sc_name = sc.name
+    if args.workload == "c2" and not args.no_sub_records:
+        del main_run, o, tracer, raster, ctx, particles, sph, rays_o, rays_d, d_rgba, d_dist, flush, feed, _G, grads
+        torch.cuda.empty_cache()
+        c3 = gut_device_loop(torch, dist, args, rank, world, dev, "c3", steps=max(2 * args.accumulate, 12), warmup=4, stage_pass=True)
+        sub_records["c3"] = {"workload": c3["objs"]["sc"].name, "value": c3["value"], "unit": UNIT, "n_gpus": world, "steps": c3["steps"],
+                             "ms_per_step": c3["total_ms"] / c3["steps"], "stage_ms": c3["stage_ms"], "exchange": c3["exchange"],
+                             "N": c3["stats"]["N"], "V": c3["stats"]["V"], "I": c3["stats"]["I"], "T": c3["stats"]["T"],
+                             "note": "BASELINE configs[2]: 6M Gaussians, 1237x822; same loop, timing and exchange as the headline, fewer steps"}
+        del c3
+        torch.cuda.empty_cache()
+        if world == 1:
+            sub_records["c4"] = run_grt(args, rank, local_rank, world, dev, dist, sub=True)
+
     if rank == 0:
-        peak, peak_src = load_peaks()
         N_, I_, V_, T_, P_ = stats["N"], stats["I"], stats["V"], stats["T"], H * W
         # algorithmic bytes per launch (SURVEY.md 8d bracketed terms)
         stage_bytes = {
@@ -751,7 +855,7 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if tj.get("workload") == sc.name:
+            if tj.get("workload") == sc_name:
                 traffic = tj["dram_bytes_per_launch"].get({"render": "render_forward"}.get(dom, dom))
         achieved = stage_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         # SURVEY 8d "Algorithmic FLOPs for G6/G7": 65 per pair test + 30 per accepted hit (forward) / 400 per accepted hit (adjoint), with the
@@ -767,16 +871,20 @@ def main():
                     "render": {"achieved": f_fwd / t_fwd / 1e12, "frac": f_fwd / t_fwd / 1e12 / fma_peak if fma_peak else None},
                     "render_backward": {"achieved": f_bwd / t_bwd / 1e12, "frac": f_bwd / t_bwd / 1e12 / fma_peak if fma_peak else None},
                     "work": work,
-                    "executed": {"forward_lane_tests": work["tests_exec"], "backward_lane_tests": work["bwd_lanes"],
-                                 "forward_warp_iterations": work["fwd_iters"], "backward_warp_iterations": work["hit_iters"],
-                                 "hit_lanes_per_backward_iteration": work["hits"] / max(work["hit_iters"], 1)}}
+                    "executed": {"forward_lane_tests": work["tests_exec"], "backward_lane_tests_whole_warp_walk": work["bwd_lanes"],
+                                 "forward_warp_iterations": work["fwd_iters"],
+                                 "backward_warp_iterations": {"quarter_warp_walk (default)": work["iters8"], "half_warp_walk": work["iters16"],
+                                                              "whole_warp_walk": work["hit_iters"]},
+                                 "gradient_rows_flushed": {"quarter": work["sub8_hits"], "half": work["sub16_hits"], "whole": work["hit_iters"]},
+                                 "hit_lanes_per_whole_warp_iteration": work["hits"] / max(work["hit_iters"], 1)}}
         frame_bytes = 356 * N_ + 796 * V_ + (156 + 24 * 6) * I_ + 24 * T_ + 136 * P_
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": run_info["steps"], "warmup": run_info["warmup"],
+            "ms_per_step": total_ms / run_info["steps"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": sc.name, "gaussians": n, "resolution": [W, H], "path": "3dgut", "views_per_step": world,
-                       "parallelism": f"view-parallel dp{world}" if world > 1 else "single",
+            "config": {"workload": sc_name, "gaussians": n, "resolution": [W, H], "path": "3dgut", "step": "one view per rank, forward + backward",
+                       "views_per_step": world, "views_per_batch": world * run_info["accumulate"],
+                       "parallelism": f"view-parallel dp{world}, gradients summed every {run_info['accumulate']} view-steps" if world > 1 else "single",
                        "exchange": (args.exchange if world > 1 else "none"), "l2": "flushed between timed steps (256 MiB fill)",
                        "N": N_, "V": V_, "I": I_, "T": T_, "P": P_},
             "clocks": clocks,
@@ -791,31 +899,21 @@ def main():
                                  "roofline_fp32 (work counters and FMA peak both measured in this run) is the figure that bounds them"},
             "roofline_fp32": fp32,
             "stage_ms": stage_ms,
-            "frame_algorithmic_gbs": frame_bytes / (total_ms / args.steps * 1e-3) / 1e9,
+            "frame_algorithmic_gbs": frame_bytes / (total_ms / run_info["steps"] * 1e-3) / 1e9,
         }
-        if world == 1 and not args.no_reference_gpu:
-            rg = time_reference_gpu(torch, dev, sc, poses, particles, sph, rays_o, rays_d, d_rgba, d_dist, flush, view_of, steps=min(args.steps, 30))
-            if rg is not None:
-                line["reference_gpu"] = rg
-                if "value" in rg:
-                    ours_map = {"project": "project", "prepare_expand": "scan", "expand": "expand", "sort": "sort+tile_ranges", "render": "render",
-                                "render_backward": "render_backward", "project_backward": "project_backward"}
-                    ours_stage = dict(stage_ms)
-                    ours_stage["sort+tile_ranges"] = stage_ms["sort"] + stage_ms["tile_ranges"]
-                    line["vs_reference_gpu"] = {"speedup_device_timed": value / rg["value"],
-                                                "per_stage_ours_over_reference_ms": {k: [ours_stage[v], rg["stage_ms"][k]] for k, v in ours_map.items()}}
-        if world == 1:
-            line["optimizer_step"] = time_optimizer_step(torch, dev, n, flush, peak, peak_src)
-            line["image_loss"] = time_image_loss(torch, dev, H, W, flush, peak, peak_src)
+        if run_info["exchange"] is not None:
+            line["exchange"] = run_info["exchange"]
+        line.update(sub_records)
+        line.update(extras)
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            fps, _ = cpu_port_frames_per_s(sc, args.cpu_tile_stride, frames=1, warm=0)
+            sc_cpu = make_scene(args.workload)
+            fps, _ = cpu_port_frames_per_s(sc_cpu, args.cpu_tile_stride, frames=1, warm=0)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"1 view: full projection+binning, compositing fwd+bwd on every {args.cpu_tile_stride}th tile, extrapolated"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
 
 if __name__ == "__main__":
     main()
