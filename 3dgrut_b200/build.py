@@ -19,6 +19,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = {
     "gut_project.cu": ["-fmad=false"],
     "gut_sort.cu": [],
+    "gut_binning.cu": [],
     # compositing kernels: same numerics mode as the reference build (-use_fast_math, setup_3dgut.py:108-109):
     # flush-to-zero, approximate div/sqrt/exp; parity is tolerance-based for these
     "gut_render.cu": ["--use_fast_math"],

@@ -5,6 +5,7 @@
 // following backward, all work enqueued on the caller's stream.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -157,12 +158,12 @@ struct gutb200_ctx {
     cudaStream_t own_stream = nullptr;
 
     // forward context (reused by backward): per particle
-    DeviceBuffer tiles_count, offsets, proj, depth, rgb, grad_acc, scan_temp;
-    DeviceBuffer ids, perm, depth_sorted, cnt_perm, dsort_temp;   // depth sort of the particles
-    // per intersection
-    DeviceBuffer keys_in, keys_out, vals_in, vals_out, sort_temp;
-    // per tile
-    DeviceBuffer ranges, tile_order, chunk_base, hit_words;
+    DeviceBuffer tiles_count, proj, depth, rgb, grad_acc;
+    // per intersection: 64-bit (depth bits << 32 | particle) keys in per-tile slices, sorted particle indices, hit words
+    DeviceBuffer keys64, vals_out, hit_words;
+    // per tile: list-length histogram, slot counters, ranges, heaviest-first order, hit-word slice offsets; {I, overflow} on the device
+    DeviceBuffer tile_hist, tile_fill, ranges, tile_order, chunk_base, totals;
+    cudaEvent_t ev_total = nullptr;
     gutb200_camera fwd_camera{};   // the camera of the forward whose context the backward replays
     // host staging for the *_host entry points
     DeviceBuffer h_particles, h_sph, h_rays_o, h_rays_d, h_rgba, h_dist, h_hits, h_vis, h_drgba, h_ddist, h_dpart, h_dsph;
@@ -363,7 +364,8 @@ int gutb200_create(const gutb200_config* cfg, int device, gutb200_ctx** out) {
     c->cfg = *cfg;
     c->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost(reinterpret_cast<void**>(&c->pinned_total), sizeof(uint32_t)) != cudaSuccess) {
+        cudaMallocHost(reinterpret_cast<void**>(&c->pinned_total), 2 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_total, cudaEventDisableTiming) != cudaSuccess) {
         delete c;
         return 4;
     }
@@ -376,15 +378,15 @@ void gutb200_destroy(gutb200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DeviceBuffer* bufs[] = {&c->tiles_count, &c->offsets, &c->proj, &c->depth, &c->rgb, &c->grad_acc, &c->scan_temp, &c->ids, &c->perm,
-                            &c->depth_sorted, &c->cnt_perm, &c->dsort_temp, &c->keys_in,
-                            &c->keys_out, &c->vals_in, &c->vals_out, &c->sort_temp, &c->ranges, &c->tile_order, &c->chunk_base, &c->hit_words, &c->h_particles, &c->h_sph,
+    DeviceBuffer* bufs[] = {&c->tiles_count, &c->proj, &c->depth, &c->rgb, &c->grad_acc, &c->keys64, &c->vals_out, &c->hit_words, &c->tile_hist,
+                            &c->tile_fill, &c->ranges, &c->tile_order, &c->chunk_base, &c->totals, &c->h_particles, &c->h_sph,
                             &c->h_rays_o, &c->h_rays_d, &c->h_rgba, &c->h_dist, &c->h_hits, &c->h_vis, &c->h_drgba, &c->h_ddist,
                             &c->h_dpart, &c->h_dsph};
     for (DeviceBuffer* b : bufs) b->release();
     if (c->pinned_total) cudaFreeHost(c->pinned_total);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
+    if (c->ev_total) cudaEventDestroy(c->ev_total);
     for (auto& pair : c->st_ev)
         for (auto& e : pair)
             if (e) cudaEventDestroy(e);
@@ -413,84 +415,86 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     }
 
     GUT_CUDA(c, c->tiles_count.reserve(nn * 4, s));
-    GUT_CUDA(c, c->offsets.reserve(nn * 4, s));
     GUT_CUDA(c, c->proj.reserve(nn * sizeof(ProjRecord), s));
     GUT_CUDA(c, c->depth.reserve(nn * 4, s));
     GUT_CUDA(c, c->rgb.reserve(nn * 12, s));
-    GUT_CUDA(c, c->ranges.reserve(static_cast<size_t>(tiles) * 8, s));
-    GUT_CUDA(c, c->tile_order.reserve(static_cast<size_t>(tiles) * 4, s));
-    GUT_CUDA(c, c->chunk_base.reserve(static_cast<size_t>(tiles) * 4, s));
-    GUT_CUDA(c, c->scan_temp.reserve(scan_temp_bytes(n) + 16, s));
-    GUT_CUDA(c, c->ids.reserve(nn * 4, s));
-    GUT_CUDA(c, c->perm.reserve(nn * 4, s));
-    GUT_CUDA(c, c->depth_sorted.reserve(nn * 4, s));
-    GUT_CUDA(c, c->cnt_perm.reserve(nn * 4, s));
-    GUT_CUDA(c, c->dsort_temp.reserve(sort32_temp_bytes(static_cast<int64_t>(nn)) + 16, s));
+    const size_t tt = static_cast<size_t>(tiles);
+    GUT_CUDA(c, c->tile_hist.reserve(tt * 4, s));
+    GUT_CUDA(c, c->tile_fill.reserve(tt * 4, s));
+    GUT_CUDA(c, c->ranges.reserve(tt * 8, s));
+    GUT_CUDA(c, c->tile_order.reserve(tt * 4, s));
+    GUT_CUDA(c, c->chunk_base.reserve(tt * 4, s));
+    GUT_CUDA(c, c->totals.reserve(16, s));
 
-    uint32_t total = 0;
-    if (n > 0) {
-        {
-            StageTimer t(c, 0, s);
-            launch_project(s, c->cam, c->fcfg, n, particles, sph, sph_degree, c->tiles_count.as<uint32_t>(), c->proj.as<ProjRecord>(),
-                           c->depth.as<float>(), c->rgb.as<float>(), visibility, c->ids.as<uint32_t>());
-        }
-        c->launches++;
+    // The frame is enqueued in one go.  The list total I is needed on the host only to SIZE the key / value / hit-word buffers, so the
+    // kernels that depend on it are launched speculatively against the capacity those (grow-only) buffers already have, and the host
+    // reads I after everything is queued -- the GPU keeps working through the round trip the reference stalls on
+    // (gutRenderer.cu:313-321).  If I does not fit (first frame, or the scene grew past the 12.5 % head-room) tile_scan publishes empty
+    // ranges, the speculative kernels find nothing to do, and the tail of the frame is queued again after the buffers have grown.
+    auto bin_and_render = [&](uint32_t capacity) -> int {
         {
             StageTimer t(c, 1, s);
-            // depth order of the particles (positive floats sort like their bit patterns), then slice offsets in that order
-            run_sort32_pairs(s, c->dsort_temp.ptr, c->dsort_temp.bytes, reinterpret_cast<const uint32_t*>(c->depth.as<float>()),
-                             c->depth_sorted.as<uint32_t>(), c->ids.as<uint32_t>(), c->perm.as<uint32_t>(), n, 32);
-            launch_gather_counts(s, n, c->perm.as<uint32_t>(), c->tiles_count.as<uint32_t>(), c->cnt_perm.as<uint32_t>());
-            run_inclusive_scan(s, c->scan_temp.ptr, c->scan_temp.bytes, c->cnt_perm.as<uint32_t>(), c->offsets.as<uint32_t>(), n);
+            launch_tile_scan(s, static_cast<int>(tiles), c->tile_hist.as<uint32_t>(), capacity, c->ranges.as<uint32_t>(), c->chunk_base.as<uint32_t>(),
+                             c->tile_order.as<uint32_t>(), c->tile_fill.as<uint32_t>(), c->totals.as<uint32_t>());
+        }
+        GUT_CUDA(c, cudaMemcpyAsync(c->pinned_total, c->totals.ptr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        GUT_CUDA(c, cudaEventRecord(c->ev_total, s));
+        c->launches++;
+        if (capacity > 0 && n > 0) {
+            {
+                StageTimer t(c, 2, s);
+                launch_expand_place(s, c->cam, c->fcfg, n, c->proj.as<ProjRecord>(), c->depth.as<float>(), c->ranges.as<uint32_t>(),
+                                    c->totals.as<uint32_t>(), capacity, c->tile_fill.as<uint32_t>(), c->keys64.as<unsigned long long>());
+            }
+            {
+                StageTimer t(c, 3, s);
+                GUT_CUDA(c, launch_tile_sort(s, static_cast<int>(tiles), c->tile_order.as<uint32_t>(), c->ranges.as<uint32_t>(), c->totals.as<uint32_t>(),
+                                             c->keys64.as<unsigned long long>(), c->vals_out.as<uint32_t>()));
+            }
+            c->launches += 3;
+        }
+        {
+            StageTimer t(c, 5, s);
+            if (c->fcfg.k_buffer_size == 0)  // chunks a forward warp never reaches must read as "no hit" in the backward
+                GUT_CUDA(c, cudaMemsetAsync(c->hit_words.ptr, 0, hit_words_capacity(capacity, tiles) * 4, s));
+            if (c->fcfg.k_buffer_size > 0)  // sorted 3DGUT (gut_render_kbuffer.cu)
+                launch_render_forward_kbuffer(s, c->cam, c->fcfg, c->fcfg.k_buffer_size, rays_o, rays_d, particles, c->rgb.as<float>(),
+                                              c->vals_out.as<uint32_t>(), c->ranges.as<uint32_t>(), out_rgba, out_dist, out_hits);
+            else
+                launch_render_forward(s, c->cam, c->fcfg, rays_o, rays_d, particles, c->rgb.as<float>(), c->vals_out.as<uint32_t>(),
+                                      c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), c->chunk_base.as<uint32_t>(),
+                                      c->hit_words.as<uint32_t>(), out_rgba, out_dist, out_hits);
         }
         c->launches++;
-        // the one host round trip of the frame, as in the reference (gutRenderer.cu:313-321): sizes the sort
-        GUT_CUDA(c, cudaMemcpyAsync(c->pinned_total, c->offsets.as<uint32_t>() + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        GUT_CUDA(c, cudaStreamSynchronize(s));
-        total = *c->pinned_total;
+        return 0;
+    };
+
+    uint32_t total = 0;
+    GUT_CUDA(c, cudaMemsetAsync(c->tile_hist.ptr, 0, tt * 4, s));
+    if (n > 0) {
+        StageTimer t(c, 0, s);
+        launch_project(s, c->cam, c->fcfg, n, particles, sph, sph_degree, c->tiles_count.as<uint32_t>(), c->proj.as<ProjRecord>(),
+                       c->depth.as<float>(), c->rgb.as<float>(), visibility, c->tile_hist.as<uint32_t>());
+        c->launches++;
     }
-    GUT_CUDA(c, cudaMemsetAsync(c->ranges.ptr, 0, static_cast<size_t>(tiles) * 8, s));
-    if (total > 0) {
-        const int end_bit = static_cast<int>(higher_msb(static_cast<uint32_t>(tiles)));  // tile bits only (gutRenderer.cu:365 sorts 32 + this)
-        GUT_CUDA(c, c->keys_in.reserve(static_cast<size_t>(total) * 4, s));
-        GUT_CUDA(c, c->keys_out.reserve(static_cast<size_t>(total) * 4, s));
-        GUT_CUDA(c, c->vals_in.reserve(static_cast<size_t>(total) * 4, s));
-        GUT_CUDA(c, c->vals_out.reserve(static_cast<size_t>(total) * 4, s));
-        GUT_CUDA(c, c->sort_temp.reserve(sort32_temp_bytes(total) + 16, s));
-        {
-            StageTimer t(c, 2, s);
-            launch_expand(s, c->cam, c->fcfg, n, c->perm.as<uint32_t>(), c->offsets.as<uint32_t>(), c->proj.as<ProjRecord>(),
-                          c->keys_in.as<uint32_t>(), c->vals_in.as<uint32_t>());
-        }
-        {
-            StageTimer t(c, 3, s);
-            run_sort32_pairs(s, c->sort_temp.ptr, c->sort_temp.bytes, c->keys_in.as<uint32_t>(), c->keys_out.as<uint32_t>(),
-                             c->vals_in.as<uint32_t>(), c->vals_out.as<uint32_t>(), total, end_bit);
-        }
-        {
-            StageTimer t(c, 4, s);
-            launch_tile_ranges(s, total, c->keys_out.as<uint32_t>(), c->ranges.as<uint32_t>());
-        }
-        c->launches += 2;
-    } else {
-        GUT_CUDA(c, c->vals_out.reserve(16, s));
+    GUT_CUDA(c, c->vals_out.reserve(16, s));
+    GUT_CUDA(c, c->hit_words.reserve(hit_words_capacity(0, tiles) * 4, s));
+    uint32_t capacity = static_cast<uint32_t>(std::min<size_t>(c->keys64.bytes / 8, 0xFFFFFFF0u));
+    // the three per-intersection buffers grow together; `capacity` is the smallest of them in entries
+    capacity = static_cast<uint32_t>(std::min<size_t>(capacity, c->vals_out.bytes / 4));
+    while (capacity > 0 && hit_words_capacity(capacity, tiles) * 4 > c->hit_words.bytes) capacity = capacity > 4096 ? capacity - 4096 : 0;
+    if (int rc = bin_and_render(capacity)) return rc;
+    GUT_CUDA(c, cudaEventSynchronize(c->ev_total));
+    total = c->pinned_total[0];
+    if (c->pinned_total[1] != 0u) {  // did not fit: grow (grow-only, 12.5 % head-room) and queue the tail of the frame again
+        GUT_CUDA(c, c->keys64.reserve(static_cast<size_t>(total) * 8, s));
+        GUT_CUDA(c, c->vals_out.reserve(static_cast<size_t>(total) * 4 + 16, s));
+        GUT_CUDA(c, c->hit_words.reserve(hit_words_capacity(total + (total >> 3) + 64, tiles) * 4, s));
+        capacity = total;
+        if (int rc = bin_and_render(capacity)) return rc;
+        GUT_CUDA(c, cudaEventSynchronize(c->ev_total));
+        if (c->pinned_total[1] != 0u || c->pinned_total[0] != total) return fail(c, "internal error: intersection count changed between two passes");
     }
-    const size_t words = hit_words_capacity(total, tiles);
-    GUT_CUDA(c, c->hit_words.reserve(words * 4, s));
-    {
-        StageTimer t(c, 5, s);
-        launch_tile_order(s, c->cam, c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), c->chunk_base.as<uint32_t>());
-        if (c->fcfg.k_buffer_size == 0)  // chunks a forward warp never reaches must read as "no hit" in the backward
-            GUT_CUDA(c, cudaMemsetAsync(c->hit_words.ptr, 0, words * 4, s));
-        if (c->fcfg.k_buffer_size > 0)  // sorted 3DGUT (gut_render_kbuffer.cu)
-            launch_render_forward_kbuffer(s, c->cam, c->fcfg, c->fcfg.k_buffer_size, rays_o, rays_d, particles, c->rgb.as<float>(),
-                                          c->vals_out.as<uint32_t>(), c->ranges.as<uint32_t>(), out_rgba, out_dist, out_hits);
-        else
-            launch_render_forward(s, c->cam, c->fcfg, rays_o, rays_d, particles, c->rgb.as<float>(), c->vals_out.as<uint32_t>(),
-                                  c->ranges.as<uint32_t>(), c->tile_order.as<uint32_t>(), c->chunk_base.as<uint32_t>(),
-                                  c->hit_words.as<uint32_t>(), out_rgba, out_dist, out_hits);
-    }
-    c->launches += 2;
     GUT_CUDA(c, cudaGetLastError());
     if (c->cfg.enable_timings) {
         GUT_CUDA(c, cudaEventRecord(c->ev[1], s));
@@ -683,8 +687,8 @@ int gutb200_debug_copy(gutb200_ctx* c, int what, void* dst, size_t bytes) {
             if (I == 0) return 0;
             void* tmp = nullptr;
             GUT_CUDA(c, cudaMalloc(&tmp, I * 8));
-            launch_synth_keys(c->fwd_stream, static_cast<int64_t>(I), c->keys_out.as<uint32_t>(), c->vals_out.as<uint32_t>(), c->depth.as<float>(),
-                              static_cast<uint64_t*>(tmp));
+            launch_synth_tile_keys(c->fwd_stream, static_cast<int>(T), c->ranges.as<uint32_t>(), c->vals_out.as<uint32_t>(), c->depth.as<float>(),
+                                   static_cast<uint64_t*>(tmp));
             cudaError_t e = cudaStreamSynchronize(c->fwd_stream);
             if (e == cudaSuccess) e = cudaMemcpy(dst, tmp, I * 8, cudaMemcpyDeviceToHost);
             cudaFree(tmp);

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
                                                                const float* __restrict__ sph, int sph_degree,
                                                                uint32_t* __restrict__ tiles_count, ProjRecord* __restrict__ proj,
                                                                float* __restrict__ depth, float* __restrict__ rgb,
-                                                               float* __restrict__ visibility, uint32_t* __restrict__ ids) {
+                                                               float* __restrict__ visibility, uint32_t* __restrict__ tile_hist) {
     __shared__ __align__(128) float4 s_rec[kProjThreads * 3];
     __shared__ __align__(8) uint64_t s_bar;
 
@@ -422,11 +422,16 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
         cells = (bb.x1 - bb.x0) * (bb.y1 - bb.y0);
         if (!cfg.tile_culling) {
             ntiles = static_cast<uint32_t>(cells);
+            for (int y = bb.y0; y < bb.y1; ++y)
+                for (int x = bb.x0; x < bb.x1; ++x) atomicAdd(&tile_hist[y * cam.grid_x + x], 1u);
             cells = 0;
         } else if (cells <= kSmallBox) {
             for (int y = bb.y0; y < bb.y1; ++y)
                 for (int x = bb.x0; x < bb.x1; ++x)
-                    if (tile_min_power(static_cast<float>(x), static_cast<float>(y), ca, cb, cc, pcx, pcy) < maxpow) ntiles++;
+                    if (tile_min_power(static_cast<float>(x), static_cast<float>(y), ca, cb, cc, pcx, pcy) < maxpow) {
+                        ntiles++;
+                        atomicAdd(&tile_hist[y * cam.grid_x + x], 1u);  // per-tile list length (gut_binning.cu: tile_scan)
+                    }
             cells = 0;
         }
     }
@@ -447,6 +452,7 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
                 if (c < nc) {
                     const int y = by0 + c / bw, x = bx0 + c % bw;
                     pass = tile_min_power(static_cast<float>(x), static_cast<float>(y), qa, qb, qc, qx, qy) < qp;
+                    if (pass) atomicAdd(&tile_hist[y * cam.grid_x + x], 1u);
                 }
                 total += __popc(__ballot_sync(0xFFFFFFFFu, pass));
             }
@@ -455,7 +461,6 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
     }
     if (!in_range) return;
     tiles_count[i] = ntiles;
-    ids[i] = static_cast<uint32_t>(i);  // payload of the depth sort
 
     ProjRecord pr;
     float zdepth = 0.f, col[3] = {0.f, 0.f, 0.f};
@@ -478,59 +483,49 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
 
 // G3: emit (tile, particle) for every surviving tile (GUTProjector::expand, gutProjector.cuh:324-388).
 // The reference emits 64-bit (tile << 32 | depth) keys in particle order and radix-sorts 44 bits of them (6 passes over
-// 12 bytes per entry).  Here the particles are depth-sorted first (N 32-bit keys), each owns the slice
-// [offset[rank-1], offset[rank]) of the stream, and only the 12-13 tile bits of the entries remain to be sorted
-// (2 passes over 8 bytes per entry): same final order, a quarter of the traffic.  Inside a slice the tiles are written
-// in the reference's row-major order (ordered ballot compaction when the warp walks a large footprint together).
-__global__ void __launch_bounds__(256) expand_kernel(FrameCamera cam, FrameConfig cfg, int64_t n, const uint32_t* __restrict__ perm,
-                                                     const uint32_t* __restrict__ offsets, const ProjRecord* __restrict__ proj,
-                                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ values) {
-    // thread j handles the particle at depth rank j: slices of the key stream are laid out in depth order, so the stable
-    // tile sort that follows yields (tile, depth, particle) order == the reference's stable sort of (tile<<32 | depth) keys
-    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const bool in_range = j < n;
-    const int64_t i = in_range ? static_cast<int64_t>(perm[j]) : 0;
+// 12 bytes per entry).  Here every pair goes straight into ITS TILE's slice of the key buffer (ranges from tile_scan) at a slot
+// claimed with one atomic on the tile's fill counter, as the key (depth bits << 32 | particle index); tile_sort (gut_binning.cu) then
+// orders each slice on chip.  The tile walk is the reference's (row-major, same culling arithmetic as project_kernel).
+__global__ void __launch_bounds__(256) expand_place_kernel(FrameCamera cam, FrameConfig cfg, int64_t n, const ProjRecord* __restrict__ proj,
+                                                           const float* __restrict__ depth, const uint32_t* __restrict__ ranges,
+                                                           const uint32_t* __restrict__ totals, uint32_t capacity,
+                                                           uint32_t* __restrict__ fill, unsigned long long* __restrict__ keys) {
+    if (totals[1] != 0u) return;  // capacity exceeded: the host grows the key buffer and launches again
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool in_range = i < n;
     ProjRecord pr;
     pr.ex = 0.f;
     if (in_range) pr = proj[i];
     const bool active = in_range && !(pr.ex <= 1e-06f);
-    uint32_t off = 0, maxoff = 0;
     TileBox bb = {0, 0, 0, 0};
     float maxpow = 0.f;
     int cells = 0;
+    unsigned long long key = 0ull;
+    auto place = [&](int tile, unsigned long long k) {
+        const uint32_t slot = atomicAdd(&fill[tile], 1u);
+        const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
+        if (begin + slot < end && begin + slot < capacity) keys[begin + slot] = k;
+    };
     if (active) {
-        off = (j == 0) ? 0u : offsets[j - 1];
-        maxoff = offsets[j];
+        key = (static_cast<unsigned long long>(__float_as_uint(depth[i])) << 32) | static_cast<unsigned long long>(static_cast<uint32_t>(i));
         bb = tile_box(cam.grid_x, cam.grid_y, pr.cx, pr.cy, pr.ex, pr.ey);
         cells = (bb.x1 - bb.x0) * (bb.y1 - bb.y0);
         if (!cfg.tile_culling) {
             for (int y = bb.y0; y < bb.y1; ++y)
-                for (int x = bb.x0; x < bb.x1; ++x) {
-                    keys[off] = static_cast<uint32_t>(y * cam.grid_x + x);
-                    values[off] = static_cast<uint32_t>(i);
-                    off++;
-                }
+                for (int x = bb.x0; x < bb.x1; ++x) place(y * cam.grid_x + x, key);
             cells = 0;
         } else {
             maxpow = logf(pr.op / cfg.min_alpha);
             if (cells <= kSmallBox) {
-                for (int y = bb.y0; (y < bb.y1) && (off < maxoff); ++y)
-                    for (int x = bb.x0; (x < bb.x1) && (off < maxoff); ++x)
-                        if (tile_min_power(static_cast<float>(x), static_cast<float>(y), pr.ca, pr.cb, pr.cc, pr.cx, pr.cy) < maxpow) {
-                            keys[off] = static_cast<uint32_t>(y * cam.grid_x + x);
-                            values[off] = static_cast<uint32_t>(i);
-                            off++;
-                        }
-                for (; off < maxoff; ++off) {  // padding, never produced when project and expand agree (gutProjector.cuh:372-376)
-                    keys[off] = kInvalid;
-                    values[off] = kInvalid;
-                }
+                for (int y = bb.y0; y < bb.y1; ++y)
+                    for (int x = bb.x0; x < bb.x1; ++x)
+                        if (tile_min_power(static_cast<float>(x), static_cast<float>(y), pr.ca, pr.cb, pr.cc, pr.cx, pr.cy) < maxpow)
+                            place(y * cam.grid_x + x, key);
                 cells = 0;
             }
         }
     }
     const unsigned lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
     unsigned big = __ballot_sync(0xFFFFFFFFu, cells > kSmallBox);
     while (big) {
         const int src = __ffs(big) - 1;
@@ -539,29 +534,13 @@ __global__ void __launch_bounds__(256) expand_kernel(FrameCamera cam, FrameConfi
         const int bw = __shfl_sync(0xFFFFFFFFu, bb.x1, src) - bx0, nc = __shfl_sync(0xFFFFFFFFu, cells, src);
         const float qa = __shfl_sync(0xFFFFFFFFu, pr.ca, src), qb = __shfl_sync(0xFFFFFFFFu, pr.cb, src), qc = __shfl_sync(0xFFFFFFFFu, pr.cc, src);
         const float qx = __shfl_sync(0xFFFFFFFFu, pr.cx, src), qy = __shfl_sync(0xFFFFFFFFu, pr.cy, src), qp = __shfl_sync(0xFFFFFFFFu, maxpow, src);
-        const uint32_t qend = __shfl_sync(0xFFFFFFFFu, maxoff, src);
-        uint32_t cur = __shfl_sync(0xFFFFFFFFu, off, src);
-        const uint32_t pid = static_cast<uint32_t>(__shfl_sync(0xFFFFFFFFu, static_cast<int>(i & 0x7FFFFFFF), src));
+        const unsigned long long qk = __shfl_sync(0xFFFFFFFFu, key, src);
         for (int c0 = 0; c0 < nc; c0 += 32) {
             const int c = c0 + static_cast<int>(lane);
-            bool pass = false;
-            int tile = 0;
             if (c < nc) {
                 const int y = by0 + c / bw, x = bx0 + c % bw;
-                tile = y * cam.grid_x + x;
-                pass = tile_min_power(static_cast<float>(x), static_cast<float>(y), qa, qb, qc, qx, qy) < qp;
+                if (tile_min_power(static_cast<float>(x), static_cast<float>(y), qa, qb, qc, qx, qy) < qp) place(y * cam.grid_x + x, qk);
             }
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
-            const uint32_t dst = cur + __popc(m & lt_mask);
-            if (pass && dst < qend) {
-                keys[dst] = static_cast<uint32_t>(tile);
-                values[dst] = pid;
-            }
-            cur += __popc(m);
-        }
-        for (uint32_t k = cur + lane; k < qend; k += 32) {  // padding (see above)
-            keys[k] = kInvalid;
-            values[k] = kInvalid;
         }
     }
 }
@@ -585,13 +564,6 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t num_keys, cons
     if (valid && (k == num_keys - 1)) ranges[tile * 2 + 1] = static_cast<uint32_t>(num_keys);
 }
 
-// counts in depth order (input of the offset scan)
-__global__ void __launch_bounds__(256) gather_counts_kernel(int64_t n, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ counts,
-                                                            uint32_t* __restrict__ out) {
-    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (j < n) out[j] = counts[perm[j]];
-}
-
 // test-only: the reference's 64-bit keys (tile << 32 | depth bits) of the sorted stream
 __global__ void __launch_bounds__(256) synth_keys_kernel(int64_t num, const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ vals,
                                                          const float* __restrict__ depth, uint64_t* __restrict__ out) {
@@ -604,11 +576,6 @@ __global__ void __launch_bounds__(256) synth_keys_kernel(int64_t num, const uint
 
 }  // namespace
 
-void launch_gather_counts(cudaStream_t s, int64_t n, const uint32_t* perm, const uint32_t* counts, uint32_t* out) {
-    if (n <= 0) return;
-    gather_counts_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(n, perm, counts, out);
-}
-
 void launch_synth_keys(cudaStream_t s, int64_t num, const uint32_t* tiles, const uint32_t* vals, const float* depth, uint64_t* out) {
     if (num <= 0) return;
     synth_keys_kernel<<<static_cast<unsigned>((num + 255) / 256), 256, 0, s>>>(num, tiles, vals, depth, out);
@@ -616,20 +583,20 @@ void launch_synth_keys(cudaStream_t s, int64_t num, const uint32_t* tiles, const
 
 void launch_project(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const float* particles,
                     const float* sph, int sph_degree, uint32_t* tiles_count, ProjRecord* proj, float* depth, float* rgb,
-                    float* visibility, uint32_t* ids) {
+                    float* visibility, uint32_t* tile_hist) {
     if (n <= 0) return;
     const unsigned blocks = static_cast<unsigned>((n + kProjThreads - 1) / kProjThreads);
     if (cam.rolling_shutter != 0)
-        project_kernel<true><<<blocks, kProjThreads, 0, s>>>(cam, cfg, n, particles, sph, sph_degree, tiles_count, proj, depth, rgb, visibility, ids);
+        project_kernel<true><<<blocks, kProjThreads, 0, s>>>(cam, cfg, n, particles, sph, sph_degree, tiles_count, proj, depth, rgb, visibility, tile_hist);
     else
-        project_kernel<false><<<blocks, kProjThreads, 0, s>>>(cam, cfg, n, particles, sph, sph_degree, tiles_count, proj, depth, rgb, visibility, ids);
+        project_kernel<false><<<blocks, kProjThreads, 0, s>>>(cam, cfg, n, particles, sph, sph_degree, tiles_count, proj, depth, rgb, visibility, tile_hist);
 }
 
-void launch_expand(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const uint32_t* perm, const uint32_t* offsets,
-                   const ProjRecord* proj, uint32_t* keys, uint32_t* values) {
+void launch_expand_place(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const ProjRecord* proj, const float* depth,
+                         const uint32_t* ranges, const uint32_t* totals, uint32_t capacity, uint32_t* fill, unsigned long long* keys) {
     if (n <= 0) return;
     const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-    expand_kernel<<<blocks, 256, 0, s>>>(cam, cfg, n, perm, offsets, proj, keys, values);
+    expand_place_kernel<<<blocks, 256, 0, s>>>(cam, cfg, n, proj, depth, ranges, totals, capacity, fill, keys);
 }
 
 void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint32_t* sorted_keys, uint32_t* ranges) {
