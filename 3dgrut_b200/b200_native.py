@@ -229,7 +229,7 @@ class GrtConfig(C.Structure):
 
 
 GRT_EXPORTS = ["grtb200_default_config", "grtb200_create", "grtb200_destroy", "grtb200_last_error", "grtb200_build_bvh", "grtb200_trace",
-               "grtb200_trace_bwd", "grtb200_scene_aabb", "grtb200_launch_count"]
+               "grtb200_trace_bwd", "grtb200_scene_aabb", "grtb200_launch_count", "grtb200_debug_trace_counters", "grtb200_set_replay"]
 
 
 def _grt_lib():
@@ -246,6 +246,8 @@ def _grt_lib():
         lib.grtb200_trace.argtypes = [vp, vp, i64, vp, vp, i32, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
         lib.grtb200_trace_bwd.argtypes = [vp, vp, i64, vp, vp, i32, f32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         lib.grtb200_scene_aabb.argtypes = [vp, vp]
+        lib.grtb200_set_replay.argtypes = [vp, i32]
+        lib.grtb200_debug_trace_counters.argtypes = [vp, vp, i64, vp, vp, i32, f32, i32, i32, i32, vp, vp, vp, vp, vp]
         lib._grt_ready = True
     return lib
 
@@ -302,6 +304,19 @@ class GrtContext:
         out = np.zeros(6, np.float32)
         self._check(self._lib.grtb200_scene_aabb(self._h, out.ctypes.data), "grtb200_scene_aabb")
         return out
+
+    def set_replay(self, enable: bool):
+        """Record hit lists in the forward for the backward's replay (default on); off frees the cache (inference-only rendering)."""
+        self._check(self._lib.grtb200_set_replay(self._h, int(bool(enable))), "grtb200_set_replay")
+
+    TRACE_COUNTERS = ("rays", "queries", "node_visits", "box_tests", "proxy_tests", "candidate_hits", "accepted_hits", "packet_rays")
+
+    def trace_counters(self, stream, n, particles, sph, sph_degree, min_t, batch, height, width, rays_o, rays_d, r2w_host, visibility_scratch):
+        """Work counters of one forward trace (debug; synchronises): dict of ints."""
+        arr = (C.c_uint64 * 8)()
+        self._check(self._lib.grtb200_debug_trace_counters(self._h, stream, n, particles, sph, sph_degree, min_t, batch, height, width, rays_o, rays_d,
+                                                           r2w_host, visibility_scratch, arr), "grtb200_debug_trace_counters")
+        return dict(zip(self.TRACE_COUNTERS, [int(v) for v in arr]))
 
     def launch_count(self) -> int:
         return int(self._lib.grtb200_launch_count(self._h))

@@ -293,6 +293,14 @@ struct TraceParams {
     float* out_rgb; float* out_alpha; float* out_dist; float* out_hits; float* visibility;
     const float* d_rgb; const float* d_alpha; const float* d_dist;
     float* d_particles; float* d_sph;
+    unsigned long long* counters;  // debug work counters (grtb200_debug_trace_counters); only the COUNT instantiation touches them
+};
+
+// work counters of one forward trace (lane-level unless noted): 0 rays, 1 k-nearest queries, 2 node visits (one per warp and node in
+// packet mode -- the node record is fetched once for the warp -- else one per lane), 3 box tests (lanes that took part in a node visit),
+// 4 proxy tests, 5 candidate hits processed, 6 accepted hits, 7 rays walked as packets
+struct LaneCounters {
+    unsigned long long queries = 0, nodes = 0, boxes = 0, proxies = 0, cands = 0, hits = 0;
 };
 
 // one k-nearest query == one optixTrace of the reference: the 16 smallest t* in (tmin, tmax) in ascending order
@@ -349,16 +357,20 @@ __device__ __forceinline__ void proxy_visit(const LeafProxy* __restrict__ lp, fl
 }
 
 // all particles of leaf g for this lane's ray
+template <bool COUNT>
 __device__ __forceinline__ void leaf_visit(const TraceParams& P, uint32_t g, float ox, float oy, float oz, float dx, float dy, float dz,
-                                           float tmin, float tmax, float (&kt)[kK], uint32_t (&kid)[kK]) {
+                                           float tmin, float tmax, float (&kt)[kK], uint32_t (&kid)[kK], LaneCounters& cc) {
     const int first = static_cast<int>(g) * P.leaf, last = min(first + P.leaf, P.n);
+    if (COUNT) cc.proxies += static_cast<unsigned long long>(last - first);
 #pragma unroll 1
     for (int k = first; k < last; ++k) proxy_visit(P.proxies + k, ox, oy, oz, dx, dy, dz, tmin, tmax, kt, kid);
 }
 
-template <bool PACKET>
+template <bool PACKET, bool COUNT>
 __device__ __forceinline__ void knn_query(const TraceParams& P, bool want, float ox, float oy, float oz, float dx, float dy, float dz,
-                                          float idx_, float idy_, float idz_, float tmin, float tmax, float (&kt)[kK], uint32_t (&kid)[kK]) {
+                                          float idx_, float idy_, float idz_, float tmin, float tmax, float (&kt)[kK], uint32_t (&kid)[kK],
+                                          LaneCounters& cc) {
+    if (COUNT && want) cc.queries++;
 #pragma unroll
     for (int i = 0; i < kK; ++i) {
         kt[i] = kInf;
@@ -380,6 +392,15 @@ __device__ __forceinline__ void knn_query(const TraceParams& P, bool want, float
     stack[sp++] = 0;
     while (sp > 0) {
         const int ni = stack[--sp];
+        if (COUNT) {
+            if (PACKET) {
+                if ((threadIdx.x & 31) == 0) cc.nodes++;
+                if (want) cc.boxes++;
+            } else {
+                cc.nodes++;
+                cc.boxes++;
+            }
+        }
         const float4* np = reinterpret_cast<const float4*>(P.nodes + ni);
         const float4 b0 = __ldg(np), b1 = __ldg(np + 1), b2 = __ldg(np + 2), mt = __ldg(np + 3);
         const float bound = kt[kK - 1];  // kInf until 16 hits are held
@@ -420,8 +441,8 @@ __device__ __forceinline__ void knn_query(const TraceParams& P, bool want, float
             if (sp < kStack) stack[sp++] = lpush ? lc : rc;
         }
         // leaves are tested immediately, by the lanes whose ray reaches them
-        if ((lc < 0) && lhit) leaf_visit(P, static_cast<uint32_t>(~lc), ox, oy, oz, dx, dy, dz, tmin, tmax, kt, kid);
-        if ((rc < 0) && rhit) leaf_visit(P, static_cast<uint32_t>(~rc), ox, oy, oz, dx, dy, dz, tmin, tmax, kt, kid);
+        if ((lc < 0) && lhit) leaf_visit<COUNT>(P, static_cast<uint32_t>(~lc), ox, oy, oz, dx, dy, dz, tmin, tmax, kt, kid, cc);
+        if ((rc < 0) && rhit) leaf_visit<COUNT>(P, static_cast<uint32_t>(~rc), ox, oy, oz, dx, dy, dz, tmin, tmax, kt, kid, cc);
     }
 }
 
@@ -485,9 +506,10 @@ __device__ __forceinline__ void backward_hit(const TraceParams& P, uint32_t pid,
 
 // Per-ray work after the rays are set up.  PACKET: the warp's 32 rays traverse together (warp-uniform loops, every lane of the warp
 // must call this, `valid` marks the lanes that own a ray).
-template <int DEG, bool BWD, bool PACKET>
+template <int DEG, bool BWD, bool PACKET, bool COUNT>
 __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int64_t ray, float ox, float oy, float oz, float dx, float dy,
                                            float dz) {
+    LaneCounters cc;
     const float idx_ = 1.0f / dx, idy_ = 1.0f / dy, idz_ = 1.0f / dz;
     // inverse direction for the node slab tests: a zero component (axis-parallel ray) would make the FMA form plane * inf + (-o * inf) a
     // NaN and cull everything; 1e-20 keeps both products finite (|plane|, |o| << 1e18) and the slab interval (-huge, +huge) as it should be
@@ -510,7 +532,7 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
         while (true) {
             want = want && (last <= t1) && (T > P.min_transmittance);
             if (PACKET ? !__any_sync(0xFFFFFFFFu, want) : !want) break;
-            knn_query<PACKET>(P, want, ox, oy, oz, dx, dy, dz, tix, tiy, tiz, last + kEpsT, t1 + kEpsT, kt, kid);
+            knn_query<PACKET, COUNT>(P, want, ox, oy, oz, dx, dy, dz, tix, tiy, tiz, last + kEpsT, t1 + kEpsT, kt, kid, cc);
             if (kid[0] == kNone) want = false;
             if (!want) continue;
             float lt[kK];
@@ -525,6 +547,10 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
                 if ((pid == kNone) || !(T > P.min_transmittance)) continue;
                 const ParticleFrame f = load_frame(P.particles, pid);
                 const CanonicalHit h = canonical_hit<DEG>(f, ox, oy, oz, dx, dy, dz, P.min_response, P.min_alpha, P.max_alpha);
+                if (COUNT) {
+                    cc.cands++;
+                    cc.hits += h.accept ? 1 : 0;
+                }
                 if (h.accept) {
                     const float w = h.alpha * T;
                     const float4* c4 = reinterpret_cast<const float4*>(P.sph + static_cast<size_t>(pid) * 48);
@@ -554,6 +580,16 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
             }
             if (li[kK - 1] == kNone) want = false;  // fewer than 16 hits: the ray is exhausted, the reference's next trace would return nothing
         }
+        if (COUNT) {
+            unsigned long long v[8] = {valid ? 1ull : 0ull, cc.queries, cc.nodes, cc.boxes, cc.proxies, cc.cands, cc.hits, (PACKET && valid) ? 1ull : 0ull};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xFFFFFFFFu, v[k], o);
+                if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(&P.counters[k], v[k]);
+            }
+            return;  // the counting pass writes no image
+        }
         if (valid) {
             P.out_rgb[ray * 3] = Cx; P.out_rgb[ray * 3 + 1] = Cy; P.out_rgb[ray * 3 + 2] = Cz;
             P.out_alpha[ray] = 1.f - T;
@@ -576,7 +612,7 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
         while (true) {
             want = want && (start < end);
             if (PACKET ? !__any_sync(0xFFFFFFFFu, want) : !want) break;
-            knn_query<PACKET>(P, want, ox, oy, oz, dx, dy, dz, tix, tiy, tiz, start + kEpsT, end, kt, kid);
+            knn_query<PACKET, COUNT>(P, want, ox, oy, oz, dx, dy, dz, tix, tiy, tiz, start + kEpsT, end, kt, kid, cc);
             if (kid[0] == kNone) want = false;
             if (!want) continue;
             float lt[kK];
@@ -597,7 +633,7 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
     }
 }
 
-template <int DEG, bool BWD>
+template <int DEG, bool BWD, bool COUNT>
 __global__ void __launch_bounds__(128, kTraceBlocksPerSm) trace_kernel(TraceParams P) {
     // a warp covers an 8x4 pixel block of one image for traversal coherence
     const int bw = (P.width + 7) / 8, bh = (P.height + 3) / 4;
@@ -629,9 +665,9 @@ __global__ void __launch_bounds__(128, kTraceBlocksPerSm) trace_kernel(TracePara
     const bool near_first = (dot > 0.f) && (dot * dot > 0.99f * n1 * n0) && (sx * sx + sy * sy + sz * sz <= 4e-4f * (ex * ex + ey * ey + ez * ez));
     const bool coherent = P.packet && __all_sync(0xFFFFFFFFu, near_first);
     if (coherent) {
-        trace_rays<DEG, BWD, true>(P, valid, ray, ox, oy, oz, dx, dy, dz);
-    } else if (valid) {
-        trace_rays<DEG, BWD, false>(P, true, ray, ox, oy, oz, dx, dy, dz);
+        trace_rays<DEG, BWD, true, COUNT>(P, valid, ray, ox, oy, oz, dx, dy, dz);
+    } else if (COUNT || valid) {   // the counting pass ends in warp shuffles: every lane takes part
+        trace_rays<DEG, BWD, false, COUNT>(P, valid, ray, ox, oy, oz, dx, dy, dz);
     }
 }
 
@@ -693,6 +729,8 @@ struct grtb200_ctx {
     void *hit_list = nullptr, *hit_count = nullptr;
     size_t hit_list_bytes = 0, hit_count_bytes = 0;
     int hit_cap = 96, hit_cap_used = 0;
+    bool record_hits = true;          // grtb200_set_replay: inference-only callers switch the hit-list cache off
+    size_t hit_budget_bytes = size_t(1) << 30;  // cap of the hit-list cache: the per-ray capacity shrinks for large ray batches
     uint64_t build_generation = 0;
     struct { const float* rays_o; const float* rays_d; const float* particles; const float* out_rgb; const float* out_dist; int64_t rays; int64_t n; uint64_t generation; float r2w[12]; bool valid; int sph_degree; float min_transmittance; } fwd_key = {};
     float scene_host[6] = {0, 0, 0, 0, 0, 0};
@@ -779,9 +817,20 @@ void launch_trace(const grtb200_config& cfg, const TraceParams& P, cudaStream_t 
     const unsigned blocks = static_cast<unsigned>((warps * 32 + 127) / 128);
     if (blocks == 0) return;
     if (cfg.kernel_degree == 4)
-        trace_kernel<4, BWD><<<blocks, 128, 0, s>>>(P);
+        trace_kernel<4, BWD, false><<<blocks, 128, 0, s>>>(P);
     else
-        trace_kernel<2, BWD><<<blocks, 128, 0, s>>>(P);
+        trace_kernel<2, BWD, false><<<blocks, 128, 0, s>>>(P);
+}
+
+void launch_trace_count(const grtb200_config& cfg, const TraceParams& P, cudaStream_t s) {
+    const int bw = (P.width + 7) / 8, bh = (P.height + 3) / 4;
+    const int64_t warps = static_cast<int64_t>(bw) * bh * P.batch;
+    const unsigned blocks = static_cast<unsigned>((warps * 32 + 127) / 128);
+    if (blocks == 0) return;
+    if (cfg.kernel_degree == 4)
+        trace_kernel<4, false, true><<<blocks, 128, 0, s>>>(P);
+    else
+        trace_kernel<2, false, true><<<blocks, 128, 0, s>>>(P);
 }
 
 }  // namespace
@@ -947,9 +996,11 @@ int grtb200_trace(grtb200_ctx* c, void* stream, int64_t n, const float* particle
     if (n > 0) GRT_CUDA(c, cudaMemsetAsync(visibility, 0, static_cast<size_t>(n) * 4, s));
     // hit-list cache for the backward of this forward (grow-only; GRTB200_HITCAP=0 turns it off, the backward then re-traces)
     c->fwd_key.valid = false;
-    int cap = c->hit_cap;
+    int cap = c->record_hits ? c->hit_cap : 0;
     if (const char* e = std::getenv("GRTB200_HITCAP")) cap = std::max(0, std::min(1024, std::atoi(e)));
     const int64_t rays = static_cast<int64_t>(batch) * height * width;
+    if (cap > 0 && rays > 0)  // keep the cache inside its byte budget (1080p x 96 x 4 B would be 0.8 GB, 4K 3.2 GB); overflowed rays re-trace
+        cap = static_cast<int>(std::min<int64_t>(cap, std::max<int64_t>(8, static_cast<int64_t>(c->hit_budget_bytes / 4) / rays)));
     if (cap > 0 && rays > 0 && n > 0) {
         const size_t need = static_cast<size_t>(rays) * cap * 4, need_c = static_cast<size_t>(rays) * 4;
         if (need > c->hit_list_bytes) {
@@ -981,6 +1032,49 @@ int grtb200_trace(grtb200_ctx* c, void* stream, int64_t n, const float* particle
     launch_trace<false>(c->cfg, P, s);
     c->launches++;
     GRT_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+// Work counters of one forward trace (debug, synchronises; writes no image): counters8 = { rays, k-nearest queries, node visits (one per
+// warp and node for packet-walked rays, else one per lane), box tests, proxy tests, candidate hits processed, accepted hits, rays walked
+// as packets } -- the units of SURVEY.md 8d "3DGRT work units".
+int grtb200_debug_trace_counters(grtb200_ctx* c, void* stream, int64_t n, const float* particles, const float* sph, int32_t sph_degree,
+                                 float min_transmittance, int32_t batch, int32_t height, int32_t width, const float* rays_o, const float* rays_d,
+                                 const float* ray_to_world_host, float* visibility_scratch, uint64_t* counters8) {
+    if (!c || !counters8) return 1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    GRT_CUDA(c, cudaSetDevice(c->device));
+    TraceParams P;
+    if (int rc = fill_params(c, P, n, particles, sph, sph_degree, min_transmittance, batch, height, width, rays_o, rays_d, ray_to_world_host, s)) return rc;
+    P.visibility = visibility_scratch;
+    P.hit_list = nullptr;
+    P.hit_count = nullptr;
+    unsigned long long* d = nullptr;
+    GRT_CUDA(c, cudaMalloc(&d, 64));
+    cudaMemsetAsync(d, 0, 64, s);
+    P.counters = d;
+    launch_trace_count(c->cfg, P, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaMemcpy(counters8, d, 64, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    GRT_CUDA(c, e);
+    return 0;
+}
+
+// Switch the forward's hit-list recording (replayed by the backward) on / off: inference-only renders need no cache.  Turning it off frees it.
+int grtb200_set_replay(grtb200_ctx* c, int32_t enable) {
+    if (!c) return 1;
+    c->record_hits = enable != 0;
+    if (!c->record_hits) {
+        GRT_CUDA(c, cudaSetDevice(c->device));
+        c->fwd_key.valid = false;
+        if (c->hit_list) {
+            GRT_CUDA(c, cudaDeviceSynchronize());
+            cudaFree(c->hit_list);
+            c->hit_list = nullptr;
+            c->hit_list_bytes = 0;
+        }
+    }
     return 0;
 }
 

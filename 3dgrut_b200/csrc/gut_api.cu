@@ -162,7 +162,7 @@ struct gutb200_ctx {
     // per intersection: 64-bit (depth bits << 32 | particle) keys in per-tile slices, sorted particle indices, hit words
     DeviceBuffer keys64, vals_out, hit_words;
     // per tile: list-length histogram, slot counters, ranges, heaviest-first order, hit-word slice offsets; {I, overflow} on the device
-    DeviceBuffer tile_hist, tile_fill, ranges, tile_order, chunk_base, totals;
+    DeviceBuffer tile_hist, tile_fill, sub_base, ranges, tile_order, chunk_base, totals;
     cudaEvent_t ev_total = nullptr;
     gutb200_camera fwd_camera{};   // the camera of the forward whose context the backward replays
     // host staging for the *_host entry points
@@ -379,7 +379,7 @@ void gutb200_destroy(gutb200_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DeviceBuffer* bufs[] = {&c->tiles_count, &c->proj, &c->depth, &c->rgb, &c->grad_acc, &c->keys64, &c->vals_out, &c->hit_words, &c->tile_hist,
-                            &c->tile_fill, &c->ranges, &c->tile_order, &c->chunk_base, &c->totals, &c->h_particles, &c->h_sph,
+                            &c->tile_fill, &c->sub_base, &c->ranges, &c->tile_order, &c->chunk_base, &c->totals, &c->h_particles, &c->h_sph,
                             &c->h_rays_o, &c->h_rays_d, &c->h_rgba, &c->h_dist, &c->h_hits, &c->h_vis, &c->h_drgba, &c->h_ddist,
                             &c->h_dpart, &c->h_dsph};
     for (DeviceBuffer* b : bufs) b->release();
@@ -419,8 +419,9 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     GUT_CUDA(c, c->depth.reserve(nn * 4, s));
     GUT_CUDA(c, c->rgb.reserve(nn * 12, s));
     const size_t tt = static_cast<size_t>(tiles);
-    GUT_CUDA(c, c->tile_hist.reserve(tt * 4, s));
-    GUT_CUDA(c, c->tile_fill.reserve(tt * 4, s));
+    GUT_CUDA(c, c->tile_hist.reserve(tt * kTileSubs * 4, s));
+    GUT_CUDA(c, c->tile_fill.reserve(tt * kTileSubs * 4, s));
+    GUT_CUDA(c, c->sub_base.reserve(tt * kTileSubs * 4, s));
     GUT_CUDA(c, c->ranges.reserve(tt * 8, s));
     GUT_CUDA(c, c->tile_order.reserve(tt * 4, s));
     GUT_CUDA(c, c->chunk_base.reserve(tt * 4, s));
@@ -434,8 +435,8 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     auto bin_and_render = [&](uint32_t capacity) -> int {
         {
             StageTimer t(c, 1, s);
-            launch_tile_scan(s, static_cast<int>(tiles), c->tile_hist.as<uint32_t>(), capacity, c->ranges.as<uint32_t>(), c->chunk_base.as<uint32_t>(),
-                             c->tile_order.as<uint32_t>(), c->tile_fill.as<uint32_t>(), c->totals.as<uint32_t>());
+            launch_tile_scan(s, static_cast<int>(tiles), c->tile_hist.as<uint32_t>(), capacity, c->ranges.as<uint32_t>(), c->sub_base.as<uint32_t>(),
+                             c->chunk_base.as<uint32_t>(), c->tile_order.as<uint32_t>(), c->tile_fill.as<uint32_t>(), c->totals.as<uint32_t>());
         }
         GUT_CUDA(c, cudaMemcpyAsync(c->pinned_total, c->totals.ptr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         GUT_CUDA(c, cudaEventRecord(c->ev_total, s));
@@ -443,8 +444,9 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
         if (capacity > 0 && n > 0) {
             {
                 StageTimer t(c, 2, s);
-                launch_expand_place(s, c->cam, c->fcfg, n, c->proj.as<ProjRecord>(), c->depth.as<float>(), c->ranges.as<uint32_t>(),
-                                    c->totals.as<uint32_t>(), capacity, c->tile_fill.as<uint32_t>(), c->keys64.as<unsigned long long>());
+                launch_expand_place(s, c->cam, c->fcfg, n, c->proj.as<ProjRecord>(), c->depth.as<float>(), c->tile_hist.as<uint32_t>(),
+                                    c->sub_base.as<uint32_t>(), c->totals.as<uint32_t>(), capacity, c->tile_fill.as<uint32_t>(),
+                                    c->keys64.as<unsigned long long>());
             }
             {
                 StageTimer t(c, 3, s);
@@ -470,7 +472,7 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     };
 
     uint32_t total = 0;
-    GUT_CUDA(c, cudaMemsetAsync(c->tile_hist.ptr, 0, tt * 4, s));
+    GUT_CUDA(c, cudaMemsetAsync(c->tile_hist.ptr, 0, tt * kTileSubs * 4, s));
     if (n > 0) {
         StageTimer t(c, 0, s);
         launch_project(s, c->cam, c->fcfg, n, particles, sph, sph_degree, c->tiles_count.as<uint32_t>(), c->proj.as<ProjRecord>(),

@@ -25,12 +25,16 @@ namespace {
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
 // ----------------------------------------------------------------------------------------------------------
-// tile_scan: single CTA.  counts[T] -> ranges[T][2], chunk_base[T], order[T] (decreasing list length, bucketed by log2), fill[T] = 0,
-// totals[0] = I, totals[1] = 1 if I exceeds the capacity of the key buffers (the host re-launches the dependent kernels then)
+// tile_scan: single CTA.  Every tile owns kTileSubs sub-counters (a particle bumps sub-counter `particle & (kTileSubs - 1)`): the atomics
+// of a hot tile -- thousands of increments of one address serialise in the L2 -- spread over kTileSubs addresses, and the slots of a
+// tile's slice are claimed per sub-bucket the same way.  counts[T][kTileSubs] -> ranges[T][2] ((0, 0) for an empty tile, as the
+// reference's zero-filled range buffer reads), sub_base[T][kTileSubs] (first slot of each sub-bucket), chunk_base[T], order[T]
+// (decreasing list length, bucketed by log2), fill[T][kTileSubs] = 0, totals[0] = I, totals[1] = 1 if I exceeds the capacity of the key
+// buffers (empty ranges are published then and the host re-launches the dependent kernels after growing the buffers).
 __global__ void __launch_bounds__(1024) tile_scan_kernel(int num_tiles, const uint32_t* __restrict__ counts, uint32_t capacity,
-                                                         uint32_t* __restrict__ ranges, uint32_t* __restrict__ chunk_base,
-                                                         uint32_t* __restrict__ order, uint32_t* __restrict__ fill,
-                                                         uint32_t* __restrict__ totals) {
+                                                         uint32_t* __restrict__ ranges, uint32_t* __restrict__ sub_base,
+                                                         uint32_t* __restrict__ chunk_base, uint32_t* __restrict__ order,
+                                                         uint32_t* __restrict__ fill, uint32_t* __restrict__ totals) {
     __shared__ uint32_t hist[34];
     __shared__ uint32_t warp_a[32], warp_b[32];
     __shared__ uint32_t s_overflow;
@@ -39,9 +43,19 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int num_tiles, const ui
     // every thread owns a contiguous strip of tiles
     const int strip = (num_tiles + static_cast<int>(blockDim.x) - 1) / static_cast<int>(blockDim.x);
     const int t0 = min(static_cast<int>(threadIdx.x) * strip, num_tiles), t1 = min(t0 + strip, num_tiles);
+    auto tile_total = [&](int t) {
+        const uint4* c4 = reinterpret_cast<const uint4*>(counts + static_cast<size_t>(t) * kTileSubs);
+        uint32_t c = 0;
+#pragma unroll
+        for (int k = 0; k < kTileSubs / 4; ++k) {
+            const uint4 v = c4[k];
+            c += v.x + v.y + v.z + v.w;
+        }
+        return c;
+    };
     uint32_t sum_n = 0, sum_c = 0;
     for (int t = t0; t < t1; ++t) {
-        const uint32_t c = counts[t];
+        const uint32_t c = tile_total(t);
         sum_n += c;
         sum_c += (c + 31u) >> 5;
         atomicAdd(&hist[__clz(c) + 1], 1u);  // __clz(0) = 32 -> last bucket; long lists -> small bucket index
@@ -84,11 +98,19 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int num_tiles, const ui
     const bool overflow = s_overflow != 0u;  // the lists do not fit the key buffer: publish empty ranges, the host grows and re-queues
     uint32_t run_n = warp_a[warp] + inc_n - sum_n, run_c = warp_b[warp] + inc_c - sum_c;
     for (int t = t0; t < t1; ++t) {
-        const uint32_t c = counts[t];
-        ranges[t * 2] = overflow ? 0u : run_n;
-        ranges[t * 2 + 1] = overflow ? 0u : run_n + c;
+        uint32_t sub = run_n;
+        for (int k = 0; k < kTileSubs; ++k) {
+            const size_t at = static_cast<size_t>(t) * kTileSubs + k;
+            const uint32_t c = counts[at];
+            sub_base[at] = sub;
+            fill[at] = overflow ? 0xC0000000u : 0u;   // a huge fill level makes every claim fall outside its sub-bucket
+            sub += c;
+        }
+        const uint32_t c = sub - run_n;
+        const bool empty = overflow || (c == 0u);
+        ranges[t * 2] = empty ? 0u : run_n;
+        ranges[t * 2 + 1] = empty ? 0u : run_n + c;
         chunk_base[t] = overflow ? 0u : run_c;
-        fill[t] = 0u;
         run_n += c;
         run_c += (c + 31u) >> 5;
         order[atomicAdd(&hist[__clz(c) + 1], 1u)] = static_cast<uint32_t>(t);
@@ -108,20 +130,24 @@ __device__ __forceinline__ void compare_exchange(unsigned long long* s, uint32_t
 
 // all steps of the ascending bitonic network with block sizes k = k_first .. k_last on s[0 .. len) (len <= chunk, local indices);
 // `flip_first`: whether the first k starts with its flip step (false = only the disperse steps j < k_first / 2 ... of an outer merge)
+// (block sizes and strides are powers of two: all index arithmetic is shifts and masks)
 template <int THREADS>
 __device__ __forceinline__ void bitonic_local(unsigned long long* s, uint32_t len, uint32_t span, uint32_t k_first, uint32_t k_last, bool inner_only) {
     for (uint32_t k = k_first; k <= k_last; k <<= 1) {
+        const uint32_t lk = 31u - __clz(k);   // log2 k
         if (!inner_only) {
+            const uint32_t half_mask = (k >> 1) - 1u;
             for (uint32_t i = threadIdx.x; i < span / 2; i += THREADS) {  // flip: i-th element of a block's lower half <-> its mirror
-                const uint32_t blk = i / (k >> 1), off = i % (k >> 1);
-                const uint32_t lo = blk * k + off, hi = blk * k + (k - 1 - off);
+                const uint32_t blk = i >> (lk - 1u), off = i & half_mask;
+                const uint32_t lo = (blk << lk) + off, hi = (blk << lk) + (k - 1u - off);
                 if (hi < len) compare_exchange(s, lo, hi);
             }
             __syncthreads();
         }
         for (uint32_t j = inner_only ? (k >> 1) : (k >> 2); j >= 1; j >>= 1) {  // disperse
+            const uint32_t lj = 31u - __clz(j);
             for (uint32_t i = threadIdx.x; i < span / 2; i += THREADS) {
-                const uint32_t lo = (i / j) * (j << 1) + (i % j), hi = lo + j;
+                const uint32_t lo = ((i >> lj) << (lj + 1u)) + (i & (j - 1u)), hi = lo + j;
                 if (hi < len) compare_exchange(s, lo, hi);
             }
             __syncthreads();
@@ -160,15 +186,17 @@ __global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint32_t* __re
         __syncthreads();
     }
     for (uint32_t k = 2u * CHUNK; k <= n2; k <<= 1) {
+        const uint32_t lk = 31u - __clz(k), half_mask = (k >> 1) - 1u;
         for (uint32_t i = threadIdx.x; i < n2 / 2; i += THREADS) {  // flip over global memory
-            const uint32_t blk = i / (k >> 1), off = i % (k >> 1);
-            const uint32_t lo = blk * k + off, hi = blk * k + (k - 1 - off);
+            const uint32_t blk = i >> (lk - 1u), off = i & half_mask;
+            const uint32_t lo = (blk << lk) + off, hi = (blk << lk) + (k - 1u - off);
             if (hi < n) compare_exchange(g, lo, hi);
         }
         __syncthreads();
         for (uint32_t j = k >> 2; j >= CHUNK; j >>= 1) {  // disperse steps wider than a chunk
+            const uint32_t lj = 31u - __clz(j);
             for (uint32_t i = threadIdx.x; i < n2 / 2; i += THREADS) {
-                const uint32_t lo = (i / j) * (j << 1) + (i % j), hi = lo + j;
+                const uint32_t lo = ((i >> lj) << (lj + 1u)) + (i & (j - 1u)), hi = lo + j;
                 if (hi < n) compare_exchange(g, lo, hi);
             }
             __syncthreads();
@@ -198,9 +226,9 @@ constexpr int kSmallChunk = 2048, kLargeChunk = 8192, kSortThreads = 256;
 
 }  // namespace
 
-void launch_tile_scan(cudaStream_t s, int num_tiles, const uint32_t* counts, uint32_t capacity, uint32_t* ranges, uint32_t* chunk_base,
-                      uint32_t* order, uint32_t* fill, uint32_t* totals) {
-    tile_scan_kernel<<<1, 1024, 0, s>>>(num_tiles, counts, capacity, ranges, chunk_base, order, fill, totals);
+void launch_tile_scan(cudaStream_t s, int num_tiles, const uint32_t* counts, uint32_t capacity, uint32_t* ranges, uint32_t* sub_base,
+                      uint32_t* chunk_base, uint32_t* order, uint32_t* fill, uint32_t* totals) {
+    tile_scan_kernel<<<1, 1024, 0, s>>>(num_tiles, counts, capacity, ranges, sub_base, chunk_base, order, fill, totals);
 }
 
 cudaError_t launch_tile_sort(cudaStream_t s, int num_tiles, const uint32_t* order, const uint32_t* ranges, const uint32_t* totals,

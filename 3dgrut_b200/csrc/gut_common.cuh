@@ -57,10 +57,12 @@ void launch_project(cudaStream_t s, const FrameCamera& cam, const FrameConfig& c
                     const float* sph, int sph_degree, uint32_t* tiles_count, ProjRecord* proj, float* depth, float* rgb,
                     float* visibility, uint32_t* tile_hist);
 void launch_expand_place(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const ProjRecord* proj, const float* depth,
-                         const uint32_t* ranges, const uint32_t* totals, uint32_t capacity, uint32_t* fill, unsigned long long* keys);
+                         const uint32_t* tile_hist, const uint32_t* sub_base, const uint32_t* totals, uint32_t capacity, uint32_t* fill,
+                         unsigned long long* keys);
 // gut_binning.cu: tile ranges / order / hit-word slices from the per-tile histogram, per-tile on-chip sort of the 64-bit keys
-void launch_tile_scan(cudaStream_t s, int num_tiles, const uint32_t* counts, uint32_t capacity, uint32_t* ranges, uint32_t* chunk_base,
-                      uint32_t* order, uint32_t* fill, uint32_t* totals);
+constexpr int kTileSubs = 16;  // sub-counters per tile (a particle uses sub-counter `particle & 15`): spreads the atomics of hot tiles
+void launch_tile_scan(cudaStream_t s, int num_tiles, const uint32_t* counts, uint32_t capacity, uint32_t* ranges, uint32_t* sub_base,
+                      uint32_t* chunk_base, uint32_t* order, uint32_t* fill, uint32_t* totals);
 cudaError_t launch_tile_sort(cudaStream_t s, int num_tiles, const uint32_t* order, const uint32_t* ranges, const uint32_t* totals,
                              unsigned long long* keys, uint32_t* sorted_values);
 void launch_synth_tile_keys(cudaStream_t s, int num_tiles, const uint32_t* ranges, const uint32_t* vals, const float* depth, uint64_t* out);

@@ -423,14 +423,14 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
         if (!cfg.tile_culling) {
             ntiles = static_cast<uint32_t>(cells);
             for (int y = bb.y0; y < bb.y1; ++y)
-                for (int x = bb.x0; x < bb.x1; ++x) atomicAdd(&tile_hist[y * cam.grid_x + x], 1u);
+                for (int x = bb.x0; x < bb.x1; ++x) atomicAdd(&tile_hist[(y * cam.grid_x + x) * kTileSubs + (static_cast<int>(i) & (kTileSubs - 1))], 1u);
             cells = 0;
         } else if (cells <= kSmallBox) {
             for (int y = bb.y0; y < bb.y1; ++y)
                 for (int x = bb.x0; x < bb.x1; ++x)
                     if (tile_min_power(static_cast<float>(x), static_cast<float>(y), ca, cb, cc, pcx, pcy) < maxpow) {
                         ntiles++;
-                        atomicAdd(&tile_hist[y * cam.grid_x + x], 1u);  // per-tile list length (gut_binning.cu: tile_scan)
+                        atomicAdd(&tile_hist[(y * cam.grid_x + x) * kTileSubs + (static_cast<int>(i) & (kTileSubs - 1))], 1u);  // list length (tile_scan)
                     }
             cells = 0;
         }
@@ -445,6 +445,7 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
             const int bw = __shfl_sync(0xFFFFFFFFu, bb.x1, src) - bx0, nc = __shfl_sync(0xFFFFFFFFu, cells, src);
             const float qa = __shfl_sync(0xFFFFFFFFu, ca, src), qb = __shfl_sync(0xFFFFFFFFu, cb, src), qc = __shfl_sync(0xFFFFFFFFu, cc, src);
             const float qx = __shfl_sync(0xFFFFFFFFu, pcx, src), qy = __shfl_sync(0xFFFFFFFFu, pcy, src), qp = __shfl_sync(0xFFFFFFFFu, maxpow, src);
+            const int qsub = static_cast<int>(base + (threadIdx.x & ~31u) + src) & (kTileSubs - 1);  // sub-counter of the owning particle
             uint32_t total = 0;
             for (int c0 = 0; c0 < nc; c0 += 32) {
                 const int c = c0 + static_cast<int>(lane);
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
                 if (c < nc) {
                     const int y = by0 + c / bw, x = bx0 + c % bw;
                     pass = tile_min_power(static_cast<float>(x), static_cast<float>(y), qa, qb, qc, qx, qy) < qp;
-                    if (pass) atomicAdd(&tile_hist[y * cam.grid_x + x], 1u);
+                    if (pass) atomicAdd(&tile_hist[(y * cam.grid_x + x) * kTileSubs + qsub], 1u);
                 }
                 total += __popc(__ballot_sync(0xFFFFFFFFu, pass));
             }
@@ -487,9 +488,10 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(FrameCamera cam, 
 // claimed with one atomic on the tile's fill counter, as the key (depth bits << 32 | particle index); tile_sort (gut_binning.cu) then
 // orders each slice on chip.  The tile walk is the reference's (row-major, same culling arithmetic as project_kernel).
 __global__ void __launch_bounds__(256) expand_place_kernel(FrameCamera cam, FrameConfig cfg, int64_t n, const ProjRecord* __restrict__ proj,
-                                                           const float* __restrict__ depth, const uint32_t* __restrict__ ranges,
-                                                           const uint32_t* __restrict__ totals, uint32_t capacity,
-                                                           uint32_t* __restrict__ fill, unsigned long long* __restrict__ keys) {
+                                                           const float* __restrict__ depth, const uint32_t* __restrict__ tile_hist,
+                                                           const uint32_t* __restrict__ sub_base, const uint32_t* __restrict__ totals,
+                                                           uint32_t capacity, uint32_t* __restrict__ fill,
+                                                           unsigned long long* __restrict__ keys) {
     if (totals[1] != 0u) return;  // capacity exceeded: the host grows the key buffer and launches again
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const bool in_range = i < n;
@@ -501,10 +503,11 @@ __global__ void __launch_bounds__(256) expand_place_kernel(FrameCamera cam, Fram
     float maxpow = 0.f;
     int cells = 0;
     unsigned long long key = 0ull;
-    auto place = [&](int tile, unsigned long long k) {
-        const uint32_t slot = atomicAdd(&fill[tile], 1u);
-        const uint32_t begin = ranges[tile * 2], end = ranges[tile * 2 + 1];
-        if (begin + slot < end && begin + slot < capacity) keys[begin + slot] = k;
+    auto place = [&](int tile, unsigned long long k) {   // sub-bucket = low bits of the particle index (low word of the key)
+        const size_t at = static_cast<size_t>(tile) * kTileSubs + (static_cast<uint32_t>(k) & (kTileSubs - 1));
+        const uint32_t slot = atomicAdd(&fill[at], 1u);
+        const uint32_t pos = sub_base[at] + slot;
+        if (slot < tile_hist[at] && pos < capacity) keys[pos] = k;
     };
     if (active) {
         key = (static_cast<unsigned long long>(__float_as_uint(depth[i])) << 32) | static_cast<unsigned long long>(static_cast<uint32_t>(i));
@@ -593,10 +596,11 @@ void launch_project(cudaStream_t s, const FrameCamera& cam, const FrameConfig& c
 }
 
 void launch_expand_place(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const ProjRecord* proj, const float* depth,
-                         const uint32_t* ranges, const uint32_t* totals, uint32_t capacity, uint32_t* fill, unsigned long long* keys) {
+                         const uint32_t* tile_hist, const uint32_t* sub_base, const uint32_t* totals, uint32_t capacity, uint32_t* fill,
+                         unsigned long long* keys) {
     if (n <= 0) return;
     const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-    expand_place_kernel<<<blocks, 256, 0, s>>>(cam, cfg, n, proj, depth, ranges, totals, capacity, fill, keys);
+    expand_place_kernel<<<blocks, 256, 0, s>>>(cam, cfg, n, proj, depth, tile_hist, sub_base, totals, capacity, fill, keys);
 }
 
 void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint32_t* sorted_keys, uint32_t* ranges) {

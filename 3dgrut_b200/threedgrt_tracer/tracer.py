@@ -89,6 +89,26 @@ class OptixTracer:
                                  _ptr(ray_ori), _ptr(ray_dir), r2w.ctypes.data, _ptr(feat), _ptr(alpha), _ptr(hit), _ptr(hits), _ptr(vis))
         return feat, alpha, hit, nrm, hits, vis[:n]
 
+    def set_replay(self, enable, device):
+        """Measurement-free switch (no reference twin): record the forward's hit lists for the backward (grtb200_set_replay)."""
+        if getattr(self, "_replay", None) != bool(enable):
+            self._context(device).set_replay(bool(enable))
+            self._replay = bool(enable)
+
+    def trace_counters(self, ray_to_world, ray_ori, ray_dir, particle_density, particle_features, sph_degree, min_transmittance):
+        """Measurement helper (no reference twin): work counters of one forward trace -- rays, k-nearest queries, node visits, box / proxy
+        tests, candidate and accepted hits (grtb200_debug_trace_counters); writes no image."""
+        dev = ray_ori.device
+        b, h, w = (int(v) for v in ray_ori.shape[:3])
+        n = int(particle_density.shape[0])
+        particle_density, particle_features = particle_density.contiguous(), particle_features.contiguous()
+        ray_ori, ray_dir = ray_ori.contiguous(), ray_dir.contiguous()
+        vis = torch.empty((max(n, 1), 1), dtype=torch.float32, device=dev)
+        r2w = self._r2w(ray_to_world)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        return self._context(dev).trace_counters(stream, n, _ptr(particle_density), _ptr(particle_features), int(sph_degree), float(min_transmittance),
+                                                 b, h, w, _ptr(ray_ori), _ptr(ray_dir), r2w.ctypes.data, _ptr(vis))
+
     def trace_bwd(self, frame_id, ray_to_world, ray_ori, ray_dir, ray_features, ray_density, ray_hit_distance, ray_normals, particle_density,
                   particle_features, ray_features_grd, ray_density_grd, ray_hit_distance_grd, ray_normals_grd, render_opts, sph_degree,
                   min_transmittance):
@@ -179,6 +199,8 @@ class Tracer:
         if self._timings_on:
             start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             start.record()
+        # hit lists for the backward's replay are only worth recording when a backward can follow
+        self.tracer_wrapper.set_replay(bool(train) or torch.is_grad_enabled(), gpu_batch.rays_ori.device)
         pred_features, pred_opacity, pred_dist, pred_normals, hits_count, mog_visibility = Tracer._Autograd.apply(
             self.tracer_wrapper, frame_id, gpu_batch.T_to_world.contiguous(), gpu_batch.rays_ori.contiguous(), gpu_batch.rays_dir.contiguous(),
             gaussians.positions.contiguous(), gaussians.get_rotation().contiguous(), gaussians.get_scale().contiguous(),

@@ -479,9 +479,34 @@ def run_grt(args, rank, local_rank, world, dev, dist, sub=False):
         flush.fill_(float(s))
         step_device(n_warm + s, timed=True)
     value = world * n_steps / (total_ms / 1000.0)
+    stage_mean = {k: float(np.mean(v)) for k, v in stage.items()}
+    grt_work = None
+    if rank == 0:
+        try:  # SURVEY 8d "3DGRT work units": counted on the device for the last view (debug entry point, outside every timed region)
+            wc = ot.trace_counters(c2ws[view_of(n_warm + n_steps - 1)], rays_o, rays_d, particles, sph, sc.sph_degree, 0.001)
+            peak_hbm, peak_src = load_peaks()
+            rays_n = max(wc["rays"], 1)
+            t_tr, t_bw = stage_mean["trace"] * 1e-3, stage_mean["trace_bwd"] * 1e-3
+            fwd_bytes = wc["accepted_hits"] * 240 + wc["node_visits"] * 64 + 48 * rays_n
+            bwd_bytes = wc["accepted_hits"] * (240 + 44 + 192) + 64 * rays_n
+            grt_work = {"counters": wc, "rays_per_s_forward": rays_n / t_tr, "accepted_hits_per_s_forward": wc["accepted_hits"] / t_tr,
+                        "node_visits_per_ray": wc["node_visits"] / rays_n, "box_tests_per_ray": wc["box_tests"] / rays_n,
+                        "proxy_tests_per_ray": wc["proxy_tests"] / rays_n, "queries_per_ray": wc["queries"] / rays_n,
+                        "accepted_hits_per_ray": wc["accepted_hits"] / rays_n,
+                        "algorithmic_bytes": {"trace": fwd_bytes, "trace_bwd": bwd_bytes,
+                                              "model": "trace: hits x 240 B (record + SH) + node visits x 64 B (two child boxes per node record; one "
+                                                       "fetch per warp for packet-walked rays) + 48 B per ray; trace_bwd: hits x (240 + 44 + 192) B "
+                                                       "(re-read + gradient RMW) + 64 B per ray (SURVEY 8d)"},
+                        "achieved_gbs": {"trace": fwd_bytes / t_tr / 1e9, "trace_bwd": bwd_bytes / t_bw / 1e9},
+                        "hbm_frac": {"trace": fwd_bytes / t_tr / 1e9 / peak_hbm, "trace_bwd": bwd_bytes / t_bw / 1e9 / peak_hbm},
+                        "peak": peak_hbm, "peak_source": peak_src,
+                        "note": "the traversal is latency / issue bound, not HBM bound: the byte figure is the SURVEY's work model, "
+                                "reported beside rays/s, hits/s and node visits per ray"}
+        except Exception as e:  # noqa: BLE001
+            grt_work = {"unavailable": repr(e)}
     if sub:  # sub-record of the default c2 line: device-timed only
         return {"workload": sc.name + " via 3dgrt", "value": value, "unit": UNIT, "n_gpus": world, "steps": n_steps, "ms_per_step": total_ms / n_steps,
-                "stage_ms": {k: float(np.mean(v)) for k, v in stage.items()}, "gaussians": n, "rays": H * W,
+                "stage_ms": stage_mean, "gaussians": n, "rays": H * W, "work": grt_work,
                 "note": "BASELINE configs[3]: the C2 scene through the 3DGRT path (software LBVH); step = build_bvh + trace + trace_bwd"}
 
     # e2e through Tracer.build_acc + Tracer.render + loss.backward with the camera batch from pinned host memory
@@ -552,9 +577,11 @@ def run_grt(args, rank, local_rank, world, dev, dist, sub=False):
                     "api": "threedgrt_tracer.Tracer.build_acc + render + loss.backward",
                     "feed": "pinned host -> device on a copy stream, one step ahead; loss read back one step later"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": (grt_work or {}).get("achieved_gbs", {}).get(dom), "peak": peak, "unit": "GB/s",
+                         "frac": (grt_work or {}).get("hbm_frac", {}).get(dom), "traffic": None,
                          "peak_source": peak_src, "kernel_ms": stage_ms[dom],
-                         "note": "traversal is latency / L2 bound; hits and node visits are not counted yet, so no algorithmic-byte figure"},
+                         "note": "traversal is latency / issue bound; achieved = SURVEY 8d's work-unit bytes (see `work`) over the live kernel time"},
+            "work": grt_work,
             "stage_ms": stage_ms,
         }
         if not args.no_cpu_baseline:

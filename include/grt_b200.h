@@ -68,6 +68,17 @@ int grtb200_scene_aabb(grtb200_ctx* ctx, float* aabb6);
 
 int64_t grtb200_launch_count(const grtb200_ctx* ctx);
 
+/* The forward records each ray's accepted hits so that the backward replays them instead of re-tracing (ours; bounded to 1 GiB, the per-ray
+ * capacity shrinks for large ray batches).  enable = 0 switches the recording off and frees the cache: inference-only callers. */
+int grtb200_set_replay(grtb200_ctx* ctx, int32_t enable);
+
+/* Measurement helper (debug, synchronises, writes no image): work counters of one forward trace with the arguments of grtb200_trace.
+ * counters8 = { rays, k-nearest queries, node visits (one per warp and node for packet-walked rays, else per lane), box tests,
+ * proxy tests, candidate hits processed, accepted hits, rays walked as packets }; visibility_scratch: device [N] floats. */
+int grtb200_debug_trace_counters(grtb200_ctx* ctx, void* stream, int64_t n, const float* particles, const float* sph, int32_t sph_degree,
+                                 float min_transmittance, int32_t batch, int32_t height, int32_t width, const float* rays_o,
+                                 const float* rays_d, const float* ray_to_world_host, float* visibility_scratch, uint64_t* counters8);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,110 @@
+"""PSNR parity after identical training (BASELINE metric: "...; PSNR parity vs ref"; reference: validate.py:159-170, trainer.py:677-747).
+
+Two arms train the SAME perturbed C1 model on the SAME views, same order, same learning rates, same Adam:
+  * GPU arm  -- the product as the training loop uses it: GaussianTrainStep (activations -> 3DGUT forward -> L1 image gradient ->
+                trace_bwd_compact -> exchange -> fused Adam; 3dgrut_b200/train_step.py),
+  * CPU arm  -- the oracle driving the same optimizer: numpy activations -> oracle forward (oracle/gut_oracle.c) -> the same L1 gradient ->
+                oracle backward -> the optimizer oracle (oracle/adam_oracle.py: activation chain rule + torch.optim.Adam's update,
+                pinned against torch on the CPU).
+The target images are rendered once by the oracle from the unperturbed model.  Every 50 steps each arm renders all views WITH ITS OWN
+renderer and PSNR = -10 log10(mean squared error) over all views is recorded (validate.py's definition on images in [0, 1]).
+Bar: the two PSNR trajectories stay within +-0.05 dB at every checkpoint, and both improve by several dB."""
+import numpy as np
+import pytest
+
+import scenes
+from helpers import tracer_pose
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+STEPS, EVERY, N_VIEWS = 300, 50, 6
+LRS = dict(positions=1e-3, density=0.02, rotation=1e-3, scale=3e-3, features_albedo=5e-3, features_specular=2.5e-4)
+
+
+def _raw_from(particles, sph):
+    dns = np.clip(particles[:, 3:4], 1e-4, 1 - 1e-4)
+    return {"positions": particles[:, 0:3].copy(), "density": np.log(dns / (1 - dns)).astype(np.float32), "rotation": particles[:, 4:8].copy(),
+            "scale": np.log(particles[:, 8:11]).astype(np.float32), "features_albedo": sph[:, 0:3].copy(), "features_specular": sph[:, 3:48].copy()}
+
+
+def _activate(raw):
+    """model.py:94-118 in numpy float32: [N,12] particles + [N,48] SH"""
+    f32 = np.float32
+    q = raw["rotation"] / np.maximum(np.sqrt((raw["rotation"] ** 2).sum(1, keepdims=True, dtype=f32)), f32(1e-12))
+    particles = np.concatenate([raw["positions"], (f32(1) / (f32(1) + np.exp(-raw["density"]))).astype(f32), q.astype(f32),
+                                np.exp(raw["scale"]).astype(f32), np.zeros_like(raw["density"])], axis=1).astype(f32)
+    sph = np.concatenate([raw["features_albedo"], raw["features_specular"]], axis=1).astype(f32)
+    return np.ascontiguousarray(particles), np.ascontiguousarray(sph)
+
+
+def _psnr(images, targets):
+    mse = float(np.mean([np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2) for a, b in zip(images, targets)]))
+    return -10.0 * np.log10(max(mse, 1e-30))
+
+
+def test_psnr_trajectories_match_the_oracle_driven_training():
+    import train_step
+    from oracle import adam_oracle as ao
+    from oracle import gut_oracle as go
+    from threedgut_tracer.tracer import ShutterType, fromOpenCVPinholeCameraModelParameters
+
+    dev = torch.device("cuda", 0)
+    sc = scenes.scene_c1(n=600, width=96, height=96)
+    W, H, deg = sc.width, sc.height, sc.sph_degree
+    ro, rd = sc.rays()
+    poses = [tracer_pose(sc.camera(i, N_VIEWS)) for i in range(N_VIEWS)]
+    cfg = go.default_config()
+    cams = [go.make_camera(W, H, sc.fx, sc.fy, sc.cx, sc.cy, p) for p in poses]
+
+    def oracle_render(particles, sph, cam):
+        pr, bn, rgba, dist, hits = go.forward_all(cfg, cam, ro, rd, particles, sph, deg)
+        return pr, bn, rgba, dist
+
+    targets = [np.clip(oracle_render(sc.particles, sc.sph, cam)[2][..., :3], 0.0, None).astype(np.float32) for cam in cams]
+
+    rng = np.random.default_rng(0)
+    P2, S2 = sc.particles.copy(), sc.sph.copy()
+    P2[:, 0:3] += (0.02 * rng.normal(size=(sc.n, 3))).astype(np.float32)
+    P2[:, 8:11] *= np.exp(0.2 * rng.normal(size=(sc.n, 3))).astype(np.float32)
+    S2[:, 0:3] += (0.5 * rng.normal(size=(sc.n, 3))).astype(np.float32)
+    raw0 = _raw_from(P2, S2)
+
+    # ---- GPU arm
+    sensor = fromOpenCVPinholeCameraModelParameters(np.array([W, H]), ShutterType.GLOBAL, np.array([sc.cx, sc.cy], np.float32),
+                                                    np.array([sc.fx, sc.fy], np.float32), np.zeros(6, np.float32), np.zeros(2, np.float32),
+                                                    np.zeros(4, np.float32))
+    rays_o, rays_d = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    fit = train_step.GaussianTrainStep({k: torch.from_numpy(v.copy()).to(dev) for k, v in raw0.items()}, LRS, sph_degree=deg)
+    t_targets = [torch.from_numpy(t).to(dev) for t in targets]
+
+    def gpu_psnr():
+        return _psnr([fit.render(rays_o, rays_d, sensor, p)[0][..., :3].cpu().numpy() for p in poses], targets)
+
+    # ---- CPU arm
+    raw = {k: v.copy() for k, v in raw0.items()}
+    m = {k: np.zeros_like(v) for k, v in raw.items()}
+    v_ = {k: np.zeros_like(v) for k, v in raw.items()}
+
+    def cpu_psnr():
+        particles, sph = _activate(raw)
+        return _psnr([oracle_render(particles, sph, cam)[2][..., :3] for cam in cams], targets)
+
+    traj = [(0, gpu_psnr(), cpu_psnr())]
+    for it in range(STEPS):
+        k = it % N_VIEWS
+        fit.step(rays_o, rays_d, sensor, poses[k], t_targets[k])
+        particles, sph = _activate(raw)
+        pr, bn, rgba, dist = oracle_render(particles, sph, cams[k])
+        diff = rgba[..., :3] - targets[k]
+        d_rgba = np.zeros_like(rgba)
+        d_rgba[..., :3] = (np.sign(diff) / np.float32(diff.size)).astype(np.float32)   # d mean|.| / d rgb, as train_step.step (world = 1)
+        dp, ds = go.render_backward(cfg, cams[k], ro, rd, particles, sph, deg, pr, bn, rgba, dist, d_rgba, np.zeros_like(dist))
+        raw, m, v_ = ao.gaussian_adam_step(raw, m, v_, LRS, dp, ds, eps=1e-15, step=it + 1)
+        if (it + 1) % EVERY == 0:
+            traj.append((it + 1, gpu_psnr(), cpu_psnr()))
+    for step, a, b in traj:
+        print(f"[psnr] step {step:3d}: GPU arm {a:.3f} dB   oracle-driven CPU arm {b:.3f} dB   diff {a - b:+.4f} dB")
+    assert traj[-1][1] > traj[0][1] + 3.0 and traj[-1][2] > traj[0][2] + 3.0, "both arms must actually train"
+    worst = max(abs(a - b) for _, a, b in traj)
+    assert worst <= 0.05, f"PSNR trajectories differ by {worst:.4f} dB"

@@ -126,3 +126,44 @@ def test_compact_exchange_matches_serial_sum(tmp_path):
         assert np.allclose(o["dp"], dp_sum, rtol=1e-6, atol=1e-7)
         assert np.allclose(o["ds"], ds_sum, rtol=2e-5, atol=1e-6 * float(np.abs(ds_sum).max()))
     assert np.array_equal(outs[0]["ds"], outs[1]["ds"])  # replicas stay bit-identical
+
+
+def _accumulate_worker(rank, world, port, out_dir):
+    import view_parallel as vp
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = scenes.scene_c1(n=60, width=32, height=32)
+    V = 2
+    mine = vp.views_for_rank(step=1, rank=rank, world=world, num_views=10, views_per_rank=V)
+    ex = vp.CompactGradientExchange(_OracleRaster(), sc.n, torch.device("cpu"), views_per_rank=V)
+    for slot, view in enumerate(mine):
+        ref = oracle_frame(sc, sc.camera(view, 10), seed=view)
+        d_particles, g = ex.out(slot)
+        d_particles.copy_(torch.from_numpy(ref["dp"]))
+        g[:, 0:3] = torch.from_numpy(ref["ds"][:, 0:3] / 0.28209479177387814)
+        g[:, 3] = 0
+        ex.submit(slot)  # accumulates, starts this view's all-gather without waiting
+    # slot-major, rank-minor: the order the gathered [V, world, N, 4] buffer is laid out in
+    order = [vp.views_for_rank(1, r, world, 10, V)[j] for j in range(V) for r in range(world)]
+    positions = np.stack([np.asarray(sc.camera(v, 10), np.float32)[:3, 3] for v in order])
+    dp, ds = ex.finish(sc.sph_degree, torch.from_numpy(sc.particles), positions)
+    np.savez(os.path.join(out_dir, f"acc{rank}.npz"), views=np.array(order), dp=dp.numpy(), ds=ds.numpy())
+    dist.destroy_process_group()
+
+
+def test_accumulated_exchange_over_two_views_per_rank(tmp_path):
+    """views_per_rank = 2: per-view asynchronous all-gathers + ONE all-reduce of the accumulated [N,12] + rebuild over all 4 views
+    == the serial sum of the four per-view oracle gradients, bit-identical on both ranks."""
+    world = 2
+    mp.spawn(_accumulate_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outs = [np.load(tmp_path / f"acc{r}.npz") for r in range(world)]
+    views = [int(v) for v in outs[0]["views"]]
+    assert len(set(views)) == 4
+    sc = scenes.scene_c1(n=60, width=32, height=32)
+    refs = [oracle_frame(sc, sc.camera(v, 10), seed=v) for v in views]
+    dp_sum, ds_sum = sum(r["dp"] for r in refs), sum(r["ds"] for r in refs)
+    for o in outs:
+        assert np.allclose(o["dp"], dp_sum, rtol=1e-5, atol=1e-6)
+        assert np.allclose(o["ds"], ds_sum, rtol=2e-5, atol=1e-6 * float(np.abs(ds_sum).max()))
+    assert np.array_equal(outs[0]["ds"], outs[1]["ds"]) and np.array_equal(outs[0]["dp"], outs[1]["dp"])
