@@ -319,7 +319,9 @@ def test_empty_and_offscreen_inputs():
 
 
 def test_per_pixel_ray_origins_take_the_general_path():
-    """Rays whose origins differ inside a tile must not use the common-origin fast path (render kernels pick it per tile)."""
+    """Rays whose origins differ inside a tile must not use the common-origin fast path (render kernels pick it per tile).  Three bands of
+    tiles: the frame's first-ray origin (forward UNIFORM, backward FAST: canonical sums relative to that origin), ANOTHER origin common to
+    the tile (forward UNIFORM with exact hit words, backward GENERAL with the origin-offset correction terms), per-pixel jitter (both general)."""
     import b200_native as nat
     from oracle import gut_oracle as go
 
@@ -329,7 +331,9 @@ def test_per_pixel_ray_origins_take_the_general_path():
     ro, rd = sc.rays()
     rng = np.random.default_rng(3)
     ro = (ro + 0.02 * rng.normal(size=ro.shape)).astype(np.float32)
-    ro[:, :64] = ro[0, 0, 0]  # left half: common origin per tile; right half: jittered
+    ro[:, :32] = ro[0, 0, 0]                                              # tiles 0-1: the frame origin
+    ro[:, 32:64] = ro[0, 0, 0] + np.array([0.03, -0.02, 0.05], np.float32)  # tiles 2-3: common to the tile, different from the frame's
+    # columns 64..: per-pixel jitter
     cfg = go.default_config()
     ocam = go.make_camera(sc.width, sc.height, sc.fx, sc.fy, sc.cx, sc.cy, pose)
     pr, bn, rgba_ref, dist_ref, hits_ref = go.forward_all(cfg, ocam, ro, rd, sc.particles, sc.sph, 3)
