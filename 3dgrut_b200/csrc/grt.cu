@@ -369,7 +369,7 @@ __device__ __forceinline__ void leaf_visit(const TraceParams& P, uint32_t g, flo
 template <bool PACKET, bool COUNT>
 __device__ __forceinline__ void knn_query(const TraceParams& P, bool want, float ox, float oy, float oz, float dx, float dy, float dz,
                                           float idx_, float idy_, float idz_, float tmin, float tmax, float (&kt)[kK], uint32_t (&kid)[kK],
-                                          LaneCounters& cc) {
+                                          LaneCounters& cc, int* __restrict__ warp_stack) {
     if (COUNT && want) cc.queries++;
 #pragma unroll
     for (int i = 0; i < kK; ++i) {
@@ -387,7 +387,10 @@ __device__ __forceinline__ void knn_query(const TraceParams& P, bool want, float
     // empty with the right sign, and |-o/d| ~ 1e20 there would inflate the slack until the other axes' tests never reject
     const float slack = 4e-7f * ((fabsf(idx_) < 1e19f ? fabsf(nox) : 0.f) + (fabsf(idy_) < 1e19f ? fabsf(noy) : 0.f) +
                                  (fabsf(idz_) < 1e19f ? fabsf(noz) : 0.f)) + 1e-30f;
-    int stack[kStack];
+    // a packet has ONE traversal stack (warp-uniform control flow): it lives in shared memory, every lane stores the same value to the
+    // same word and reads back what it stored; per-thread walks keep a private stack
+    int local_stack[PACKET ? 1 : kStack];
+    int* stack = PACKET ? warp_stack : local_stack;
     int sp = 0;
     stack[sp++] = 0;
     while (sp > 0) {
@@ -508,7 +511,7 @@ __device__ __forceinline__ void backward_hit(const TraceParams& P, uint32_t pid,
 // must call this, `valid` marks the lanes that own a ray).
 template <int DEG, bool BWD, bool PACKET, bool COUNT>
 __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int64_t ray, float ox, float oy, float oz, float dx, float dy,
-                                           float dz) {
+                                           float dz, int* __restrict__ warp_stack) {
     LaneCounters cc;
     const float idx_ = 1.0f / dx, idy_ = 1.0f / dy, idz_ = 1.0f / dz;
     // inverse direction for the node slab tests: a zero component (axis-parallel ray) would make the FMA form plane * inf + (-o * inf) a
@@ -532,7 +535,7 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
         while (true) {
             want = want && (last <= t1) && (T > P.min_transmittance);
             if (PACKET ? !__any_sync(0xFFFFFFFFu, want) : !want) break;
-            knn_query<PACKET, COUNT>(P, want, ox, oy, oz, dx, dy, dz, tix, tiy, tiz, last + kEpsT, t1 + kEpsT, kt, kid, cc);
+            knn_query<PACKET, COUNT>(P, want, ox, oy, oz, dx, dy, dz, tix, tiy, tiz, last + kEpsT, t1 + kEpsT, kt, kid, cc, warp_stack);
             if (kid[0] == kNone) want = false;
             if (!want) continue;
             float lt[kK];
@@ -612,7 +615,7 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
         while (true) {
             want = want && (start < end);
             if (PACKET ? !__any_sync(0xFFFFFFFFu, want) : !want) break;
-            knn_query<PACKET, COUNT>(P, want, ox, oy, oz, dx, dy, dz, tix, tiy, tiz, start + kEpsT, end, kt, kid, cc);
+            knn_query<PACKET, COUNT>(P, want, ox, oy, oz, dx, dy, dz, tix, tiy, tiz, start + kEpsT, end, kt, kid, cc, warp_stack);
             if (kid[0] == kNone) want = false;
             if (!want) continue;
             float lt[kK];
@@ -636,6 +639,7 @@ __device__ __forceinline__ void trace_rays(const TraceParams& P, bool valid, int
 template <int DEG, bool BWD, bool COUNT>
 __global__ void __launch_bounds__(128, kTraceBlocksPerSm) trace_kernel(TraceParams P) {
     // a warp covers an 8x4 pixel block of one image for traversal coherence
+    __shared__ int s_stack[4][kStack];  // one traversal stack per warp (packet walks)
     const int bw = (P.width + 7) / 8, bh = (P.height + 3) / 4;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int per_image = bw * bh;
@@ -644,6 +648,7 @@ __global__ void __launch_bounds__(128, kTraceBlocksPerSm) trace_kernel(TracePara
     const int px = (blk % bw) * 8 + (lane & 7), py = (blk / bw) * 4 + (lane >> 3);
     const bool valid = (px < P.width) && (py < P.height);
     const int64_t ray = (static_cast<int64_t>(img) * P.height + min(py, P.height - 1)) * P.width + min(px, P.width - 1);
+    int* warp_stack = s_stack[threadIdx.x >> 5];
 
     const float rox = P.rays_o[ray * 3], roy = P.rays_o[ray * 3 + 1], roz = P.rays_o[ray * 3 + 2];
     const float rdx = P.rays_d[ray * 3], rdy = P.rays_d[ray * 3 + 1], rdz = P.rays_d[ray * 3 + 2];
@@ -665,9 +670,9 @@ __global__ void __launch_bounds__(128, kTraceBlocksPerSm) trace_kernel(TracePara
     const bool near_first = (dot > 0.f) && (dot * dot > 0.99f * n1 * n0) && (sx * sx + sy * sy + sz * sz <= 4e-4f * (ex * ex + ey * ey + ez * ez));
     const bool coherent = P.packet && __all_sync(0xFFFFFFFFu, near_first);
     if (coherent) {
-        trace_rays<DEG, BWD, true, COUNT>(P, valid, ray, ox, oy, oz, dx, dy, dz);
+        trace_rays<DEG, BWD, true, COUNT>(P, valid, ray, ox, oy, oz, dx, dy, dz, warp_stack);
     } else if (COUNT || valid) {   // the counting pass ends in warp shuffles: every lane takes part
-        trace_rays<DEG, BWD, false, COUNT>(P, valid, ray, ox, oy, oz, dx, dy, dz);
+        trace_rays<DEG, BWD, false, COUNT>(P, valid, ray, ox, oy, oz, dx, dy, dz, warp_stack);
     }
 }
 
