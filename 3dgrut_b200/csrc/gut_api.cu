@@ -160,7 +160,7 @@ struct gutb200_ctx {
     // forward context (reused by backward): per particle
     DeviceBuffer tiles_count, proj, depth, rgb, grad_acc;
     // per intersection: 64-bit (depth bits << 32 | particle) keys in per-tile slices, sorted particle indices, hit words
-    DeviceBuffer keys64, vals_out, hit_words;
+    DeviceBuffer keys64, keys64_alt, vals_out, hit_words;
     // per tile: list-length histogram, slot counters, ranges, heaviest-first order, hit-word slice offsets; {I, overflow} on the device
     DeviceBuffer tile_hist, tile_fill, sub_base, ranges, tile_order, chunk_base, totals;
     cudaEvent_t ev_total = nullptr;
@@ -378,7 +378,7 @@ void gutb200_destroy(gutb200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DeviceBuffer* bufs[] = {&c->tiles_count, &c->proj, &c->depth, &c->rgb, &c->grad_acc, &c->keys64, &c->vals_out, &c->hit_words, &c->tile_hist,
+    DeviceBuffer* bufs[] = {&c->tiles_count, &c->proj, &c->depth, &c->rgb, &c->grad_acc, &c->keys64, &c->keys64_alt, &c->vals_out, &c->hit_words, &c->tile_hist,
                             &c->tile_fill, &c->sub_base, &c->ranges, &c->tile_order, &c->chunk_base, &c->totals, &c->h_particles, &c->h_sph,
                             &c->h_rays_o, &c->h_rays_d, &c->h_rgba, &c->h_dist, &c->h_hits, &c->h_vis, &c->h_drgba, &c->h_ddist,
                             &c->h_dpart, &c->h_dsph};
@@ -451,9 +451,9 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
             {
                 StageTimer t(c, 3, s);
                 GUT_CUDA(c, launch_tile_sort(s, static_cast<int>(tiles), c->tile_order.as<uint32_t>(), c->ranges.as<uint32_t>(), c->totals.as<uint32_t>(),
-                                             c->keys64.as<unsigned long long>(), c->vals_out.as<uint32_t>()));
+                                             c->keys64.as<unsigned long long>(), c->keys64_alt.as<unsigned long long>(), c->vals_out.as<uint32_t>()));
             }
-            c->launches += 3;
+            c->launches += 2;
         }
         {
             StageTimer t(c, 5, s);
@@ -481,7 +481,7 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     }
     GUT_CUDA(c, c->vals_out.reserve(16, s));
     GUT_CUDA(c, c->hit_words.reserve(hit_words_capacity(0, tiles) * 4, s));
-    uint32_t capacity = static_cast<uint32_t>(std::min<size_t>(c->keys64.bytes / 8, 0xFFFFFFF0u));
+    uint32_t capacity = static_cast<uint32_t>(std::min<size_t>(std::min(c->keys64.bytes, c->keys64_alt.bytes) / 8, 0xFFFFFFF0u));
     // the three per-intersection buffers grow together; `capacity` is the smallest of them in entries
     capacity = static_cast<uint32_t>(std::min<size_t>(capacity, c->vals_out.bytes / 4));
     while (capacity > 0 && hit_words_capacity(capacity, tiles) * 4 > c->hit_words.bytes) capacity = capacity > 4096 ? capacity - 4096 : 0;
@@ -490,6 +490,7 @@ int gutb200_forward(gutb200_ctx* c, void* stream, const gutb200_camera* cam, int
     total = c->pinned_total[0];
     if (c->pinned_total[1] != 0u) {  // did not fit: grow (grow-only, 12.5 % head-room) and queue the tail of the frame again
         GUT_CUDA(c, c->keys64.reserve(static_cast<size_t>(total) * 8, s));
+        GUT_CUDA(c, c->keys64_alt.reserve(static_cast<size_t>(total) * 8, s));
         GUT_CUDA(c, c->vals_out.reserve(static_cast<size_t>(total) * 4 + 16, s));
         GUT_CUDA(c, c->hit_words.reserve(hit_words_capacity(total + (total >> 3) + 64, tiles) * 4, s));
         capacity = total;

@@ -10,9 +10,9 @@
 //                  heaviest-first tile order, total I and the capacity check on the device
 //   expand_place   every (particle, tile) pair is dropped into its tile's slice at an atomically claimed slot as the 64-bit key
 //                  (depth bits << 32 | particle index)                                      (gut_project.cu)
-//   tile_sort      one CTA per tile sorts its slice by that key -- a bitonic network in shared memory, all comparators ascending
-//                  ("flip" + "disperse" steps), so the slots beyond the list length act as +infinity without being stored; lists
-//                  longer than the shared-memory chunk run the outer steps of the same network through global memory
+//   tile_sort      one CTA per tile sorts its slice by that key: a stable LSD radix sort over the depth bits (8 bits a pass, passes
+//                  with a single digit skipped, slice ping-ponged through the L2) + a fix-up of equal-depth runs by particle index
+//                  (a first version used a bitonic network: 125 M compare-exchanges at C2 cost 0.13 ms, 2.0 ms at C3 -- replaced)
 // The keys are unique inside a tile (a particle enters a tile once), so the result is exactly the reference's order whatever order
 // the atomics claimed the slots in; only sorted artefacts are observable and they stay bit-identical (tests/test_gut_parity_gpu.py).
 // Work: I x 8 B written once, sorted in place on chip; no N-sized depth sort, no scan over N, no multi-pass radix sort over I.
@@ -35,27 +35,20 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int num_tiles, const ui
                                                          uint32_t* __restrict__ ranges, uint32_t* __restrict__ sub_base,
                                                          uint32_t* __restrict__ chunk_base, uint32_t* __restrict__ order,
                                                          uint32_t* __restrict__ fill, uint32_t* __restrict__ totals) {
+    static_assert(kTileSubs == 16, "a half-warp scans one tile's sub-counters");
     __shared__ uint32_t hist[34];
     __shared__ uint32_t warp_a[32], warp_b[32];
     __shared__ uint32_t s_overflow;
     if (threadIdx.x < 34) hist[threadIdx.x] = 0;
     __syncthreads();
-    // every thread owns a contiguous strip of tiles
+    // pass 1: tile totals.  Every thread owns a contiguous strip of tiles; the 16 counters of a tile are four 16-byte loads
     const int strip = (num_tiles + static_cast<int>(blockDim.x) - 1) / static_cast<int>(blockDim.x);
     const int t0 = min(static_cast<int>(threadIdx.x) * strip, num_tiles), t1 = min(t0 + strip, num_tiles);
-    auto tile_total = [&](int t) {
-        const uint4* c4 = reinterpret_cast<const uint4*>(counts + static_cast<size_t>(t) * kTileSubs);
-        uint32_t c = 0;
-#pragma unroll
-        for (int k = 0; k < kTileSubs / 4; ++k) {
-            const uint4 v = c4[k];
-            c += v.x + v.y + v.z + v.w;
-        }
-        return c;
-    };
     uint32_t sum_n = 0, sum_c = 0;
     for (int t = t0; t < t1; ++t) {
-        const uint32_t c = tile_total(t);
+        const uint4* c4 = reinterpret_cast<const uint4*>(counts + static_cast<size_t>(t) * kTileSubs);
+        const uint4 v0 = c4[0], v1 = c4[1], v2 = c4[2], v3 = c4[3];
+        const uint32_t c = (v0.x + v0.y + v0.z + v0.w) + (v1.x + v1.y + v1.z + v1.w) + (v2.x + v2.y + v2.z + v2.w) + (v3.x + v3.y + v3.z + v3.w);
         sum_n += c;
         sum_c += (c + 31u) >> 5;
         atomicAdd(&hist[__clz(c) + 1], 1u);  // __clz(0) = 32 -> last bucket; long lists -> small bucket index
@@ -96,121 +89,148 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int num_tiles, const ui
     }
     __syncthreads();
     const bool overflow = s_overflow != 0u;  // the lists do not fit the key buffer: publish empty ranges, the host grows and re-queues
+    // pass 2: per-tile outputs (begin written unconditionally into ranges[2t]; pass 3 reads it back)
     uint32_t run_n = warp_a[warp] + inc_n - sum_n, run_c = warp_b[warp] + inc_c - sum_c;
     for (int t = t0; t < t1; ++t) {
-        uint32_t sub = run_n;
-        for (int k = 0; k < kTileSubs; ++k) {
-            const size_t at = static_cast<size_t>(t) * kTileSubs + k;
-            const uint32_t c = counts[at];
-            sub_base[at] = sub;
-            fill[at] = overflow ? 0xC0000000u : 0u;   // a huge fill level makes every claim fall outside its sub-bucket
-            sub += c;
-        }
-        const uint32_t c = sub - run_n;
-        const bool empty = overflow || (c == 0u);
-        ranges[t * 2] = empty ? 0u : run_n;
-        ranges[t * 2 + 1] = empty ? 0u : run_n + c;
+        const uint4* c4 = reinterpret_cast<const uint4*>(counts + static_cast<size_t>(t) * kTileSubs);
+        const uint4 v0 = c4[0], v1 = c4[1], v2 = c4[2], v3 = c4[3];
+        const uint32_t c = (v0.x + v0.y + v0.z + v0.w) + (v1.x + v1.y + v1.z + v1.w) + (v2.x + v2.y + v2.z + v2.w) + (v3.x + v3.y + v3.z + v3.w);
+        ranges[t * 2] = run_n;   // provisional: the tile's first slot even if it is empty (pass 3 needs it)
+        ranges[t * 2 + 1] = run_n + c;
         chunk_base[t] = overflow ? 0u : run_c;
         run_n += c;
         run_c += (c + 31u) >> 5;
         order[atomicAdd(&hist[__clz(c) + 1], 1u)] = static_cast<uint32_t>(t);
     }
+    __syncthreads();
+    // pass 3: first slot of every sub-bucket, coalesced: a half-warp owns one tile, 16 lanes = its 16 sub-counters (the loop is
+    // warp-uniform: both halves of a warp run the same number of iterations, the shuffles name every lane)
+    const int sub = threadIdx.x & 15;
+    for (int tb = (threadIdx.x >> 5) * 2; tb < num_tiles; tb += (static_cast<int>(blockDim.x) >> 5) * 2) {
+        const int t = tb + ((threadIdx.x >> 4) & 1);
+        const bool live = t < num_tiles;
+        const size_t at = static_cast<size_t>(live ? t : 0) * kTileSubs + sub;
+        const uint32_t c = live ? counts[at] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(kFullMask, incl, o, 16);
+            if (sub >= o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(kFullMask, incl, 15, 16);
+        if (live) {
+            const uint32_t begin = ranges[t * 2];
+            sub_base[at] = begin + incl - c;
+            fill[at] = overflow ? 0xC0000000u : 0u;   // a huge fill level makes every claim fall outside its sub-bucket
+        }
+        __syncwarp();
+        if (live && sub == 0 && (overflow || total == 0u)) {  // empty tile (or nothing fits): (0, 0) like the reference's zero-filled buffer
+            ranges[t * 2] = 0u;
+            ranges[t * 2 + 1] = 0u;
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// tile_sort
+// tile_sort: one CTA per tile sorts the tile's slice of 64-bit keys (depth bits << 32 | particle) -- a least-significant-digit radix
+// sort over the 32 depth bits, 8 bits a pass, ping-ponging between the key buffer and its twin (both stay in the L2: a slice is a few
+// tens of KB), shared memory holding only the digit counters.  Each of the CTA's warps owns a contiguous segment of the slice and
+// keeps its elements in order (32 at a time: `match.any` groups equal digits, the group's first lane claims their slots), so a pass is
+// stable; passes in which every key carries the same digit (typically the exponent byte) are skipped.  The depth order the passes
+// produce is completed to (depth, particle) order by a fix-up of runs of EQUAL depth bits -- duplicates of a position, e.g. freshly
+// cloned Gaussians; the slots were claimed in arbitrary order, so the sort cannot rely on stability for them.
 
-__device__ __forceinline__ void compare_exchange(unsigned long long* s, uint32_t lo, uint32_t hi) {
-    const unsigned long long a = s[lo], b = s[hi];
-    if (a > b) {
-        s[lo] = b;
-        s[hi] = a;
-    }
-}
+constexpr int kSortThreads = 256, kSortWarps = kSortThreads / 32;
 
-// all steps of the ascending bitonic network with block sizes k = k_first .. k_last on s[0 .. len) (len <= chunk, local indices);
-// `flip_first`: whether the first k starts with its flip step (false = only the disperse steps j < k_first / 2 ... of an outer merge)
-// (block sizes and strides are powers of two: all index arithmetic is shifts and masks)
-template <int THREADS>
-__device__ __forceinline__ void bitonic_local(unsigned long long* s, uint32_t len, uint32_t span, uint32_t k_first, uint32_t k_last, bool inner_only) {
-    for (uint32_t k = k_first; k <= k_last; k <<= 1) {
-        const uint32_t lk = 31u - __clz(k);   // log2 k
-        if (!inner_only) {
-            const uint32_t half_mask = (k >> 1) - 1u;
-            for (uint32_t i = threadIdx.x; i < span / 2; i += THREADS) {  // flip: i-th element of a block's lower half <-> its mirror
-                const uint32_t blk = i >> (lk - 1u), off = i & half_mask;
-                const uint32_t lo = (blk << lk) + off, hi = (blk << lk) + (k - 1u - off);
-                if (hi < len) compare_exchange(s, lo, hi);
-            }
-            __syncthreads();
-        }
-        for (uint32_t j = inner_only ? (k >> 1) : (k >> 2); j >= 1; j >>= 1) {  // disperse
-            const uint32_t lj = 31u - __clz(j);
-            for (uint32_t i = threadIdx.x; i < span / 2; i += THREADS) {
-                const uint32_t lo = ((i >> lj) << (lj + 1u)) + (i & (j - 1u)), hi = lo + j;
-                if (hi < len) compare_exchange(s, lo, hi);
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// One CTA per tile.  CHUNK = keys held in shared memory at a time (a power of two).  Tiles whose list length is outside
-// (min_len, max_len] leave at once: two launches (small / large chunk) cover all tiles with the occupancy each class wants.
-template <int CHUNK, int THREADS>
-__global__ void __launch_bounds__(THREADS) tile_sort_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
-                                                            const uint32_t* __restrict__ totals, uint32_t min_len, uint32_t max_len,
-                                                            unsigned long long* __restrict__ keys, uint32_t* __restrict__ sorted_values) {
-    extern __shared__ __align__(16) unsigned long long s_keys[];
+__global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
+                                                                 const uint32_t* __restrict__ totals, unsigned long long* keys,
+                                                                 unsigned long long* keys_alt, uint32_t* __restrict__ sorted_values) {
+    __shared__ uint32_t s_cnt[kSortWarps][256];   // per-warp digit counts -> running slot of (warp, digit)
+    __shared__ uint32_t s_tot[256];
+    __shared__ int s_flag;
     if (totals[1] != 0u) return;  // capacity exceeded: the host grows the buffers and launches again
     const uint32_t tile = order[blockIdx.x];
     const uint32_t begin = ranges[tile * 2], n = ranges[tile * 2 + 1] - begin;
-    if (n <= min_len || n > max_len) return;
-    unsigned long long* g = keys + begin;
-    uint32_t n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    if (n2 <= CHUNK) {
-        for (uint32_t i = threadIdx.x; i < n; i += THREADS) s_keys[i] = g[i];
+    if (n == 0u) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned long long* src = keys + begin;
+    unsigned long long* dst = keys_alt + begin;
+    // warp w owns elements [w * seg, min(n, (w + 1) * seg)), seg a multiple of 32
+    const uint32_t seg = ((n + kSortWarps - 1) / kSortWarps + 31u) & ~31u;
+    const uint32_t w0 = min(n, warp * seg), w1 = min(n, w0 + seg);
+    for (int shift = 32; shift < 64; shift += 8) {
+        for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0u;
         __syncthreads();
-        bitonic_local<THREADS>(s_keys, n, n2, 2, n2, false);
-        for (uint32_t i = threadIdx.x; i < n; i += THREADS) sorted_values[begin + i] = static_cast<uint32_t>(s_keys[i]);
-        return;
-    }
-    // long list: sort CHUNK-sized pieces on chip, then merge with the outer steps of the same network through global memory
-    for (uint32_t c0 = 0; c0 < n; c0 += CHUNK) {
-        const uint32_t len = min(static_cast<uint32_t>(CHUNK), n - c0);
-        for (uint32_t i = threadIdx.x; i < len; i += THREADS) s_keys[i] = g[c0 + i];
+        for (uint32_t i = w0 + lane; i < w1; i += 32) atomicAdd(&s_cnt[warp][static_cast<uint32_t>(src[i] >> shift) & 255u], 1u);
         __syncthreads();
-        bitonic_local<THREADS>(s_keys, len, CHUNK, 2, CHUNK, false);
-        for (uint32_t i = threadIdx.x; i < len; i += THREADS) g[c0 + i] = s_keys[i];
-        __syncthreads();
-    }
-    for (uint32_t k = 2u * CHUNK; k <= n2; k <<= 1) {
-        const uint32_t lk = 31u - __clz(k), half_mask = (k >> 1) - 1u;
-        for (uint32_t i = threadIdx.x; i < n2 / 2; i += THREADS) {  // flip over global memory
-            const uint32_t blk = i >> (lk - 1u), off = i & half_mask;
-            const uint32_t lo = (blk << lk) + off, hi = (blk << lk) + (k - 1u - off);
-            if (hi < n) compare_exchange(g, lo, hi);
-        }
-        __syncthreads();
-        for (uint32_t j = k >> 2; j >= CHUNK; j >>= 1) {  // disperse steps wider than a chunk
-            const uint32_t lj = 31u - __clz(j);
-            for (uint32_t i = threadIdx.x; i < n2 / 2; i += THREADS) {
-                const uint32_t lo = ((i >> lj) << (lj + 1u)) + (i & (j - 1u)), hi = lo + j;
-                if (hi < n) compare_exchange(g, lo, hi);
+        {   // thread d: digit d's total, then an exclusive scan over the digits, then the first slot of (warp, d)
+            const int d = threadIdx.x;
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) tot += s_cnt[w][d];
+            s_tot[d] = tot;
+            if (d == 0) s_flag = 0;
+            __syncthreads();
+            if (tot == n) s_flag = 1;   // every key has this digit: the pass would be the identity
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(kFullMask, incl, o);
+                if (lane >= o) incl += v;
             }
             __syncthreads();
-        }
-        for (uint32_t c0 = 0; c0 < n; c0 += CHUNK) {  // the remaining steps (j < CHUNK) stay inside a chunk
-            const uint32_t len = min(static_cast<uint32_t>(CHUNK), n - c0);
-            for (uint32_t i = threadIdx.x; i < len; i += THREADS) s_keys[i] = g[c0 + i];
+            if (lane == 31) s_tot[warp] = incl;   // warp totals (8 warps x 32 digits)
             __syncthreads();
-            bitonic_local<THREADS>(s_keys, len, CHUNK, CHUNK, CHUNK, true);
-            for (uint32_t i = threadIdx.x; i < len; i += THREADS) g[c0 + i] = s_keys[i];
+            uint32_t base = incl - tot;
+            for (int w = 0; w < warp; ++w) base += s_tot[w];
+            const bool skip = s_flag != 0;
             __syncthreads();
+            if (skip) continue;   // uniform across the CTA
+            uint32_t run = base;
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) {
+                const uint32_t c = s_cnt[w][d];
+                s_cnt[w][d] = run;
+                run += c;
+            }
         }
+        __syncthreads();
+        for (uint32_t i0 = w0; i0 < w1; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const bool have = i < w1;
+            const unsigned long long k = have ? src[i] : 0ull;
+            const uint32_t d = have ? (static_cast<uint32_t>(k >> shift) & 255u) : 256u + lane;  // idle lanes: unique pseudo-digits
+            const unsigned peers = __match_any_sync(kFullMask, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t slot = 0;
+            if (have && lane == leader) slot = atomicAdd(&s_cnt[warp][d], static_cast<uint32_t>(__popc(peers)));
+            slot = __shfl_sync(kFullMask, slot, leader);
+            if (have) dst[slot + __popc(peers & lt_mask)] = k;
+        }
+        __syncthreads();
+        unsigned long long* t = src;
+        src = dst;
+        dst = t;
     }
-    for (uint32_t i = threadIdx.x; i < n; i += THREADS) sorted_values[begin + i] = static_cast<uint32_t>(g[i]);
+    // `src` holds the slice in depth order.  Equal depth bits: order those runs by particle index (rare; one thread walks the slice)
+    int ties = 0;
+    for (uint32_t i = threadIdx.x; i + 1 < n; i += kSortThreads) ties |= ((src[i] >> 32) == (src[i + 1] >> 32)) && (src[i] > src[i + 1]);
+    if (__syncthreads_or(ties)) {
+        if (threadIdx.x == 0) {
+            for (uint32_t i = 1; i < n; ++i) {   // insertion sort restricted to runs of equal depth
+                const unsigned long long k = src[i];
+                uint32_t j = i;
+                while (j > 0 && (src[j - 1] >> 32) == (k >> 32) && src[j - 1] > k) {
+                    src[j] = src[j - 1];
+                    --j;
+                }
+                src[j] = k;
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) sorted_values[begin + i] = static_cast<uint32_t>(src[i]);
 }
 
 // test-only: the reference's sorted 64-bit keys (tile << 32 | depth bits), rebuilt per tile from the sorted values
@@ -222,8 +242,6 @@ __global__ void __launch_bounds__(256) synth_tile_keys_kernel(const uint32_t* __
         out[k] = (static_cast<uint64_t>(tile) << 32) | __float_as_uint(depth[vals[k]]);
 }
 
-constexpr int kSmallChunk = 2048, kLargeChunk = 8192, kSortThreads = 256;
-
 }  // namespace
 
 void launch_tile_scan(cudaStream_t s, int num_tiles, const uint32_t* counts, uint32_t capacity, uint32_t* ranges, uint32_t* sub_base,
@@ -231,19 +249,11 @@ void launch_tile_scan(cudaStream_t s, int num_tiles, const uint32_t* counts, uin
     tile_scan_kernel<<<1, 1024, 0, s>>>(num_tiles, counts, capacity, ranges, sub_base, chunk_base, order, fill, totals);
 }
 
+// heaviest tiles come first in `order`: the long lists start before the bulk of the short ones
 cudaError_t launch_tile_sort(cudaStream_t s, int num_tiles, const uint32_t* order, const uint32_t* ranges, const uint32_t* totals,
-                             unsigned long long* keys, uint32_t* sorted_values) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tile_sort_kernel<kLargeChunk, kSortThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kLargeChunk * 8);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+                             unsigned long long* keys, unsigned long long* keys_alt, uint32_t* sorted_values) {
     if (num_tiles <= 0) return cudaSuccess;
-    // heaviest tiles come first in `order`: the long lists start before the bulk of the short ones
-    tile_sort_kernel<kLargeChunk, kSortThreads><<<num_tiles, kSortThreads, kLargeChunk * 8, s>>>(order, ranges, totals, kSmallChunk, 0xFFFFFFFFu, keys, sorted_values);
-    tile_sort_kernel<kSmallChunk, kSortThreads><<<num_tiles, kSortThreads, kSmallChunk * 8, s>>>(order, ranges, totals, 0u, kSmallChunk, keys, sorted_values);
+    tile_sort_kernel<<<num_tiles, kSortThreads, 0, s>>>(order, ranges, totals, keys, keys_alt, sorted_values);
     return cudaGetLastError();
 }
 

@@ -64,7 +64,7 @@ constexpr int kTileSubs = 16;  // sub-counters per tile (a particle uses sub-cou
 void launch_tile_scan(cudaStream_t s, int num_tiles, const uint32_t* counts, uint32_t capacity, uint32_t* ranges, uint32_t* sub_base,
                       uint32_t* chunk_base, uint32_t* order, uint32_t* fill, uint32_t* totals);
 cudaError_t launch_tile_sort(cudaStream_t s, int num_tiles, const uint32_t* order, const uint32_t* ranges, const uint32_t* totals,
-                             unsigned long long* keys, uint32_t* sorted_values);
+                             unsigned long long* keys, unsigned long long* keys_alt, uint32_t* sorted_values);
 void launch_synth_tile_keys(cudaStream_t s, int num_tiles, const uint32_t* ranges, const uint32_t* vals, const float* depth, uint64_t* out);
 void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint32_t* sorted_keys, uint32_t* ranges);
 void launch_synth_keys(cudaStream_t s, int64_t num, const uint32_t* tiles, const uint32_t* vals, const float* depth, uint64_t* out);
