@@ -213,23 +213,26 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(const uint32_t*
         src = dst;
         dst = t;
     }
-    // `src` holds the slice in depth order.  Equal depth bits: order those runs by particle index (rare; one thread walks the slice)
-    int ties = 0;
-    for (uint32_t i = threadIdx.x; i + 1 < n; i += kSortThreads) ties |= ((src[i] >> 32) == (src[i + 1] >> 32)) && (src[i] > src[i + 1]);
-    if (__syncthreads_or(ties)) {
-        if (threadIdx.x == 0) {
-            for (uint32_t i = 1; i < n; ++i) {   // insertion sort restricted to runs of equal depth
-                const unsigned long long k = src[i];
-                uint32_t j = i;
-                while (j > 0 && (src[j - 1] >> 32) == (k >> 32) && src[j - 1] > k) {
-                    src[j] = src[j - 1];
-                    --j;
-                }
-                src[j] = k;
+    // `src` holds the slice in depth order.  Runs of EQUAL depth bits are ordered by particle index by the thread whose element starts
+    // the run (runs are disjoint, a run is two or three keys long; a serial walk by one thread cost milliseconds here: every second C3
+    // tile has such a pair)
+    for (uint32_t i = threadIdx.x; i + 1 < n; i += kSortThreads) {
+        const unsigned long long a = src[i];
+        if ((a >> 32) != (src[i + 1] >> 32)) continue;
+        if (i > 0 && (src[i - 1] >> 32) == (a >> 32)) continue;  // inside a run: its first element's thread handles it
+        uint32_t e = i + 2;
+        while (e < n && (src[e] >> 32) == (a >> 32)) ++e;
+        for (uint32_t p = i + 1; p < e; ++p) {  // insertion sort of src[i .. e)
+            const unsigned long long k = src[p];
+            uint32_t q = p;
+            while (q > i && src[q - 1] > k) {
+                src[q] = src[q - 1];
+                --q;
             }
+            src[q] = k;
         }
-        __syncthreads();
     }
+    __syncthreads();
     for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) sorted_values[begin + i] = static_cast<uint32_t>(src[i]);
 }
 
