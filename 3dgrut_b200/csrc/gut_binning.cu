@@ -140,13 +140,14 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int num_tiles, const ui
 // produce is completed to (depth, particle) order by a fix-up of runs of EQUAL depth bits -- duplicates of a position, e.g. freshly
 // cloned Gaussians; the slots were claimed in arbitrary order, so the sort cannot rely on stability for them.
 
-constexpr int kSortThreads = 256, kSortWarps = kSortThreads / 32;
+constexpr int kSortThreads = 512, kSortWarps = kSortThreads / 32;   // 16 warps per tile: the long lists (6-30 k keys at C3) are latency-bound
+constexpr int kSortUnroll = 4;                                      // keys in flight per lane in the count / scatter loops
 
 __global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
                                                                  const uint32_t* __restrict__ totals, unsigned long long* keys,
                                                                  unsigned long long* keys_alt, uint32_t* __restrict__ sorted_values) {
     __shared__ uint32_t s_cnt[kSortWarps][256];   // per-warp digit counts -> running slot of (warp, digit)
-    __shared__ uint32_t s_tot[256];
+    __shared__ uint32_t s_tot[8];
     __shared__ int s_flag;
     if (totals[1] != 0u) return;  // capacity exceeded: the host grows the buffers and launches again
     const uint32_t tile = order[blockIdx.x];
@@ -161,33 +162,40 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(const uint32_t*
     const uint32_t w0 = min(n, warp * seg), w1 = min(n, w0 + seg);
     for (int shift = 32; shift < 64; shift += 8) {
         for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0u;
+        if (threadIdx.x == 0) s_flag = 0;
         __syncthreads();
-        for (uint32_t i = w0 + lane; i < w1; i += 32) atomicAdd(&s_cnt[warp][static_cast<uint32_t>(src[i] >> shift) & 255u], 1u);
+        for (uint32_t i0 = w0; i0 < w1; i0 += 32 * kSortUnroll) {  // digit counts of this warp's segment, kSortUnroll loads in flight
+            unsigned long long k[kSortUnroll];
+#pragma unroll
+            for (int u = 0; u < kSortUnroll; ++u) {
+                const uint32_t i = i0 + u * 32 + lane;
+                k[u] = i < w1 ? src[i] : ~0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < kSortUnroll; ++u)
+                if (i0 + u * 32 + lane < w1) atomicAdd(&s_cnt[warp][static_cast<uint32_t>(k[u] >> shift) & 255u], 1u);
+        }
         __syncthreads();
-        {   // thread d: digit d's total, then an exclusive scan over the digits, then the first slot of (warp, d)
-            const int d = threadIdx.x;
-            uint32_t tot = 0;
+        // threads 0..255: digit d's total, an exclusive scan over the digits, then the first slot of (warp, d)
+        const int d = threadIdx.x;
+        uint32_t tot = 0, incl = 0;
+        if (d < 256) {
 #pragma unroll
             for (int w = 0; w < kSortWarps; ++w) tot += s_cnt[w][d];
-            s_tot[d] = tot;
-            if (d == 0) s_flag = 0;
-            __syncthreads();
             if (tot == n) s_flag = 1;   // every key has this digit: the pass would be the identity
-            uint32_t incl = tot;
+            incl = tot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t v = __shfl_up_sync(kFullMask, incl, o);
                 if (lane >= o) incl += v;
             }
-            __syncthreads();
-            if (lane == 31) s_tot[warp] = incl;   // warp totals (8 warps x 32 digits)
-            __syncthreads();
-            uint32_t base = incl - tot;
-            for (int w = 0; w < warp; ++w) base += s_tot[w];
-            const bool skip = s_flag != 0;
-            __syncthreads();
-            if (skip) continue;   // uniform across the CTA
-            uint32_t run = base;
+            if (lane == 31) s_tot[warp] = incl;   // totals of the 8 groups of 32 digits
+        }
+        __syncthreads();
+        const bool skip = s_flag != 0;   // uniform across the CTA
+        if (!skip && d < 256) {
+            uint32_t run = incl - tot;
+            for (int w = 0; w < warp; ++w) run += s_tot[w];
 #pragma unroll
             for (int w = 0; w < kSortWarps; ++w) {
                 const uint32_t c = s_cnt[w][d];
@@ -196,17 +204,26 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(const uint32_t*
             }
         }
         __syncthreads();
-        for (uint32_t i0 = w0; i0 < w1; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            const bool have = i < w1;
-            const unsigned long long k = have ? src[i] : 0ull;
-            const uint32_t d = have ? (static_cast<uint32_t>(k >> shift) & 255u) : 256u + lane;  // idle lanes: unique pseudo-digits
-            const unsigned peers = __match_any_sync(kFullMask, d);
-            const int leader = __ffs(peers) - 1;
-            uint32_t slot = 0;
-            if (have && lane == leader) slot = atomicAdd(&s_cnt[warp][d], static_cast<uint32_t>(__popc(peers)));
-            slot = __shfl_sync(kFullMask, slot, leader);
-            if (have) dst[slot + __popc(peers & lt_mask)] = k;
+        if (skip) continue;
+        for (uint32_t i0 = w0; i0 < w1; i0 += 32 * kSortUnroll) {
+            unsigned long long k[kSortUnroll];
+#pragma unroll
+            for (int u = 0; u < kSortUnroll; ++u) {
+                const uint32_t i = i0 + u * 32 + lane;
+                k[u] = i < w1 ? src[i] : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < kSortUnroll; ++u) {   // 32 keys at a time, in order: the pass is stable
+                if (i0 + u * 32 >= w1) break;         // warp-uniform
+                const bool have = i0 + u * 32 + lane < w1;
+                const uint32_t dg = have ? (static_cast<uint32_t>(k[u] >> shift) & 255u) : 256u + lane;  // idle lanes: unique pseudo-digits
+                const unsigned peers = __match_any_sync(kFullMask, dg);
+                const int leader = __ffs(peers) - 1;
+                uint32_t slot = 0;
+                if (have && lane == leader) slot = atomicAdd(&s_cnt[warp][dg], static_cast<uint32_t>(__popc(peers)));
+                slot = __shfl_sync(kFullMask, slot, leader);
+                if (have) dst[slot + __popc(peers & lt_mask)] = k[u];
+            }
         }
         __syncthreads();
         unsigned long long* t = src;
