@@ -742,7 +742,7 @@ def main():
     ap.add_argument("--exchange", default="compact", choices=["compact", "allreduce"],
                     help="multi-GPU gradient exchange of the 3DGUT path: compact = all-reduce [N,12] + all-gather [N,4] + rebuild of the SH "
                          "gradient (64 B per Gaussian on the wire), allreduce = one all-reduce of [N,60] (240 B)")
-    ap.add_argument("--accumulate", type=int, default=2,
+    ap.add_argument("--accumulate", type=int, default=4,
                     help="multi-GPU: view-steps per rank between two gradient exchanges (a batch = accumulate x world views); ignored at N=1")
     ap.add_argument("--no-sub-records", action="store_true", help="skip the c3 (6M Gaussians) and c4 (3DGRT) sub-records of the default c2 line")
     args = ap.parse_args()

@@ -13,5 +13,10 @@ except Exception as e:
     print("N=$N $1: failed", e); print(open("gpurun_out/r02_scale_n${N}_$1.err").read()[-1500:])
 PY
 }
-run acc2 "--accumulate 2"
+if [ "${2:-all}" = "default" ]; then
+run acc4 ""
+else
+run acc4 ""
+run acc2 "--accumulate 2 --no-sub-records"
 run acc1 "--accumulate 1 --no-sub-records"
+fi
