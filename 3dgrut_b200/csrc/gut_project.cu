@@ -520,29 +520,10 @@ __global__ void __launch_bounds__(256) expand_place_kernel(FrameCamera cam, Fram
         } else {
             maxpow = logf(pr.op / cfg.min_alpha);
             if (cells <= kSmallBox) {
-                // all slot claims of the footprint are issued before the first key is stored: up to kSmallBox atomics in flight per thread
-                // instead of one round trip to the L2 per tile
-                const int bw = bb.x1 - bb.x0;
-                const size_t subk = static_cast<uint32_t>(key) & (kTileSubs - 1);
-                uint32_t slot[kSmallBox];
-                size_t at[kSmallBox];
-                bool pass[kSmallBox];
-#pragma unroll
-                for (int c = 0; c < kSmallBox; ++c) {
-                    pass[c] = false;
-                    if (c < cells) {
-                        const int y = bb.y0 + c / bw, x = bb.x0 + c % bw;
-                        pass[c] = tile_min_power(static_cast<float>(x), static_cast<float>(y), pr.ca, pr.cb, pr.cc, pr.cx, pr.cy) < maxpow;
-                        at[c] = static_cast<size_t>(y * cam.grid_x + x) * kTileSubs + subk;
-                        if (pass[c]) slot[c] = atomicAdd(&fill[at[c]], 1u);
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < kSmallBox; ++c)
-                    if (pass[c]) {
-                        const uint32_t pos = sub_base[at[c]] + slot[c];
-                        if (slot[c] < tile_hist[at[c]] && pos < capacity) keys[pos] = key;
-                    }
+                for (int y = bb.y0; y < bb.y1; ++y)
+                    for (int x = bb.x0; x < bb.x1; ++x)
+                        if (tile_min_power(static_cast<float>(x), static_cast<float>(y), pr.ca, pr.cb, pr.cc, pr.cx, pr.cy) < maxpow)
+                            place(y * cam.grid_x + x, key);
                 cells = 0;
             }
         }
