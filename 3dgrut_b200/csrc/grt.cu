@@ -321,18 +321,7 @@ __device__ __forceinline__ void proxy_visit(const LeafProxy* __restrict__ lp, fl
                 oiz = a2.x * vx + a2.y * vy + a2.z * vz;
     const float dix = a0.x * dx + a0.y * dy + a0.z * dz, diy = a1.x * dx + a1.y * dy + a1.z * dz,
                 diz = a2.x * dx + a2.y * dy + a2.z * dz;
-    // The candidate rule is a conjunction -- ray segment meets the unit cube of instance space (the custom primitive's AABB),
-    // intersectInstanceParticle accepts (gaussianParticles.cuh:449-465), t* is nearer than the current 16th hit -- evaluated cheapest and
-    // most selective first: of ~440 proxies a C4 ray reaches, ~20 become candidates (work counters), so the t* interval test (two dot
-    // products) runs before the distance test (a cross product) and the cube slab test (three divisions) comes last.
-    const float dd = dix * dix + diy * diy + diz * diz;
-    const float den = 1.f / dd;
-    float ht = -(oix * dix + oiy * diy + oiz * diz) * den;
-    if (!((ht > tmin) && (ht < tmax)) || !(ht < kt[kK - 1])) return;
-    const float il = dd > 0.f ? rsqrtf(dd) : 1.f;
-    const float n0 = dix * il, n1 = diy * il, n2 = diz * il;
-    const float c0 = n1 * oiz - n2 * oiy, c1 = n2 * oix - n0 * oiz, c2 = n0 * oiy - n1 * oix;
-    if (!((c0 * c0 + c1 * c1 + c2 * c2) * den < 9.f)) return;
+    // ray segment vs the unit cube of instance space (the custom primitive's AABB)
     float tin = tmin, tout = tmax, q0, q1;
     q0 = (-1.f - oix) / dix; q1 = (1.f - oix) / dix;
     tin = fmaxf(tin, fminf(q0, q1)); tout = fminf(tout, fmaxf(q0, q1));
@@ -341,8 +330,17 @@ __device__ __forceinline__ void proxy_visit(const LeafProxy* __restrict__ lp, fl
     q0 = (-1.f - oiz) / diz; q1 = (1.f - oiz) / diz;
     tin = fmaxf(tin, fminf(q0, q1)); tout = fminf(tout, fmaxf(q0, q1));
     if (!(tin <= tout)) return;
+    // intersectInstanceParticle (gaussianParticles.cuh:449-465)
+    const float dd = dix * dix + diy * diy + diz * diz;
+    const float den = 1.f / dd;
+    float ht = -(oix * dix + oiy * diy + oiz * diz) * den;
+    if (!((ht > tmin) && (ht < tmax))) return;
+    const float il = dd > 0.f ? rsqrtf(dd) : 1.f;
+    const float n0 = dix * il, n1 = diy * il, n2 = diz * il;
+    const float c0 = n1 * oiz - n2 * oiy, c1 = n2 * oix - n0 * oiz, c2 = n0 * oiy - n1 * oix;
+    if (!((c0 * c0 + c1 * c1 + c2 * c2) * den < 9.f)) return;
     // __anyhit__ah (referenceOptix.cu:222-248): bubble the hit into the sorted 16-slot payload
-    {
+    if (ht < kt[kK - 1]) {
         uint32_t hid = __ldg(&lp->pid);
 #pragma unroll
         for (int i = 0; i < kK; ++i) {
