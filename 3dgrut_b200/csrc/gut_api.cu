@@ -109,16 +109,6 @@ void pose_cols(const Pose& p, float cols[12]) {
     cols[11] = p.t[2];
 }
 
-uint32_t higher_msb(uint32_t n) {  // bits needed for tile ids (gutRenderer.cu:79-94)
-    uint32_t msb = 16, step = 16;
-    while (step > 1) {
-        step /= 2;
-        if (n >> msb) msb += step; else msb -= step;
-    }
-    if (n >> msb) msb++;
-    return msb;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 
 struct DeviceBuffer {

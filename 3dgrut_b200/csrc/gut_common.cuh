@@ -66,13 +66,10 @@ void launch_tile_scan(cudaStream_t s, int num_tiles, const uint32_t* counts, uin
 cudaError_t launch_tile_sort(cudaStream_t s, int num_tiles, const uint32_t* order, const uint32_t* ranges, const uint32_t* totals,
                              unsigned long long* keys, unsigned long long* keys_alt, uint32_t* sorted_values);
 void launch_synth_tile_keys(cudaStream_t s, int num_tiles, const uint32_t* ranges, const uint32_t* vals, const float* depth, uint64_t* out);
-void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint32_t* sorted_keys, uint32_t* ranges);
-void launch_synth_keys(cudaStream_t s, int64_t num, const uint32_t* tiles, const uint32_t* vals, const float* depth, uint64_t* out);
 
 // hit words: one 32-bit word per (32-entry chunk of a tile list, warp of the tile's CTA, quarter of the warp's 8x4 pixel block);
 // tile t's slice starts at chunk_base[t] * 32 words
 inline size_t hit_words_capacity(int64_t num_isect, int64_t tiles) { return (static_cast<size_t>(num_isect) / 32 + static_cast<size_t>(tiles) + 1) * 32; }
-void launch_tile_order(cudaStream_t s, const FrameCamera& cam, const uint32_t* ranges, uint32_t* tile_order, uint32_t* chunk_base);
 void launch_render_forward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
                            const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,
                            const uint32_t* ranges, const uint32_t* tile_order, const uint32_t* chunk_base, uint32_t* hit_words, float* out_rgba,
@@ -98,8 +95,6 @@ void launch_sph_from_views(cudaStream_t s, int64_t n, const float* particles, in
                            const float* d_radiance_all, float* d_sph);
 
 // CUB-backed helpers (scan + radix sort), gut_sort.cu
-size_t scan_temp_bytes(int64_t n);
-void run_inclusive_scan(cudaStream_t s, void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, int64_t n);
 size_t sort32_temp_bytes(int64_t n);
 void run_sort32_pairs(cudaStream_t s, void* temp, size_t temp_bytes, const uint32_t* kin, uint32_t* kout, const uint32_t* vin,
                       uint32_t* vout, int64_t n, int end_bit);

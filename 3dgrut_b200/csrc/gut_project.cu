@@ -1,5 +1,5 @@
-// 3dgrut_b200/csrc/gut_project.cu -- per-particle stages of the 3DGUT forward: unscented projection + tile
-// counting (G1), key expansion (G3), tile ranges (G5).
+// 3dgrut_b200/csrc/gut_project.cu -- per-particle stages of the 3DGUT forward: unscented projection + tile counting + per-tile
+// histogram (G1), key expansion into the tiles' slices (G3).  Tile ranges (G2 / G5) and the per-tile sort (G4) live in gut_binning.cu.
 //
 // Built with -fmad=false and IEEE div/sqrt: tile counts and sort keys are INTEGER outputs that must be
 // bit-identical to the checker, so every fp32 operation here is written in the order the reference writes it
@@ -548,41 +548,7 @@ __global__ void __launch_bounds__(256) expand_place_kernel(FrameCamera cam, Fram
     }
 }
 
-// G5: [begin,end) of every tile in the sorted key stream (computeSortedTileRangeIndices, gutRenderer.cu:46-76)
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t num_keys, const uint32_t* __restrict__ keys,
-                                                          uint32_t* __restrict__ ranges) {
-    const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (k >= num_keys) return;
-    const uint32_t tile = keys[k];
-    const bool valid = tile != kInvalid;
-    if (k == 0) {
-        if (valid) ranges[tile * 2] = 0u;
-    } else {
-        const uint32_t prev = keys[k - 1];
-        if (prev != tile) {
-            if (prev != kInvalid) ranges[prev * 2 + 1] = static_cast<uint32_t>(k);
-            if (valid) ranges[tile * 2] = static_cast<uint32_t>(k);
-        }
-    }
-    if (valid && (k == num_keys - 1)) ranges[tile * 2 + 1] = static_cast<uint32_t>(num_keys);
-}
-
-// test-only: the reference's 64-bit keys (tile << 32 | depth bits) of the sorted stream
-__global__ void __launch_bounds__(256) synth_keys_kernel(int64_t num, const uint32_t* __restrict__ tiles, const uint32_t* __restrict__ vals,
-                                                         const float* __restrict__ depth, uint64_t* __restrict__ out) {
-    const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (k >= num) return;
-    const uint32_t v = vals[k];
-    const uint32_t d = v == kInvalid ? __float_as_uint(3.4028235e+38f) : __float_as_uint(depth[v]);
-    out[k] = (static_cast<uint64_t>(tiles[k]) << 32) | d;
-}
-
 }  // namespace
-
-void launch_synth_keys(cudaStream_t s, int64_t num, const uint32_t* tiles, const uint32_t* vals, const float* depth, uint64_t* out) {
-    if (num <= 0) return;
-    synth_keys_kernel<<<static_cast<unsigned>((num + 255) / 256), 256, 0, s>>>(num, tiles, vals, depth, out);
-}
 
 void launch_project(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const float* particles,
                     const float* sph, int sph_degree, uint32_t* tiles_count, ProjRecord* proj, float* depth, float* rgb,
@@ -601,12 +567,6 @@ void launch_expand_place(cudaStream_t s, const FrameCamera& cam, const FrameConf
     if (n <= 0) return;
     const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
     expand_place_kernel<<<blocks, 256, 0, s>>>(cam, cfg, n, proj, depth, tile_hist, sub_base, totals, capacity, fill, keys);
-}
-
-void launch_tile_ranges(cudaStream_t s, int64_t num_keys, const uint32_t* sorted_keys, uint32_t* ranges) {
-    if (num_keys <= 0) return;
-    const unsigned blocks = static_cast<unsigned>((num_keys + 255) / 256);
-    tile_ranges_kernel<<<blocks, 256, 0, s>>>(num_keys, sorted_keys, ranges);
 }
 
 }  // namespace gutb200

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
                                                                      float* __restrict__ out_rgba, float* __restrict__ out_dist,
                                                                      float* __restrict__ out_hits, WorkCounters* __restrict__ ctr) {
     __shared__ FwdSmem sm;
-    const int tile = tile_order[blockIdx.x];  // heaviest tiles first (tile_order_kernel): shortens the tail of the grid
+    const int tile = tile_order[blockIdx.x];  // heaviest tiles first (tile_scan_kernel's order): shortens the tail of the grid
     const int tid = threadIdx.x;
     int px, py;
     tile_pixel(tile, cam.grid_x, tid, px, py);
@@ -398,58 +398,6 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
         reinterpret_cast<float4*>(out_rgba)[pix] = make_float4(0.f, 0.f, 0.f, 0.f);
         out_dist[pix] = 1e06f;  // torch::ones(...)*1e6 (splatRaster.cpp:213)
         out_hits[pix] = 0.f;
-    }
-}
-
-// Order tiles by decreasing list length (bucketed by log2) and lay out the per-tile slices of the hit-word buffer
-// (chunk_base[t] = exclusive prefix sum of ceil(list length / 32)): one small single-CTA kernel per frame.
-__global__ void __launch_bounds__(1024) tile_order_kernel(int num_tiles, const uint32_t* __restrict__ ranges, uint32_t* __restrict__ order,
-                                                          uint32_t* __restrict__ chunk_base) {
-    __shared__ uint32_t hist[34];
-    __shared__ uint32_t warp_sums[32];
-    if (threadIdx.x < 34) hist[threadIdx.x] = 0;
-    __syncthreads();
-    for (int t = threadIdx.x; t < num_tiles; t += blockDim.x) {
-        const uint32_t c = ranges[t * 2 + 1] - ranges[t * 2];
-        atomicAdd(&hist[__clz(c) + 1], 1u);  // __clz(0) = 32 -> last bucket; long lists -> small bucket index
-    }
-    // chunk_base: every thread owns a contiguous strip of tiles
-    const int strip = (num_tiles + static_cast<int>(blockDim.x) - 1) / static_cast<int>(blockDim.x);
-    const int t0 = min(static_cast<int>(threadIdx.x) * strip, num_tiles), t1 = min(t0 + strip, num_tiles);
-    uint32_t mine = 0;
-    for (int t = t0; t < t1; ++t) mine += (ranges[t * 2 + 1] - ranges[t * 2] + 31u) >> 5;
-    uint32_t incl = mine;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int b = 1; b < 34; ++b) {
-            const uint32_t h = hist[b];
-            hist[b] = run;
-            run += h;
-        }
-        run = 0;
-        for (int w = 0; w < 32; ++w) {
-            const uint32_t v = warp_sums[w];
-            warp_sums[w] = run;
-            run += v;
-        }
-    }
-    __syncthreads();
-    uint32_t run = warp_sums[warp] + incl - mine;
-    for (int t = t0; t < t1; ++t) {
-        chunk_base[t] = run;
-        run += (ranges[t * 2 + 1] - ranges[t * 2] + 31u) >> 5;
-    }
-    for (int t = threadIdx.x; t < num_tiles; t += blockDim.x) {
-        const uint32_t c = ranges[t * 2 + 1] - ranges[t * 2];
-        order[atomicAdd(&hist[__clz(c) + 1], 1u)] = static_cast<uint32_t>(t);
     }
 }
 
@@ -1003,10 +951,6 @@ __global__ void __launch_bounds__(128) sph_from_views_kernel(int64_t n, const fl
 }
 
 }  // namespace
-
-void launch_tile_order(cudaStream_t s, const FrameCamera& cam, const uint32_t* ranges, uint32_t* tile_order, uint32_t* chunk_base) {
-    tile_order_kernel<<<1, 1024, 0, s>>>(cam.grid_x * cam.grid_y, ranges, tile_order, chunk_base);
-}
 
 void launch_render_forward(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, const float* rays_o,
                            const float* rays_d, const float* particles, const float* rgb, const uint32_t* sorted_values,

@@ -145,6 +145,16 @@ def _ptr(t: torch.Tensor) -> int:
     return t.data_ptr()
 
 
+def _c(t: torch.Tensor) -> torch.Tensor:
+    """.contiguous() without the dispatcher round trip when the tensor already is (the host side of a 0.9 ms frame is on the critical path)"""
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _raw_stream(dev: torch.device) -> int:
+    """cudaStream_t of torch's current stream on `dev` (what torch.cuda.current_stream(dev).cuda_stream returns, minus ~10 us of Python)"""
+    return torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None else torch.cuda.current_device())
+
+
 class SplatRaster:
     """Python twin of the pybind class lib3dgut_cc.SplatRaster (bindings.cpp:103-109)."""
 
@@ -153,12 +163,25 @@ class SplatRaster:
             raise RuntimeError("threedgut_tracer (B200): CUDA device required; there is no CPU path")
         self._cfg = _native_config(conf)
         self._ctx = {}  # one native context per device, like one SplatRaster per process/GPU in the reference
+        self._last_camera = None  # (sensor, pose_start, pose_end, w, h, native.Camera) of the latest call: trace_bwd re-uses trace's struct
 
     def _context(self, device: torch.device) -> native.Context:
         idx = device.index if device.index is not None else torch.cuda.current_device()
         if idx not in self._ctx:
             self._ctx[idx] = native.Context(self._cfg, idx)
         return self._ctx[idx]
+
+    def _camera_cached(self, sensor, pose_start, pose_end, width: int, height: int) -> native.Camera:
+        """_camera, re-used when the very same sensor / pose OBJECTS come back (trace -> trace_bwd of one frame); the tuple keeps them alive,
+        so an `is` match cannot be a recycled id.  Callers that mutate a pose array in place between trace and trace_bwd get the reference's
+        behaviour only through _camera -- the C side rejects a backward whose camera differs from the forward's either way."""
+        last = self._last_camera
+        if (last is not None and last[0] is sensor and last[1] is pose_start and last[2] is pose_end and last[3] == width and last[4] == height
+                and np.array_equal(last[6], pose_start) and np.array_equal(last[7], pose_end)):
+            return last[5]
+        cam = self._camera(sensor, pose_start, pose_end, width, height)
+        self._last_camera = (sensor, pose_start, pose_end, width, height, cam, np.array(pose_start, copy=True), np.array(pose_end, copy=True))
+        return cam
 
     @staticmethod
     def _camera(sensor: CameraModelParameters, pose_start, pose_end, width: int, height: int) -> native.Camera:
@@ -189,9 +212,8 @@ class SplatRaster:
         dev = ray_ori.device
         h, w = int(ray_ori.shape[1]), int(ray_ori.shape[2])
         n = int(particle_density.shape[0])
-        particle_density = particle_density.contiguous()
-        particle_radiance = particle_radiance.contiguous()
-        ray_ori, ray_dir = ray_ori.contiguous(), ray_dir.contiguous()
+        particle_density, particle_radiance = _c(particle_density), _c(particle_radiance)
+        ray_ori, ray_dir = _c(ray_ori), _c(ray_dir)
         for t in (particle_density, particle_radiance, ray_ori, ray_dir):
             if t.dtype != torch.float32 or not t.is_cuda:
                 raise RuntimeError("trace: tensors must be float32 CUDA tensors")
@@ -199,8 +221,8 @@ class SplatRaster:
         dist = torch.empty((h, w, 1), dtype=torch.float32, device=dev)
         hits = torch.empty((h, w, 1), dtype=torch.float32, device=dev)
         vis = torch.empty((n, 1), dtype=torch.float32, device=dev)
-        cam = self._camera(sensor_params, pose_start, pose_end, w, h)
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        cam = self._camera_cached(sensor_params, pose_start, pose_end, w, h)
+        stream = _raw_stream(dev)
         self._context(dev).forward(stream, cam, n, _ptr(particle_density), _ptr(particle_radiance), int(n_active_features),
                                    _ptr(ray_ori), _ptr(ray_dir), _ptr(rgba), _ptr(dist), _ptr(hits), _ptr(vis))
         return rgba, dist, hits, vis
@@ -213,19 +235,18 @@ class SplatRaster:
         dev = ray_ori.device
         h, w = int(ray_ori.shape[1]), int(ray_ori.shape[2])
         n = int(particle_density.shape[0])
-        particle_density = particle_density.contiguous()
-        particle_radiance = particle_radiance.contiguous()
-        ray_ori, ray_dir = ray_ori.contiguous(), ray_dir.contiguous()
-        rgba, d_rgba = ray_radiance_density.contiguous(), ray_radiance_density_grd.contiguous().float()
-        dist, d_dist = ray_hit_distance.contiguous(), ray_hit_distance_grd.contiguous().float()
+        particle_density, particle_radiance = _c(particle_density), _c(particle_radiance)
+        ray_ori, ray_dir = _c(ray_ori), _c(ray_dir)
+        rgba, d_rgba = _c(ray_radiance_density), _c(ray_radiance_density_grd).float()
+        dist, d_dist = _c(ray_hit_distance), _c(ray_hit_distance_grd).float()
         if out is not None:
             d_density, d_radiance = out
             assert d_density.shape == (n, 12) and d_radiance.shape == (n, 48) and d_density.is_contiguous() and d_radiance.is_contiguous()
         else:
             d_density = torch.empty((n, 12), dtype=torch.float32, device=dev)
             d_radiance = torch.empty((n, 48), dtype=torch.float32, device=dev)
-        cam = self._camera(sensor_params, pose_start, pose_end, w, h)
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        cam = self._camera_cached(sensor_params, pose_start, pose_end, w, h)
+        stream = _raw_stream(dev)
         self._context(dev).backward(stream, cam, n, _ptr(particle_density), _ptr(particle_radiance), int(n_active_features),
                                     _ptr(ray_ori), _ptr(ray_dir), _ptr(rgba), _ptr(d_rgba), _ptr(dist), _ptr(d_dist),
                                     _ptr(d_density), _ptr(d_radiance))
@@ -241,19 +262,18 @@ class SplatRaster:
         dev = ray_ori.device
         h, w = int(ray_ori.shape[1]), int(ray_ori.shape[2])
         n = int(particle_density.shape[0])
-        particle_density = particle_density.contiguous()
-        particle_radiance = particle_radiance.contiguous()
-        ray_ori, ray_dir = ray_ori.contiguous(), ray_dir.contiguous()
-        rgba, d_rgba = ray_radiance_density.contiguous(), ray_radiance_density_grd.contiguous().float()
-        dist, d_dist = ray_hit_distance.contiguous(), ray_hit_distance_grd.contiguous().float()
+        particle_density, particle_radiance = _c(particle_density), _c(particle_radiance)
+        ray_ori, ray_dir = _c(ray_ori), _c(ray_dir)
+        rgba, d_rgba = _c(ray_radiance_density), _c(ray_radiance_density_grd).float()
+        dist, d_dist = _c(ray_hit_distance), _c(ray_hit_distance_grd).float()
         if out is not None:
             d_density, g = out
             assert d_density.shape == (n, 12) and g.shape == (n, 4) and d_density.is_contiguous() and g.is_contiguous()
         else:
             d_density = torch.empty((n, 12), dtype=torch.float32, device=dev)
             g = torch.empty((n, 4), dtype=torch.float32, device=dev)
-        cam = self._camera(sensor_params, pose_start, pose_end, w, h)
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        cam = self._camera_cached(sensor_params, pose_start, pose_end, w, h)
+        stream = _raw_stream(dev)
         self._context(dev).backward_compact(stream, cam, n, _ptr(particle_density), _ptr(particle_radiance), int(n_active_features),
                                             _ptr(ray_ori), _ptr(ray_dir), _ptr(rgba), _ptr(d_rgba), _ptr(dist), _ptr(d_dist),
                                             _ptr(d_density), _ptr(g))
@@ -268,12 +288,12 @@ class SplatRaster:
         view_positions: [views,3] (numpy / sequence, host); g_all: [views,N,4] device tensor (e.g. the result of an all-gather)."""
         dev = particle_density.device
         n = int(particle_density.shape[0])
-        particle_density = particle_density.contiguous()
-        g_all = g_all.contiguous()
+        particle_density = _c(particle_density)
+        g_all = _c(g_all)
         assert g_all.dim() == 3 and g_all.shape[1] == n and g_all.shape[2] == 4
         d_radiance = out if out is not None else torch.empty((n, 48), dtype=torch.float32, device=dev)
         assert d_radiance.shape == (n, 48) and d_radiance.is_contiguous()
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _raw_stream(dev)
         self._context(dev).sph_grad_from_views(stream, n, _ptr(particle_density), int(n_active_features),
                                                np.asarray(view_positions, np.float32).reshape(-1, 3), _ptr(g_all), _ptr(d_radiance))
         return d_radiance
@@ -301,10 +321,10 @@ class Tracer:
         @staticmethod
         def forward(ctx, tracer_wrapper, frame_id, n_active_features, ray_ori, ray_dir, mog_pos, mog_rot, mog_scl, mog_dns, mog_sph,
                     sensor_params, sensor_poses):
-            particle_density = torch.concat([mog_pos, mog_dns, mog_rot, mog_scl, torch.zeros_like(mog_dns)], dim=1).contiguous()
-            particle_features = mog_sph.contiguous()
+            particle_density = _c(torch.concat([mog_pos, mog_dns, mog_rot, mog_scl, torch.zeros_like(mog_dns)], dim=1))
+            particle_features = _c(mog_sph)
             ray_features_density, ray_hit_distance, ray_hit_count, mog_visibility = tracer_wrapper.trace(
-                frame_id, n_active_features, particle_density, particle_features, ray_ori.contiguous(), ray_dir.contiguous(), None,
+                frame_id, n_active_features, particle_density, particle_features, _c(ray_ori), _c(ray_dir), None,
                 sensor_params, sensor_poses.timestamps_us[0], sensor_poses.timestamps_us[1], sensor_poses.T_world_sensors[0],
                 sensor_poses.T_world_sensors[1])
             ctx.save_for_backward(ray_ori, ray_dir, ray_features_density, ray_hit_distance, particle_density, particle_features)
@@ -340,14 +360,24 @@ class Tracer:
     def build_acc(self, gaussians, rebuild=True):
         pass  # no-op for 3DGUT (tracer.py:301)
 
+    def _constant_normals(self, like: torch.Tensor) -> torch.Tensor:
+        """normalize(ones_like(pred_features), dim=3) (tracer.py:304-349 returns this constant as "pred_normals"): a function of shape /
+        dtype / device only, so it is built once per shape instead of with four kernels per frame."""
+        key = (tuple(like.shape), like.dtype, like.device)
+        cached = getattr(self, "_normals_cache", None)
+        if cached is None or cached[0] != key:
+            cached = (key, torch.nn.functional.normalize(torch.ones_like(like), dim=3))
+            self._normals_cache = cached
+        return cached[1]
+
     def render(self, gaussians, gpu_batch, train=False, frame_id=0):
         """tracer.py:304-349"""
         rays_o, rays_d = gpu_batch.rays_ori, gpu_batch.rays_dir
         sensor, poses = Tracer._create_camera_parameters(gpu_batch)
         pred_features_alpha, pred_dist, hits_count, mog_visibility = Tracer._Autograd.apply(
-            self.tracer_wrapper, frame_id, gaussians.n_active_features, rays_o.contiguous(), rays_d.contiguous(),
-            gaussians.positions.contiguous(), gaussians.get_rotation().contiguous(), gaussians.get_scale().contiguous(),
-            gaussians.get_density().contiguous(), gaussians.get_features().contiguous(), sensor, poses)
+            self.tracer_wrapper, frame_id, gaussians.n_active_features, _c(rays_o), _c(rays_d),
+            _c(gaussians.positions), _c(gaussians.get_rotation()), _c(gaussians.get_scale()),
+            _c(gaussians.get_density()), _c(gaussians.get_features()), sensor, poses)
         ray_feature_dim = getattr(gaussians, "ray_feature_dim", 3)
         pred_features = pred_features_alpha[..., :ray_feature_dim].unsqueeze(0).contiguous()
         pred_opacity = pred_features_alpha[..., ray_feature_dim:].unsqueeze(0).contiguous()
@@ -355,9 +385,9 @@ class Tracer:
         return {
             "pred_features": pred_features,
             "pred_opacity": pred_opacity,
-            "pred_dist": pred_dist.unsqueeze(0).contiguous(),
-            "pred_normals": torch.nn.functional.normalize(torch.ones_like(pred_features), dim=3),
-            "hits_count": hits_count.unsqueeze(0).contiguous(),
+            "pred_dist": _c(pred_dist.unsqueeze(0)),
+            "pred_normals": self._constant_normals(pred_features),
+            "hits_count": _c(hits_count.unsqueeze(0)),
             "frame_time_ms": timings["forward_render"] if "forward_render" in timings else 0.0,
             "mog_visibility": mog_visibility,
         }
@@ -379,8 +409,9 @@ class Tracer:
         else:
             start = gpu_batch.T_to_world.squeeze()
             assert start.ndim == 2
-            end = gpu_batch.T_to_world_end.squeeze() if getattr(gpu_batch, "T_to_world_end", None) is not None else start
-            pose_start, pose_end = Tracer._pose_from_c2w(start), Tracer._pose_from_c2w(end)
+            end_raw = getattr(gpu_batch, "T_to_world_end", None)
+            pose_start = Tracer._pose_from_c2w(start)
+            pose_end = pose_start.copy() if end_raw is None else Tracer._pose_from_c2w(end_raw.squeeze())
         poses = SensorPose3D(T_world_sensors=[pose_start, pose_end], timestamps_us=[0, 1])
         K = getattr(gpu_batch, "intrinsics", None)
         if K is not None:

@@ -346,6 +346,8 @@ class HostFeed:
 
     def __init__(self, torch, dev, pinned):
         self.torch, self.dev, self.pinned = torch, dev, pinned
+        self.layout = [(tuple(t.shape), t.numel()) for t in pinned]
+        self.slab = torch.cat([t.reshape(-1) for t in pinned]).pin_memory()  # what a collating DataLoader hands over: one pinned buffer
         self.stream = torch.cuda.Stream(device=dev)
         self.next = None
         self.loss_slots = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -357,21 +359,24 @@ class HostFeed:
         torch = self.torch
         self.stream.wait_stream(torch.cuda.current_stream(self.dev))  # buffers freed by older steps are safe to reuse
         with torch.cuda.stream(self.stream):
-            tensors = [t.to(self.dev, non_blocking=True) for t in self.pinned]
+            slab = self.slab.to(self.dev, non_blocking=True)  # ONE copy per step: the collated batch (rays + target image)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return tensors, ev
+        tensors, at = [], 0
+        for shape, numel in self.layout:
+            tensors.append(slab[at:at + numel].view(shape))
+            at += numel
+        return tensors, ev, slab
 
     def take(self):
         """This step's device tensors (copy already in flight) + issue the next step's copy."""
         torch = self.torch
         if self.next is None:
             self.next = self._issue()
-        tensors, ev = self.next
+        tensors, ev, slab = self.next
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_event(ev)
-        for t in tensors:
-            t.record_stream(cur)
+        slab.record_stream(cur)
         self.next = self._issue()
         return tensors
 
@@ -744,6 +749,7 @@ def main():
                          "gradient (64 B per Gaussian on the wire), allreduce = one all-reduce of [N,60] (240 B)")
     ap.add_argument("--accumulate", type=int, default=4,
                     help="multi-GPU: view-steps per rank between two gradient exchanges (a batch = accumulate x world views); ignored at N=1")
+    ap.add_argument("--profile-host", default=None, help="write a cProfile of the end-to-end loop's host side to this file (diagnostic; the e2e number of such a run is not a bench value)")
     ap.add_argument("--no-sub-records", action="store_true", help="skip the c3 (6M Gaussians) and c4 (3DGRT) sub-records of the default c2 line")
     args = ap.parse_args()
 
@@ -846,8 +852,22 @@ def main():
         step_e2e(s)
     barrier()
     t0 = time.perf_counter()
+    prof = None
+    if args.profile_host:
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     for s in range(e2e_steps):
         step_e2e(args.warmup + s)
+    if prof is not None:
+        prof.disable()
+        import io, pstats
+        buf = io.StringIO()
+        pstats.Stats(prof, stream=buf).sort_stats("cumulative").print_stats(70)
+        pstats.Stats(prof, stream=buf).sort_stats("tottime").print_stats(40)
+        with open(args.profile_host, "w") as f:
+            f.write(f"steps {e2e_steps}\n" + buf.getvalue())
+    e2e_host_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps  # host time to ISSUE a step (includes the forward's wait on the list total)
     feed.drain()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
@@ -944,7 +964,7 @@ def main():
                        "exchange": (args.exchange if world > 1 else "none"), "l2": "flushed between timed steps (256 MiB fill)",
                        "N": N_, "V": V_, "I": I_, "T": T_, "P": P_},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps, "host_issue_ms_per_step": e2e_host_ms,
                     "api": "threedgut_tracer.Tracer.render + loss.backward",
                     "feed": "pinned host -> device on a copy stream, one step ahead; loss read back one step later"},
             "gpu_launches": int(launches),

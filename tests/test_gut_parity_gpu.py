@@ -420,6 +420,39 @@ def test_error_conventions():
     ctx2.close()
 
 
+def test_backward_rejects_a_camera_other_than_the_forwards():
+    """The backward replays the lists, the projection and the hit words of the immediately preceding forward: called with another view's
+    camera (same resolution) it must fail, not mix two views silently (the reference uses the stale context, gutRenderer.cu:436-440)."""
+    import b200_native as nat
+
+    sc = scenes.scene_c1(n=200, width=64, height=64)
+    ctx = nat.Context(nat.default_config(), 0)
+
+    def camera(i):
+        pose = tracer_pose(sc.camera(i, 10))
+        cam = nat.Camera()
+        cam.width, cam.height = sc.width, sc.height
+        cam.principal[:] = [sc.cx, sc.cy]
+        cam.focal[:] = [sc.fx, sc.fy]
+        cam.pose_start[:] = [float(v) for v in pose]
+        cam.pose_end[:] = [float(v) for v in pose]
+        return cam
+
+    n, hw = sc.n, sc.width * sc.height
+    rgba, dist, hits, vis = (np.zeros((hw, 4), np.float32), np.zeros(hw, np.float32), np.zeros(hw, np.float32), np.zeros(n, np.float32))
+    ro, rd = sc.rays()
+    ro, rd = np.ascontiguousarray(ro), np.ascontiguousarray(rd)
+    p = lambda a: a.ctypes.data  # noqa: E731
+    ctx.forward_host(camera(1), n, p(sc.particles), p(sc.sph), 3, p(ro), p(rd), p(rgba), p(dist), p(hits), p(vis))
+    dp, ds = np.zeros((n, 12), np.float32), np.zeros((n, 48), np.float32)
+    d_rgba, d_dist = np.ones((hw, 4), np.float32), np.zeros(hw, np.float32)
+    with pytest.raises(RuntimeError, match="differs from the immediately preceding forward"):
+        ctx.backward_host(camera(2), n, p(sc.particles), p(sc.sph), 3, p(ro), p(rd), p(rgba), p(d_rgba), p(dist), p(d_dist), p(dp), p(ds))
+    ctx.backward_host(camera(1), n, p(sc.particles), p(sc.sph), 3, p(ro), p(rd), p(rgba), p(d_rgba), p(dist), p(d_dist), p(dp), p(ds))
+    assert np.abs(dp).sum() > 0
+    ctx.close()
+
+
 def test_compact_exchange_rebuilds_the_sh_gradient():
     """View-parallel exchange (gutb200_backward_compact + gutb200_sph_grad_from_views): the SH gradient rebuilt from the [N,4]
     radiance gradients of two views equals the sum of the two views' full [N,48] gradients, and d_particles is unchanged."""
