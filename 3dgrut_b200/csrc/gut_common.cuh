@@ -49,9 +49,11 @@ struct __align__(16) ProjRecord {
     float ca, cb, cc, op;
 };
 
-// Gradient accumulator row (64 B): one coalesced vector RED per (warp, particle).
-//   0..2 pos, 3 density, 4..7 quat(wxyz), 8..10 scale, 11 pad, 12..14 precomputed-rgb grad, 15 pad
-constexpr int kGradRow = 16;
+// Gradient accumulator row (80 B), filled with vector REDs by G7 and consumed + re-zeroed by G8.
+//   unsorted 3DGUT (canonical sums, gut_render.cu "G7 backward"): 0..2 sum groGrd, 3 density, 4..12 W (3x3 row-major), 13..15 rgb,
+//                                                                  16..18 depth branch's direct scale part, 19 pad
+//   sorted k-buffer (final gradients): 0..2 pos, 3 density, 4..7 quat(wxyz), 8..10 scale, 11 pad, 12..14 rgb, 15..19 pad
+constexpr int kGradRow = 20;
 
 void launch_project(cudaStream_t s, const FrameCamera& cam, const FrameConfig& cfg, int64_t n, const float* particles,
                     const float* sph, int sph_degree, uint32_t* tiles_count, ProjRecord* proj, float* depth, float* rgb,

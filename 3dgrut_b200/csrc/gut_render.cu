@@ -406,20 +406,27 @@ __global__ void __launch_bounds__(kTilePixels) render_forward_kernel(FrameCamera
 //
 // What is summed per particle, and where: with gro = S^-1 R (o - mu) and grdu = S^-1 R d the hand adjoint
 // (gaussianParticles.cuh:684-747) ends in terms that are LINEAR in per-particle constants once the ray origin is fixed:
-//     d pos   = -R^T (S^-1 groGrd)                      d scale_i = <per-pair part>_i - gro_i (S^-1 groGrd)_i
+//     d pos   = -R^T (S^-1 groGrd)
+//     d scale_i = <depth part>_i - grdu_i (S^-1 grduGrd)_i - gro_i (S^-1 groGrd)_i
 //     d quat  = J(q)^T vec( (S^-1 groGrd) (o - mu)^T + (S^-1 grduGrd) d^T )
-// The kernel therefore accumulates, per particle, the canonical sums  G = sum groGrd (slots 0..2),  the per-pair scale part
-// (slots 8..10) and the quaternion contraction of the d-dependent outer product only (slots 4..7), all relative to the FRAME origin
-// o_f = origin of the frame's first ray; G8 (project_backward_kernel<.., CANON = true>) applies the three linear maps once per
+// and grdu_i = (R d)_i / s_i, so both the scale term and the quaternion term are contractions of the 3x3 matrix
+//     W = sum over the particle's (pixel, hit) pairs of  grduGrd (x) d   (+ groGrd (x) (o - o_f) for pixels off the frame origin):
+//     d scale_i -= (R_i . W_i) / s_i^2,      d quat = J(q)^T vec( S^-1 (W + G (o_f - mu)^T) ).
+// The kernel therefore accumulates, per particle, the canonical sums  G = sum groGrd (slots 0..2), W (slots 4..12, row-major) and the
+// depth branch's direct scale part (slots 16..18; only warps whose pixels carry a distance gradient touch them), all relative to the
+// FRAME origin o_f = origin of the frame's first ray; G8 (project_backward_kernel<.., CANON = true>) applies the linear maps once per
 // particle instead of once per (pixel, particle).  Pixels whose origin differs from o_f (GENERAL tiles: per-pixel origins) add the
 // exact correction terms, so the result is the reference's gradient for any ray bundle.
+// Without a distance gradient the adjoint of normalize() collapses: grdGrd = gro x k and groGrd = k x grd with k parallel to grd x gro
+// give  grduGrd = (-(grd . gro) / |grdu|) groGrd  exactly, so the cross product, the dot product and the three-term normalisation
+// adjoint of (:684-731) are one multiply; the terms that cancel analytically there (grd |gro|^2) are never formed.
 //
-// staged record, 7 x float4:
+// staged record, 6 x float4:
 //   r0, r1, r2 = rows of quaternionWXYZToMatrix (columns of R); .w = canonical frame origin S^-1 R (o_f - mu) (FAST) | position (GENERAL)
-//   sc = scale.xyz, density     is = 1/scale.xyz, _     qt = quat wxyz     cl = clamped rgb, particle index bits
+//   sc = scale.xyz, density     is = 1/scale.xyz, _     cl = clamped rgb, particle index bits
 
 struct BwdSmem {
-    float4 r0[kBatch], r1[kBatch], r2[kBatch], sc[kBatch], is[kBatch], qt[kBatch], cl[kBatch];
+    float4 r0[kBatch], r1[kBatch], r2[kBatch], sc[kBatch], is[kBatch], cl[kBatch];
     uint32_t hw[(kBatch / 32) * kWordsPerChunk];  // the forward's hit words of this batch, [chunk][warp][quarter]
 };
 
@@ -458,6 +465,22 @@ __device__ __forceinline__ void sub_reduce16(float (&v)[16], int lane) {
     }
 }
 
+// plain sum over the lanes of a sub-block (every lane receives it) and the lane that writes it
+template <int SUBL>
+__device__ __forceinline__ float sub_sum(float v) {
+    if (SUBL >= 16) v += __shfl_xor_sync(kFull, v, 16);
+    v += __shfl_xor_sync(kFull, v, 8);
+    if (SUBL == 32) v += __shfl_xor_sync(kFull, v, 4);
+    v += __shfl_xor_sync(kFull, v, 2);
+    v += __shfl_xor_sync(kFull, v, 1);
+    return v;
+}
+
+template <int SUBL>
+__device__ __forceinline__ bool sub_leader(int lane) {
+    return SUBL == 32 ? lane == 0 : SUBL == 16 ? (lane & 27) == 0 : (lane & 11) == 0;
+}
+
 template <int SUBL>
 __device__ __forceinline__ int sub_component(int lane) {
     if (SUBL == 32) return lane >> 1;
@@ -474,7 +497,7 @@ struct BwdRay {
 // exact test + adjoint of one (pixel, staged entry j) pair (processHitBwd, gaussianParticles.cuh:484-751); fills g[] and returns true on a hit
 template <int DEG, bool FAST>
 __device__ __forceinline__ bool backward_pair(const FrameConfig& cfg, const BwdSmem& sm, int j, const Ray& ray, float dox, float doy, float doz,
-                                              bool depth_grads, BwdRay& st, bool& alive, float (&g)[16]) {
+                                              bool depth_grads, BwdRay& st, bool& alive, float (&g)[16], float (&ex)[3]) {
     const float4 r0 = sm.r0[j], r1 = sm.r1[j], r2 = sm.r2[j], sc = sm.sc[j], is = sm.is[j];
     float gox, goy, goz;                                                                          // gro
     float pcx = 0.f, pcy = 0.f, pcz = 0.f;
@@ -526,7 +549,7 @@ __device__ __forceinline__ bool backward_pair(const FrameConfig& cfg, const BwdS
     const float resT = alpha < 0.999999f ? st.Tint / (1.f - alpha) : T;
     const float a_dns = resT * -st.Tgrad;
     // radiance branch (:602-612)
-    g[12] = st.Cgx * weight; g[13] = st.Cgy * weight; g[14] = st.Cgz * weight;
+    g[13] = st.Cgx * weight; g[14] = st.Cgy * weight; g[15] = st.Cgz * weight;
     st.Cx += weight * cl.x; st.Cy += weight * cl.y; st.Cz += weight * cl.z;
     const float rcx = fmaxf((st.Cix - st.Cx) * inv_next, 0.f);
     const float rcy = fmaxf((st.Ciy - st.Cy) * inv_next, 0.f);
@@ -536,43 +559,32 @@ __device__ __forceinline__ bool backward_pair(const FrameConfig& cfg, const BwdS
     const float gray_g = kernel_response_grad<DEG>(gray, gres, dns * common);                       // (:639-648)
     // gray = |grd x gro|^2  (:684-702)
     const float kx = 2.f * ccx * gray_g, ky = 2.f * ccy * gray_g, kz = 2.f * ccz * gray_g;          // gcrodGrd
-    float gd_gx = kz * goy - ky * goz, gd_gy = kx * goz - kz * gox, gd_gz = ky * gox - kx * goy;    // grdGrd
     float go_gx = ky * gdz - kz * gdy, go_gy = kz * gdx - kx * gdz, go_gz = kx * gdy - ky * gdx;    // groGrd
-    if (depth_grads) {                                                                              // + grdRayHitGrd, groRayHitGrd
-        gd_gx += sc.x * hgx * pd - gox * sd; gd_gy += sc.y * hgy * pd - goy * sd; gd_gz += sc.z * hgz * pd - goz * sd;
+    float ug_x, ug_y, ug_z;                                                                         // grduGrd
+    if (depth_grads) {
+        // + grdRayHitGrd = S grdsRayHitGrd pd - gro sd, groRayHitGrd = -grd sd (:560-580), then grd = normalize(grdu) (:729-731): with
+        // P = k x grd (the groGrd above) the projection (I - grd grd^T) of grdGrd = gro x k + S hg pd - gro sd is, term by term,
+        // pd P,  pd (S hg - grd sd)  and  -sd (gro + pd grd), i.e.  grduGrd = (pd (P + S hg - 2 sd grd) - sd gro) / |grdu|
+        const float sd2 = 2.f * sd;
+        const float vx = (go_gx + sc.x * hgx) - sd2 * gdx, vy = (go_gy + sc.y * hgy) - sd2 * gdy, vz = (go_gz + sc.z * hgz) - sd2 * gdz;
+        ug_x = il * (pd * vx - sd * gox); ug_y = il * (pd * vy - sd * goy); ug_z = il * (pd * vz - sd * goz);
         go_gx -= gdx * sd; go_gy -= gdy * sd; go_gz -= gdz * sd;
+        ex[0] = ddx * hgx; ex[1] = ddy * hgy; ex[2] = ddz * hgz;                                     // gsclRayHitGrd (:705-713)
+    } else {  // the same chain in closed form (section comment): grduGrd = (pd / |grdu|) groGrd
+        const float tq = pd * il;
+        ug_x = tq * go_gx; ug_y = tq * go_gy; ug_z = tq * go_gz;
     }
     g[0] = go_gx; g[1] = go_gy; g[2] = go_gz;          // canonical: G8 turns the sums into d pos, the gro part of d scale and of d quat
-    // grd = normalize(grdu)  (:729-731, safe_normalize_bw mathUtils.cuh:410-420)
-    const float il3 = il * il * il;
-    const float du = gd_gx * ux + gd_gy * uy + gd_gz * uz;
-    const float ug_x = l > 0.f ? il * gd_gx - il3 * ux * du : 0.f;                                  // grduGrd
-    const float ug_y = l > 0.f ? il * gd_gy - il3 * uy * du : 0.f;
-    const float ug_z = l > 0.f ? il * gd_gz - il3 * uz * du : 0.f;
-    // grdu = (1/s) rayDirR  (:733-738)
-    const float rdg_x = is.x * ug_x, rdg_y = is.y * ug_y, rdg_z = is.z * ug_z;                      // rayDirRGrd
-    float sgx = ddx * hgx - ux * rdg_x, sgy = ddy * hgy - uy * rdg_y, sgz = ddz * hgz - uz * rdg_z; // gsclRayHitGrd, rayDirR/s^2 = grdu/s
-    // rotation rows receive dM_i = rdg_i * d  (+ prg_i * (o - o_f) for pixels off the frame origin; the o_f - mu part is G8's)
-    float m00 = rdg_x * ray.dx, m01 = rdg_x * ray.dy, m02 = rdg_x * ray.dz;
-    float m10 = rdg_y * ray.dx, m11 = rdg_y * ray.dy, m12 = rdg_y * ray.dz;
-    float m20 = rdg_z * ray.dx, m21 = rdg_z * ray.dy, m22 = rdg_z * ray.dz;
+    // W rows: grduGrd_i * d  (+ groGrd_i * (o - o_f) for pixels off the frame origin); G8 scales row i by 1/s_i (rayDirRGrd, gposcrGrd)
+    // and contracts it with R for d scale (:733-738) and with the quaternion Jacobian for d quat (matmul_bw_quat, :719-747)
+    g[4] = ug_x * ray.dx; g[5] = ug_x * ray.dy; g[6] = ug_x * ray.dz;
+    g[7] = ug_y * ray.dx; g[8] = ug_y * ray.dy; g[9] = ug_y * ray.dz;
+    g[10] = ug_z * ray.dx; g[11] = ug_z * ray.dy; g[12] = ug_z * ray.dz;
     if (!FAST) {
-        const float prg_x = is.x * go_gx, prg_y = is.y * go_gy, prg_z = is.z * go_gz;               // gposcrGrd
-        // gro(pixel) - gro(frame) = S^-1 R (o - o_f)
-        sgx -= is.x * (r0.x * dox + r0.y * doy + r0.z * doz) * prg_x;
-        sgy -= is.y * (r1.x * dox + r1.y * doy + r1.z * doz) * prg_y;
-        sgz -= is.z * (r2.x * dox + r2.y * doy + r2.z * doz) * prg_z;
-        m00 += prg_x * dox; m01 += prg_x * doy; m02 += prg_x * doz;
-        m10 += prg_y * dox; m11 += prg_y * doy; m12 += prg_y * doz;
-        m20 += prg_z * dox; m21 += prg_z * doy; m22 += prg_z * doz;
+        g[4] += go_gx * dox; g[5] += go_gx * doy; g[6] += go_gx * doz;
+        g[7] += go_gy * dox; g[8] += go_gy * doy; g[9] += go_gy * doz;
+        g[10] += go_gz * dox; g[11] += go_gz * doy; g[12] += go_gz * doz;
     }
-    g[8] = sgx; g[9] = sgy; g[10] = sgz;
-    const float4 q = sm.qt[j];                                                                      // matmul_bw_quat (:719-747)
-    const float qr = q.x, qx = q.y, qy = q.z, qz = q.w;
-    g[4] = 2.f * (qz * (m01 - m10) + qy * (m20 - m02) + qx * (m12 - m21));
-    g[5] = 2.f * (qy * (m01 + m10) + qz * (m02 + m20) + qr * (m12 - m21)) - 4.f * qx * (m11 + m22);
-    g[6] = 2.f * (qx * (m01 + m10) + qr * (m20 - m02) + qz * (m12 + m21)) - 4.f * qy * (m00 + m22);
-    g[7] = 2.f * (qr * (m01 - m10) + qx * (m02 + m20) + qy * (m12 + m21)) - 4.f * qz * (m00 + m11);
     st.T = nextT;
     if (nextT < cfg.min_transmittance) alive = false;
     return true;
@@ -619,7 +631,6 @@ __device__ __forceinline__ void backward_tile(const FrameConfig& cfg, BwdSmem& s
             sm.r2[tid] = t2;
             sm.sc[tid] = make_float4(s.x, s.y, s.z, a.w);
             sm.is[tid] = make_float4(1.0f / s.x, 1.0f / s.y, 1.0f / s.z, 0.f);
-            sm.qt[tid] = q;
             sm.cl[tid] = make_float4(fmaxf(rgb[idx * 3 + 0], 0.f), fmaxf(rgb[idx * 3 + 1], 0.f), fmaxf(rgb[idx * 3 + 2], 0.f),
                                      __uint_as_float(idx));
         }
@@ -640,14 +651,21 @@ __device__ __forceinline__ void backward_tile(const FrameConfig& cfg, BwdSmem& s
                 const bool act = todo != 0u;
                 const int j = act ? c + __ffs(todo) - 1 : c;
                 todo &= todo - 1;
-                float g[16];
+                float g[16], ex[3];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) g[i] = 0.f;
+                ex[0] = ex[1] = ex[2] = 0.f;
                 bool hit = false;
-                if (act && alive) hit = backward_pair<DEG, FAST>(cfg, sm, j, ray, dox, doy, doz, depth_grads, st, alive, g);
+                if (act && alive) hit = backward_pair<DEG, FAST>(cfg, sm, j, ray, dox, doy, doz, depth_grads, st, alive, g, ex);
                 const unsigned hits = __ballot_sync(kFull, hit);
                 if (hits) {
                     sub_reduce16<SUBL>(g, lane);
+                    if (depth_grads) {  // warp-uniform: the depth branch's direct scale part, slots 16..18 of the row
+                        ex[0] = sub_sum<SUBL>(ex[0]); ex[1] = sub_sum<SUBL>(ex[1]); ex[2] = sub_sum<SUBL>(ex[2]);
+                        if ((hits & sub_lanes) && sub_leader<SUBL>(lane))
+                            atomicAdd(reinterpret_cast<float4*>(grad_acc + static_cast<size_t>(__float_as_uint(sm.cl[j].w)) * kGradRow + 16),
+                                      make_float4(ex[0], ex[1], ex[2], 0.f));
+                    }
                     if (hits & sub_lanes) {  // this sub-block's particle received something
                         float* row = grad_acc + static_cast<size_t>(__float_as_uint(sm.cl[j].w)) * kGradRow + comp;
                         if (SUBL == 32) {
@@ -747,20 +765,22 @@ __constant__ float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.457045
 // d_sph rows, the d_particles rows and the re-zeroed accumulator rows (every output row is written, zeros for invisible
 // particles, so the caller needs no memset).  Threads only touch shared memory, with 128-bit accesses.
 constexpr int kPbThreads = 128;
+constexpr int kAccVec = kGradRow / 4;          // float4 per accumulator row
+constexpr uint32_t kAccBytes = kGradRow * 4;  // bytes per accumulator row
 
 // COMPACT (view-parallel training): instead of the [N,48] SH gradient row the kernel emits the masked radiance gradient (3 floats) the
 // row is the outer product of -- d_sph[j][c] = basis_j(direction) * g[c] -- so ranks exchange 16 instead of 192 bytes per particle and
 // rebuild the summed rows with sph_from_views_kernel.
-// CANON: the accumulator rows hold G7's canonical sums (see the G7 section comment): slots 0..2 = sum groGrd, 8..10 = per-pair part of
-// d scale, 4..7 = quaternion contraction of the direction-dependent outer products; the three per-particle linear maps are applied here.
-// (The sorted k-buffer kernels still accumulate final gradients: CANON = false.)
+// CANON: the accumulator rows (kGradRow = 20 floats) hold G7's canonical sums (see the G7 section comment): slots 0..2 = G = sum groGrd,
+// 3 = d density, 4..12 = W (row-major), 13..15 = d rgb, 16..18 = the depth branch's direct part of d scale; the per-particle linear maps
+// are applied here.  (The sorted k-buffer kernels still accumulate final gradients: CANON = false, slots 0..10 + rgb in 12..14.)
 template <bool COMPACT, bool CANON>
 __global__ void __launch_bounds__(kPbThreads) project_backward_kernel(FrameCamera cam, int64_t n, const float* __restrict__ particles,
                                                                       const float* __restrict__ sph, int deg, const float* __restrict__ rgb,
                                                                       const uint32_t* __restrict__ tiles_count, const float* __restrict__ rays_o,
                                                                       float* __restrict__ grad_acc, float* __restrict__ d_particles,
                                                                       float* __restrict__ d_sph) {
-    __shared__ __align__(128) float4 s_acc[kPbThreads * 4];   // in: accumulator rows, out: zeros
+    __shared__ __align__(128) float4 s_acc[kPbThreads * kAccVec];   // in: accumulator rows, out: zeros
     __shared__ __align__(128) float4 s_sh[kPbThreads * 12];   // in: SH coefficients, out: d_sph rows
     __shared__ __align__(128) float4 s_dp[kPbThreads * 3];    // out: d_particles rows
     __shared__ __align__(8) uint64_t s_bar;
@@ -776,8 +796,8 @@ __global__ void __launch_bounds__(kPbThreads) project_backward_kernel(FrameCamer
     const bool in_range = tid < cnt;
     const bool vis = in_range && (tiles_count[i] != 0u);
     const bool want_sh = vis && (deg > 0);
-    mbar_expect_tx(&s_bar, (tid == 0 ? static_cast<uint32_t>(cnt) * 64u : 0u) + (want_sh ? 192u : 0u));
-    if (tid == 0) tma_bulk_g2s(s_acc, grad_acc + base * kGradRow, static_cast<uint32_t>(cnt) * 64u, &s_bar);
+    mbar_expect_tx(&s_bar, (tid == 0 ? static_cast<uint32_t>(cnt) * kAccBytes : 0u) + (want_sh ? 192u : 0u));
+    if (tid == 0) tma_bulk_g2s(s_acc, grad_acc + base * kGradRow, static_cast<uint32_t>(cnt) * kAccBytes, &s_bar);
     if (want_sh) tma_bulk_g2s(s_sh + tid * 12, sph + i * 48, 192u, &s_bar);
     // overlap the remaining scalar loads with the bulk copies
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f), pq = p, ps = p;
@@ -802,33 +822,45 @@ __global__ void __launch_bounds__(kPbThreads) project_backward_kernel(FrameCamer
 
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     if (in_range) {
-        float4 a0 = s_acc[tid * 4 + 0], a1 = s_acc[tid * 4 + 1], a2 = s_acc[tid * 4 + 2];
-        const float4 a3 = s_acc[tid * 4 + 3];
-        s_acc[tid * 4 + 0] = zero; s_acc[tid * 4 + 1] = zero; s_acc[tid * 4 + 2] = zero; s_acc[tid * 4 + 3] = zero;
-        if (CANON && vis) {
-            const float r = pq.x, x = pq.y, y = pq.z, z = pq.w;
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
-            const float rx = r * x, ry = r * y, rz = r * z;
-            const float r0x = 1.f - 2.f * (yy + zz), r0y = 2.f * (xy + rz), r0z = 2.f * (xz - ry);
-            const float r1x = 2.f * (xy - rz), r1y = 1.f - 2.f * (xx + zz), r1z = 2.f * (yz + rx);
-            const float r2x = 2.f * (xz + ry), r2y = 2.f * (yz - rx), r2z = 1.f - 2.f * (xx + yy);
-            const float isx = 1.0f / ps.x, isy = 1.0f / ps.y, isz = 1.0f / ps.z;
-            const float pcx = ofx - p.x, pcy = ofy - p.y, pcz = ofz - p.z;                      // gposc of the frame origin
-            const float gox = isx * (r0x * pcx + r0y * pcy + r0z * pcz);                        // gro of the frame origin
-            const float goy = isy * (r1x * pcx + r1y * pcy + r1z * pcz);
-            const float goz = isz * (r2x * pcx + r2y * pcy + r2z * pcz);
-            const float prx = isx * a0.x, pry = isy * a0.y, prz = isz * a0.z;                   // gposcrGrd = S^-1 sum groGrd
-            a0.x = -(prx * r0x + pry * r1x + prz * r2x);                                        // gposcr = R gposc  (gaussianParticles.cuh:715-726)
-            a0.y = -(prx * r0y + pry * r1y + prz * r2y);
-            a0.z = -(prx * r0z + pry * r1z + prz * r2z);
-            a2.x -= gox * prx; a2.y -= goy * pry; a2.z -= goz * prz;                            // gposcr/s^2 = gro/s  (:705-713)
-            const float m00 = prx * pcx, m01 = prx * pcy, m02 = prx * pcz;                      // matmul_bw_quat (:719-726)
-            const float m10 = pry * pcx, m11 = pry * pcy, m12 = pry * pcz;
-            const float m20 = prz * pcx, m21 = prz * pcy, m22 = prz * pcz;
-            a1.x += 2.f * (z * (m01 - m10) + y * (m20 - m02) + x * (m12 - m21));
-            a1.y += 2.f * (y * (m01 + m10) + z * (m02 + m20) + r * (m12 - m21)) - 4.f * x * (m11 + m22);
-            a1.z += 2.f * (x * (m01 + m10) + r * (m20 - m02) + z * (m12 + m21)) - 4.f * y * (m00 + m22);
-            a1.w += 2.f * (r * (m01 - m10) + x * (m02 + m20) + y * (m12 + m21)) - 4.f * z * (m00 + m11);
+        float4 a0 = s_acc[tid * kAccVec + 0], a1 = s_acc[tid * kAccVec + 1], a2 = s_acc[tid * kAccVec + 2];
+        float4 a3 = s_acc[tid * kAccVec + 3];
+        const float4 a4 = s_acc[tid * kAccVec + 4];
+#pragma unroll
+        for (int k = 0; k < kAccVec; ++k) s_acc[tid * kAccVec + k] = zero;
+        if (CANON) {
+            const float w00 = a1.x, w01 = a1.y, w02 = a1.z, w10 = a1.w, w11 = a2.x, w12 = a2.y, w20 = a2.z, w21 = a2.w, w22 = a3.x;
+            a3 = make_float4(a3.y, a3.z, a3.w, 0.f);                                            // d rgb to the legacy position
+            a1 = zero;
+            a2 = zero;
+            if (vis) {
+                const float r = pq.x, x = pq.y, y = pq.z, z = pq.w;
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z;
+                const float rx = r * x, ry = r * y, rz = r * z;
+                const float r0x = 1.f - 2.f * (yy + zz), r0y = 2.f * (xy + rz), r0z = 2.f * (xz - ry);
+                const float r1x = 2.f * (xy - rz), r1y = 1.f - 2.f * (xx + zz), r1z = 2.f * (yz + rx);
+                const float r2x = 2.f * (xz + ry), r2y = 2.f * (yz - rx), r2z = 1.f - 2.f * (xx + yy);
+                const float isx = 1.0f / ps.x, isy = 1.0f / ps.y, isz = 1.0f / ps.z;
+                const float pcx = ofx - p.x, pcy = ofy - p.y, pcz = ofz - p.z;                      // gposc of the frame origin
+                const float gox = isx * (r0x * pcx + r0y * pcy + r0z * pcz);                        // gro of the frame origin
+                const float goy = isy * (r1x * pcx + r1y * pcy + r1z * pcz);
+                const float goz = isz * (r2x * pcx + r2y * pcy + r2z * pcz);
+                const float prx = isx * a0.x, pry = isy * a0.y, prz = isz * a0.z;                   // gposcrGrd = S^-1 sum groGrd
+                a0.x = -(prx * r0x + pry * r1x + prz * r2x);                                        // gposcr = R gposc  (gaussianParticles.cuh:715-726)
+                a0.y = -(prx * r0y + pry * r1y + prz * r2y);
+                a0.z = -(prx * r0z + pry * r1z + prz * r2z);
+                // d scale: depth part - grdu_i rayDirRGrd_i (= (R_i . W_i) / s_i^2, :733-738) - gro_i gposcrGrd_i (gposcr/s^2 = gro/s, :705-713)
+                a2.x = a4.x - isx * isx * (r0x * w00 + r0y * w01 + r0z * w02) - gox * prx;
+                a2.y = a4.y - isy * isy * (r1x * w10 + r1y * w11 + r1z * w12) - goy * pry;
+                a2.z = a4.z - isz * isz * (r2x * w20 + r2y * w21 + r2z * w22) - goz * prz;
+                // rotation rows receive  rayDirRGrd_i d + gposcrGrd_i (o - mu) = (W_i + G_i (o_f - mu)) / s_i;  matmul_bw_quat (:719-747)
+                const float m00 = isx * w00 + prx * pcx, m01 = isx * w01 + prx * pcy, m02 = isx * w02 + prx * pcz;
+                const float m10 = isy * w10 + pry * pcx, m11 = isy * w11 + pry * pcy, m12 = isy * w12 + pry * pcz;
+                const float m20 = isz * w20 + prz * pcx, m21 = isz * w21 + prz * pcy, m22 = isz * w22 + prz * pcz;
+                a1.x = 2.f * (z * (m01 - m10) + y * (m20 - m02) + x * (m12 - m21));
+                a1.y = 2.f * (y * (m01 + m10) + z * (m02 + m20) + r * (m12 - m21)) - 4.f * x * (m11 + m22);
+                a1.z = 2.f * (x * (m01 + m10) + r * (m20 - m02) + z * (m12 + m21)) - 4.f * y * (m00 + m22);
+                a1.w = 2.f * (r * (m01 - m10) + x * (m02 + m20) + y * (m12 + m21)) - 4.f * z * (m00 + m11);
+            }
         }
         float dpx = a0.x, dpy = a0.y, dpz = a0.z;
         float4* row = s_sh + tid * 12;
@@ -909,7 +941,7 @@ __global__ void __launch_bounds__(kPbThreads) project_backward_kernel(FrameCamer
         else
             tma_bulk_s2g(d_sph + base * 48, s_sh, static_cast<uint32_t>(cnt) * 192u);
         tma_bulk_s2g(d_particles + base * 12, s_dp, static_cast<uint32_t>(cnt) * 48u);
-        tma_bulk_s2g(grad_acc + base * kGradRow, s_acc, static_cast<uint32_t>(cnt) * 64u);
+        tma_bulk_s2g(grad_acc + base * kGradRow, s_acc, static_cast<uint32_t>(cnt) * kAccBytes);
         tma_commit_group();
         tma_wait_group_read0();  // shared memory must stay valid until the engine has read it
     }

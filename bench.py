@@ -598,7 +598,7 @@ def run_grt(args, rank, local_rank, world, dev, dist, sub=False):
         dist.destroy_process_group()
 
 
-def gut_device_loop(torch, dist, args, rank, world, dev, workload, steps, warmup, stage_pass=True):
+def gut_device_loop(torch, dist, args, rank, world, dev, workload, steps, warmup, stage_pass=True, zero_dist_grad=False):
     """Device-timed 3DGUT loop on one workload: `warmup` untimed + `steps` timed view-steps per rank (one view forward + backward each), L2
     flushed between steps, per-step CUDA events, MAX over ranks.  With world > 1 every rank renders a different camera and the gradients are
     summed every `--accumulate` view-steps (a step's batch = accumulate x world views): `compact` all-gathers each
@@ -624,6 +624,8 @@ def gut_device_loop(torch, dist, args, rank, world, dev, workload, steps, warmup
     gen = torch.Generator(device=dev).manual_seed(1234)
     d_rgba = torch.randn((H, W, 4), device=dev, generator=gen)
     d_dist = 0.05 * torch.randn((H, W, 1), device=dev, generator=gen)
+    if zero_dist_grad:  # what autograd hands trace_bwd when the loss does not use pred_dist (the reference's default training loss)
+        d_dist = torch.zeros_like(d_dist)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
     V = max(1, args.accumulate) if world > 1 else 1
 
@@ -750,6 +752,7 @@ def main():
     ap.add_argument("--accumulate", type=int, default=4,
                     help="multi-GPU: view-steps per rank between two gradient exchanges (a batch = accumulate x world views); ignored at N=1")
     ap.add_argument("--profile-host", default=None, help="write a cProfile of the end-to-end loop's host side to this file (diagnostic; the e2e number of such a run is not a bench value)")
+    ap.add_argument("--sub-records", default="train_default,c3,c4", help="which sub-records the default c2 line carries (comma list)")
     ap.add_argument("--no-sub-records", action="store_true", help="skip the c3 (6M Gaussians) and c4 (3DGRT) sub-records of the default c2 line")
     args = ap.parse_args()
 
@@ -902,14 +905,25 @@ def main():
     if args.workload == "c2" and not args.no_sub_records:
         del main_run, o, tracer, raster, ctx, particles, sph, rays_o, rays_d, d_rgba, d_dist, flush, feed, _G, grads
         torch.cuda.empty_cache()
-        c3 = gut_device_loop(torch, dist, args, rank, world, dev, "c3", steps=max(2 * args.accumulate, 12), warmup=4, stage_pass=True)
-        sub_records["c3"] = {"workload": c3["objs"]["sc"].name, "value": c3["value"], "unit": UNIT, "n_gpus": world, "steps": c3["steps"],
-                             "ms_per_step": c3["total_ms"] / c3["steps"], "stage_ms": c3["stage_ms"], "exchange": c3["exchange"],
-                             "N": c3["stats"]["N"], "V": c3["stats"]["V"], "I": c3["stats"]["I"], "T": c3["stats"]["T"],
-                             "note": "BASELINE configs[2]: 6M Gaussians, 1237x822; same loop, timing and exchange as the headline, fewer steps"}
-        del c3
-        torch.cuda.empty_cache()
-        if world == 1:
+        want_sub = set(args.sub_records.split(","))
+        if world == 1 and "train_default" in want_sub:
+            td = gut_device_loop(torch, dist, args, rank, world, dev, "c2", steps=min(args.steps, 50), warmup=5, stage_pass=True, zero_dist_grad=True)
+            sub_records["train_default"] = {"workload": td["objs"]["sc"].name, "value": td["value"], "unit": UNIT, "steps": td["steps"],
+                                            "ms_per_step": td["total_ms"] / td["steps"], "stage_ms": td["stage_ms"],
+                                            "note": "the headline loop with a ZERO distance gradient (a loss on rgb / opacity only, the reference's default "
+                                                    "training loss): renderBackward then skips the depth branch of the adjoint; `value` keeps random "
+                                                    "gradients on every output (rgba and distance), the harder case"}
+            del td
+            torch.cuda.empty_cache()
+        if "c3" in want_sub:
+            c3 = gut_device_loop(torch, dist, args, rank, world, dev, "c3", steps=max(2 * args.accumulate, 12), warmup=4, stage_pass=True)
+            sub_records["c3"] = {"workload": c3["objs"]["sc"].name, "value": c3["value"], "unit": UNIT, "n_gpus": world, "steps": c3["steps"],
+                                 "ms_per_step": c3["total_ms"] / c3["steps"], "stage_ms": c3["stage_ms"], "exchange": c3["exchange"],
+                                 "N": c3["stats"]["N"], "V": c3["stats"]["V"], "I": c3["stats"]["I"], "T": c3["stats"]["T"],
+                                 "note": "BASELINE configs[2]: 6M Gaussians, 1237x822; same loop, timing and exchange as the headline, fewer steps"}
+            del c3
+            torch.cuda.empty_cache()
+        if world == 1 and "c4" in want_sub:
             sub_records["c4"] = run_grt(args, rank, local_rank, world, dev, dist, sub=True)
 
     if rank == 0:
