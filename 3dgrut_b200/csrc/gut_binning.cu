@@ -16,6 +16,8 @@
 // The keys are unique inside a tile (a particle enters a tile once), so the result is exactly the reference's order whatever order
 // the atomics claimed the slots in; only sorted artefacts are observable and they stay bit-identical (tests/test_gut_parity_gpu.py).
 // Work: I x 8 B written once, sorted in place on chip; no N-sized depth sort, no scan over N, no multi-pass radix sort over I.
+#include <cstdlib>
+
 #include "gut_common.cuh"
 
 namespace gutb200 {
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int num_tiles, const ui
 constexpr int kSortThreads = 512, kSortWarps = kSortThreads / 32;   // 16 warps per tile: the long lists (6-30 k keys at C3) are latency-bound
 constexpr int kSortUnroll = 4;                                      // keys in flight per lane in the count / scatter loops
 
+template <bool BALLOT>
 __global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ ranges,
                                                                  const uint32_t* __restrict__ totals, unsigned long long* keys,
                                                                  unsigned long long* keys_alt, uint32_t* __restrict__ sorted_values) {
@@ -157,11 +160,14 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(const uint32_t*
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long* src = keys + begin;
     unsigned long long* dst = keys_alt + begin;
-    // warp w owns elements [w * seg, min(n, (w + 1) * seg)), seg a multiple of 32
-    const uint32_t seg = ((n + kSortWarps - 1) / kSortWarps + 31u) & ~31u;
+    // Short lists use fewer warps (>= 128 keys each): the per-pass fixed cost -- zeroing, summing and scanning one counter row per warp --
+    // scales with the warps that take part, and most C2 tiles hold a few hundred keys.
+    const int aw = static_cast<int>(min(static_cast<uint32_t>(kSortWarps), max(1u, (n + 127u) / 128u)));
+    // warp w < aw owns elements [w * seg, min(n, (w + 1) * seg)), seg a multiple of 32
+    const uint32_t seg = ((n + aw - 1) / aw + 31u) & ~31u;
     const uint32_t w0 = min(n, warp * seg), w1 = min(n, w0 + seg);
     for (int shift = 32; shift < 64; shift += 8) {
-        for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0u;
+        for (int i = threadIdx.x; i < aw * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0u;
         if (threadIdx.x == 0) s_flag = 0;
         __syncthreads();
         for (uint32_t i0 = w0; i0 < w1; i0 += 32 * kSortUnroll) {  // digit counts of this warp's segment, kSortUnroll loads in flight
@@ -180,8 +186,7 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(const uint32_t*
         const int d = threadIdx.x;
         uint32_t tot = 0, incl = 0;
         if (d < 256) {
-#pragma unroll
-            for (int w = 0; w < kSortWarps; ++w) tot += s_cnt[w][d];
+            for (int w = 0; w < aw; ++w) tot += s_cnt[w][d];
             if (tot == n) s_flag = 1;   // every key has this digit: the pass would be the identity
             incl = tot;
 #pragma unroll
@@ -196,8 +201,7 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(const uint32_t*
         if (!skip && d < 256) {
             uint32_t run = incl - tot;
             for (int w = 0; w < warp; ++w) run += s_tot[w];
-#pragma unroll
-            for (int w = 0; w < kSortWarps; ++w) {
+            for (int w = 0; w < aw; ++w) {
                 const uint32_t c = s_cnt[w][d];
                 s_cnt[w][d] = run;
                 run += c;
@@ -217,7 +221,19 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(const uint32_t*
                 if (i0 + u * 32 >= w1) break;         // warp-uniform
                 const bool have = i0 + u * 32 + lane < w1;
                 const uint32_t dg = have ? (static_cast<uint32_t>(k[u] >> shift) & 255u) : 256u + lane;  // idle lanes: unique pseudo-digits
-                const unsigned peers = __match_any_sync(kFullMask, dg);
+                unsigned peers;
+                if (BALLOT) {  // lanes with the same 8-bit digit, from one ballot per bit (the multi-split CUB's ranking uses)
+                    peers = __ballot_sync(kFullMask, have);
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        const bool bit = (dg >> b) & 1u;
+                        const unsigned bal = __ballot_sync(kFullMask, bit);
+                        peers &= bit ? bal : ~bal;
+                    }
+                    if (!have) peers = 1u << lane;
+                } else {
+                    peers = __match_any_sync(kFullMask, dg);
+                }
                 const int leader = __ffs(peers) - 1;
                 uint32_t slot = 0;
                 if (have && lane == leader) slot = atomicAdd(&s_cnt[warp][dg], static_cast<uint32_t>(__popc(peers)));
@@ -273,7 +289,11 @@ void launch_tile_scan(cudaStream_t s, int num_tiles, const uint32_t* counts, uin
 cudaError_t launch_tile_sort(cudaStream_t s, int num_tiles, const uint32_t* order, const uint32_t* ranges, const uint32_t* totals,
                              unsigned long long* keys, unsigned long long* keys_alt, uint32_t* sorted_values) {
     if (num_tiles <= 0) return cudaSuccess;
-    tile_sort_kernel<<<num_tiles, kSortThreads, 0, s>>>(order, ranges, totals, keys, keys_alt, sorted_values);
+    static const bool use_match = [] { const char* e = std::getenv("GUTB200_SORT_MATCH"); return e && std::atoi(e) != 0; }();  // A/B switch
+    if (use_match)
+        tile_sort_kernel<false><<<num_tiles, kSortThreads, 0, s>>>(order, ranges, totals, keys, keys_alt, sorted_values);
+    else
+        tile_sort_kernel<true><<<num_tiles, kSortThreads, 0, s>>>(order, ranges, totals, keys, keys_alt, sorted_values);
     return cudaGetLastError();
 }
 
