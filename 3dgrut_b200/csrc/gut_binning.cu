@@ -47,16 +47,27 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int num_tiles, const ui
     const int strip = (num_tiles + static_cast<int>(blockDim.x) - 1) / static_cast<int>(blockDim.x);
     const int t0 = min(static_cast<int>(threadIdx.x) * strip, num_tiles), t1 = min(t0 + strip, num_tiles);
     uint32_t sum_n = 0, sum_c = 0;
-    for (int t = t0; t < t1; ++t) {
-        const uint4* c4 = reinterpret_cast<const uint4*>(counts + static_cast<size_t>(t) * kTileSubs);
-        const uint4 v0 = c4[0], v1 = c4[1], v2 = c4[2], v3 = c4[3];
-        const uint32_t c = (v0.x + v0.y + v0.z + v0.w) + (v1.x + v1.y + v1.z + v1.w) + (v2.x + v2.y + v2.z + v2.w) + (v3.x + v3.y + v3.z + v3.w);
-        sum_n += c;
-        sum_c += (c + 31u) >> 5;
-        atomicAdd(&hist[__clz(c) + 1], 1u);  // __clz(0) = 32 -> last bucket; long lists -> small bucket index
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // The length buckets are few and most tiles fall into two or three of them, so a warp's lanes that land in the same bucket go through
+    // ONE shared-memory atomic (match.any + population count) instead of serialising on its address; the loops are warp-uniform for that.
+    // (Measured at C2: 0.027 ms with or without -- the kernel is bound by the latency of its two dependent passes, not by these atomics.)
+    for (int k = 0; k < strip; ++k) {
+        const int t = t0 + k;
+        const bool live = t < t1;
+        uint32_t c = 0;
+        if (live) {
+            const uint4* c4 = reinterpret_cast<const uint4*>(counts + static_cast<size_t>(t) * kTileSubs);
+            const uint4 v0 = c4[0], v1 = c4[1], v2 = c4[2], v3 = c4[3];
+            c = (v0.x + v0.y + v0.z + v0.w) + (v1.x + v1.y + v1.z + v1.w) + (v2.x + v2.y + v2.z + v2.w) + (v3.x + v3.y + v3.z + v3.w);
+            sum_n += c;
+            sum_c += (c + 31u) >> 5;
+        }
+        const int bucket = live ? __clz(c) + 1 : 64 + lane;  // __clz(0) = 32 -> last bucket; long lists -> small bucket index
+        const unsigned peers = __match_any_sync(kFullMask, bucket);
+        if (live && (peers & lt_mask) == 0u) atomicAdd(&hist[bucket], static_cast<uint32_t>(__popc(peers)));
     }
     uint32_t inc_n = sum_n, inc_c = sum_c;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t a = __shfl_up_sync(kFullMask, inc_n, o), b = __shfl_up_sync(kFullMask, inc_c, o);
@@ -91,45 +102,42 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int num_tiles, const ui
     }
     __syncthreads();
     const bool overflow = s_overflow != 0u;  // the lists do not fit the key buffer: publish empty ranges, the host grows and re-queues
-    // pass 2: per-tile outputs (begin written unconditionally into ranges[2t]; pass 3 reads it back)
+    // pass 2: per-tile outputs.  The thread that owns a tile has its 16 sub-counters at hand (four 16-byte loads, L1 hits after pass 1):
+    // it lays out the sub-buckets itself and writes them with 16-byte stores (a separate coalesced pass over the counters was 2 us).
     uint32_t run_n = warp_a[warp] + inc_n - sum_n, run_c = warp_b[warp] + inc_c - sum_c;
-    for (int t = t0; t < t1; ++t) {
-        const uint4* c4 = reinterpret_cast<const uint4*>(counts + static_cast<size_t>(t) * kTileSubs);
-        const uint4 v0 = c4[0], v1 = c4[1], v2 = c4[2], v3 = c4[3];
-        const uint32_t c = (v0.x + v0.y + v0.z + v0.w) + (v1.x + v1.y + v1.z + v1.w) + (v2.x + v2.y + v2.z + v2.w) + (v3.x + v3.y + v3.z + v3.w);
-        ranges[t * 2] = run_n;   // provisional: the tile's first slot even if it is empty (pass 3 needs it)
-        ranges[t * 2 + 1] = run_n + c;
-        chunk_base[t] = overflow ? 0u : run_c;
-        run_n += c;
-        run_c += (c + 31u) >> 5;
-        order[atomicAdd(&hist[__clz(c) + 1], 1u)] = static_cast<uint32_t>(t);
-    }
-    __syncthreads();
-    // pass 3: first slot of every sub-bucket, coalesced: a half-warp owns one tile, 16 lanes = its 16 sub-counters (the loop is
-    // warp-uniform: both halves of a warp run the same number of iterations, the shuffles name every lane)
-    const int sub = threadIdx.x & 15;
-    for (int tb = (threadIdx.x >> 5) * 2; tb < num_tiles; tb += (static_cast<int>(blockDim.x) >> 5) * 2) {
-        const int t = tb + ((threadIdx.x >> 4) & 1);
-        const bool live = t < num_tiles;
-        const size_t at = static_cast<size_t>(live ? t : 0) * kTileSubs + sub;
-        const uint32_t c = live ? counts[at] : 0u;
-        uint32_t incl = c;
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(kFullMask, incl, o, 16);
-            if (sub >= o) incl += v;
-        }
-        const uint32_t total = __shfl_sync(kFullMask, incl, 15, 16);
+    const uint32_t fill0 = overflow ? 0xC0000000u : 0u;   // a huge fill level makes every claim fall outside its sub-bucket
+    const uint4 fill4 = make_uint4(fill0, fill0, fill0, fill0);
+    for (int k = 0; k < strip; ++k) {
+        const int t = t0 + k;
+        const bool live = t < t1;
+        uint32_t c = 0;
         if (live) {
-            const uint32_t begin = ranges[t * 2];
-            sub_base[at] = begin + incl - c;
-            fill[at] = overflow ? 0xC0000000u : 0u;   // a huge fill level makes every claim fall outside its sub-bucket
+            const uint4* c4 = reinterpret_cast<const uint4*>(counts + static_cast<size_t>(t) * kTileSubs);
+            const uint4 v0 = c4[0], v1 = c4[1], v2 = c4[2], v3 = c4[3];
+            uint32_t r = run_n;
+            uint4 b0, b1, b2, b3;
+            b0.x = r; r += v0.x; b0.y = r; r += v0.y; b0.z = r; r += v0.z; b0.w = r; r += v0.w;
+            b1.x = r; r += v1.x; b1.y = r; r += v1.y; b1.z = r; r += v1.z; b1.w = r; r += v1.w;
+            b2.x = r; r += v2.x; b2.y = r; r += v2.y; b2.z = r; r += v2.z; b2.w = r; r += v2.w;
+            b3.x = r; r += v3.x; b3.y = r; r += v3.y; b3.z = r; r += v3.z; b3.w = r; r += v3.w;
+            c = r - run_n;
+            uint4* sb = reinterpret_cast<uint4*>(sub_base + static_cast<size_t>(t) * kTileSubs);
+            sb[0] = b0; sb[1] = b1; sb[2] = b2; sb[3] = b3;
+            uint4* fl = reinterpret_cast<uint4*>(fill + static_cast<size_t>(t) * kTileSubs);
+            fl[0] = fill4; fl[1] = fill4; fl[2] = fill4; fl[3] = fill4;
+            // empty tile (or nothing fits): (0, 0) like the reference's zero-filled range buffer
+            reinterpret_cast<uint2*>(ranges)[t] = (overflow || c == 0u) ? make_uint2(0u, 0u) : make_uint2(run_n, r);
+            chunk_base[t] = overflow ? 0u : run_c;
+            run_n = r;
+            run_c += (c + 31u) >> 5;
         }
-        __syncwarp();
-        if (live && sub == 0 && (overflow || total == 0u)) {  // empty tile (or nothing fits): (0, 0) like the reference's zero-filled buffer
-            ranges[t * 2] = 0u;
-            ranges[t * 2 + 1] = 0u;
-        }
+        const int bucket = live ? __clz(c) + 1 : 64 + lane;
+        const unsigned peers = __match_any_sync(kFullMask, bucket);
+        const int leader = __ffs(peers) - 1;
+        uint32_t slot = 0;
+        if (live && lane == leader) slot = atomicAdd(&hist[bucket], static_cast<uint32_t>(__popc(peers)));
+        slot = __shfl_sync(kFullMask, slot, leader);
+        if (live) order[slot + __popc(peers & lt_mask)] = static_cast<uint32_t>(t);
     }
 }
 
