@@ -11,9 +11,9 @@
 // shape is fixed by parity), 256 threads = 256 pixels, sorted particle lists consumed in batches staged in
 // shared memory as render-ready records (scale folded into the rotation rows once per staged particle
 // instead of once per pixel test).  Both kernels are FP32/SFU-issue bound, not HBM bound.
-// G7 reduces the 14 per-particle gradient floats across the warp with a 16-value transposing butterfly
-// (16 SHFL instead of 70) and lands them with ONE coalesced 64-byte vector RED per (warp, particle) into a
-// [N,16] accumulator that G8 consumes and re-zeroes.
+// G7 reduces the 16 canonical per-particle sums (section comment "G7 backward") across a quarter of the warp with a
+// 16-value transposing butterfly (14 SHFL) and lands them with one 8-byte vector RED per lane into a [N,20]
+// accumulator that G8 maps to the final gradients and re-zeroes.
 #include "gut_common.cuh"
 #include "hit_math.cuh"
 #include "subtile_cull.cuh"

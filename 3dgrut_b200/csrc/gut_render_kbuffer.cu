@@ -10,7 +10,7 @@
 // (hit_math.cuh: hit_adjoint, restated from models/gaussianParticles.cuh:484-751) is applied in the buffer's processing order, which is
 // the exact gradient of the same forward (the CPU restatement used by the tests checks this against torch autograd).
 // One CTA per 16x16 tile, one thread per pixel; particle records are read through the read-only cache (every thread of the CTA reads the
-// same record); gradients are scattered with four 16-byte vector reductions per processed hit into the [N,16] accumulator G8 consumes.
+// same record); gradients are scattered with four 16-byte vector reductions per processed hit into the [N,20] accumulator (kGradRow floats per row, the first 15 used here) G8 consumes.
 #include "kbuffer_walk.cuh"
 
 namespace gutb200 {
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kTilePixels) render_backward_kbuffer_kernel(Fr
         st.Dint = out_dist[pix];
         st.Dgrad = d_dist[pix];
     }
-    auto scatter = [&](uint32_t idx, const float* g, const float* rg) {  // four 16-byte vector reductions into the [N,16] accumulator
+    auto scatter = [&](uint32_t idx, const float* g, const float* rg) {  // four 16-byte vector reductions into the accumulator row
         float4* row = reinterpret_cast<float4*>(grad_acc + static_cast<size_t>(idx) * kGradRow);
         atomicAdd(row + 0, make_float4(g[0], g[1], g[2], g[3]));
         atomicAdd(row + 1, make_float4(g[4], g[5], g[6], g[7]));
