@@ -172,15 +172,18 @@ class SplatRaster:
         return self._ctx[idx]
 
     def _camera_cached(self, sensor, pose_start, pose_end, width: int, height: int) -> native.Camera:
-        """_camera, re-used when the very same sensor / pose OBJECTS come back (trace -> trace_bwd of one frame); the tuple keeps them alive,
-        so an `is` match cannot be a recycled id.  Callers that mutate a pose array in place between trace and trace_bwd get the reference's
-        behaviour only through _camera -- the C side rejects a backward whose camera differs from the forward's either way."""
+        """_camera, re-used when the very same sensor / pose OBJECTS come back with the same values (trace -> trace_bwd of one frame); the
+        tuple keeps them alive, so an `is` match cannot be a recycled id, and the value snapshot catches a pose array mutated in place in
+        between.  (The C side rejects a backward whose camera differs from the forward's either way.)"""
+        def snap(pose):  # host copy of a pose given as ndarray / sequence / tensor (the reference takes tensors and calls .cpu())
+            return pose.detach().cpu().numpy().copy() if isinstance(pose, torch.Tensor) else np.array(pose, copy=True)
+        ps, pe = snap(pose_start), snap(pose_end)
         last = self._last_camera
         if (last is not None and last[0] is sensor and last[1] is pose_start and last[2] is pose_end and last[3] == width and last[4] == height
-                and np.array_equal(last[6], pose_start) and np.array_equal(last[7], pose_end)):
+                and np.array_equal(last[6], ps) and np.array_equal(last[7], pe)):
             return last[5]
-        cam = self._camera(sensor, pose_start, pose_end, width, height)
-        self._last_camera = (sensor, pose_start, pose_end, width, height, cam, np.array(pose_start, copy=True), np.array(pose_end, copy=True))
+        cam = self._camera(sensor, ps, pe, width, height)
+        self._last_camera = (sensor, pose_start, pose_end, width, height, cam, ps, pe)
         return cam
 
     @staticmethod

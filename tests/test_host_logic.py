@@ -106,3 +106,26 @@ def test_densify_step_schedule_and_optimizer_groups_are_consistent():
     c = densify.DensifyConfig()
     fired = [s for s in range(1, 2001) if densify.check_step_condition(s, c.densify_start, c.densify_end, c.densify_frequency)]
     assert fired == [600, 900, 1200, 1500, 1800]  # configs/strategy/gs.yaml: start 500, every 300
+
+
+def test_camera_struct_is_reused_only_for_the_same_unchanged_frame():
+    """SplatRaster._camera_cached: trace_bwd re-uses trace's native.Camera when the same sensor / pose objects come back unchanged; a new
+    pose object, a pose mutated in place, another resolution or a tensor pose (the reference's binding takes tensors) build a fresh struct."""
+    import torch
+    from threedgut_tracer.tracer import ShutterType, SplatRaster, fromOpenCVPinholeCameraModelParameters
+
+    raster = object.__new__(SplatRaster)  # no CUDA context needed for the host-side struct
+    raster._last_camera = None
+    sensor = fromOpenCVPinholeCameraModelParameters(np.array([64, 48]), ShutterType.GLOBAL, [32, 24], [50, 51], np.zeros(6), np.zeros(2), np.zeros(4))
+    pose = np.array([0.1, 0.2, 0.3, 0, 0, 0, 1], np.float32)
+    a = raster._camera_cached(sensor, pose, pose, 64, 48)
+    assert raster._camera_cached(sensor, pose, pose, 64, 48) is a
+    assert raster._camera_cached(sensor, pose.copy(), pose, 64, 48) is not a            # another object
+    b = raster._camera_cached(sensor, pose, pose, 64, 48)
+    pose[0] = 0.5                                                                         # same object, mutated in place
+    c = raster._camera_cached(sensor, pose, pose, 64, 48)
+    assert c is not b and abs(c.pose_start[0] - 0.5) < 1e-7 and abs(b.pose_start[0] - 0.1) < 1e-7
+    assert raster._camera_cached(sensor, pose, pose, 32, 48) is not c                    # another resolution
+    t = torch.tensor([0.0, 0, 0, 0, 0, 0, 1])
+    d = raster._camera_cached(sensor, t, t, 64, 48)
+    assert raster._camera_cached(sensor, t, t, 64, 48) is d and abs(d.pose_start[6] - 1.0) < 1e-7
