@@ -111,3 +111,46 @@ def test_w_and_g_sums_give_the_per_pair_gradients():
         assert np.allclose(pos, ref_pos, rtol=1e-9, atol=1e-10)
         assert np.allclose(scale, ref_scale, rtol=1e-9, atol=1e-9), (depth, scale, ref_scale)
         assert np.allclose(quat, ref_quat, rtol=1e-9, atol=1e-9), (depth, quat, ref_quat)
+
+
+def test_closed_form_is_at_least_as_accurate_as_the_chain_in_float32():
+    """The claim of DESIGN.md section 4 (item 4): in float32 the closed form grduGrd = (pd / |grdu|) groGrd does not lose accuracy against
+    the reference's three-step chain -- which forms grd |gro|^2-sized terms and cancels them -- measured against float64 on geometries with
+    |gro| in the hundreds (small Gaussians seen from a few units away), the regime of the C2 / C3 scenes."""
+    rng = np.random.default_rng(11)
+    f32 = np.float32
+    err_chain, err_closed = [], []
+    for _ in range(400):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        s = np.exp(rng.normal(size=3) * 0.5) * 0.01                      # scales around 0.01
+        mu = rng.normal(size=3) * 0.5
+        o = mu + 4.0 * (lambda v: v / np.linalg.norm(v))(rng.normal(size=3))   # 4 units away: |gro| ~ 400
+        aim = mu + s.max() * rng.normal(size=3)                          # the ray passes within ~1 sigma of the centre
+        d = (aim - o) / np.linalg.norm(aim - o)
+        gray_g = rng.normal()
+
+        def run(dt):
+            R = _rot(q).astype(dt)
+            go = (R @ (o - mu).astype(dt)) / s.astype(dt)
+            u = (R @ d.astype(dt)) / s.astype(dt)
+            il = dt(1) / np.sqrt(u @ u)
+            gd = u * il
+            cc = np.cross(gd, go)
+            k = dt(2) * cc * dt(gray_g)
+            gd_g = np.cross(go, k)
+            P = np.cross(k, gd)
+            chain = il * gd_g - il * il * il * u * (gd_g @ u)
+            closed = (-(gd @ go) * il) * P
+            return chain, closed
+
+        truth, truth2 = run(np.float64)
+        assert np.allclose(truth, truth2, rtol=1e-7, atol=1e-9 * np.abs(truth).max())
+        chain, closed = run(f32)
+        scale = np.abs(truth).max()
+        err_chain.append(np.abs(chain - truth).max() / scale)
+        err_closed.append(np.abs(closed - truth).max() / scale)
+    err_chain, err_closed = np.array(err_chain), np.array(err_closed)
+    print(f"[algebra] float32 relative error vs float64: chain median {np.median(err_chain):.2e} p99 {np.quantile(err_chain, 0.99):.2e}; "
+          f"closed form median {np.median(err_closed):.2e} p99 {np.quantile(err_closed, 0.99):.2e}")
+    assert np.median(err_closed) <= np.median(err_chain) * 1.05
+    assert np.quantile(err_closed, 0.99) <= np.quantile(err_chain, 0.99) * 1.05
